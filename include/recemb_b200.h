@@ -1,0 +1,232 @@
+/*
+ * recemb_b200.h -- C ABI of the B200 (sm_100a) embedding hot path.
+ *
+ * The reference (ranjanbalappa-nykaa/recommendations) is pure Python: it has no
+ * FFI of its own.  The boundary this library sits behind is the nn.Module
+ * surface of commons/layers.py and commons/transformers/layers.py; every entry
+ * point below names the reference call site whose ATen library call it
+ * replaces.  The Python host layer (recommendations_b200/*.py) binds these
+ * symbols with ctypes and keeps the reference constructors / forward /
+ * state_dict keys (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name
+ *     ends in _host; the library never allocates, frees or retains pointers.
+ *   - `device` / `stream` are explicit (backward runs on the autograd engine
+ *     thread, not the thread that ran forward); all work is asynchronous on
+ *     `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = RECEMB_OK, negative = error; recemb_last_error() gives
+ *     the thread-local message.  Nothing throws across the ABI.
+ *   - ids are signed 64-bit (xxh64 - 2^63, commons/feature_utils.py:40-46).
+ *   - tables are row-major [num_rows, dim], fp32 or bf16.
+ */
+#ifndef RECEMB_B200_H_
+#define RECEMB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECEMB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RECEMB_API __attribute__((visibility("default")))
+#else
+#define RECEMB_API
+#endif
+
+typedef void* recemb_stream_t; /* cudaStream_t */
+
+enum recemb_status {
+  RECEMB_OK = 0,
+  RECEMB_ERR_INVALID = -1,     /* bad argument */
+  RECEMB_ERR_CUDA = -2,        /* CUDA runtime error (see recemb_last_error) */
+  RECEMB_ERR_UNSUPPORTED = -3, /* shape / dtype not supported by the kernels */
+  RECEMB_ERR_WORKSPACE = -4    /* caller-provided workspace too small */
+};
+
+enum recemb_dtype { RECEMB_F32 = 0, RECEMB_BF16 = 1 };
+
+/* id -> row index transforms (all bit-exact restatements of the reference):
+ *   IDENTITY      row = id                                   (ids already rows)
+ *   FLOORMOD      row = floor_mod(id, num_rows)              commons/layers.py:57, :185 (col 0)
+ *   ROTL_FLOORMOD row = floor_mod((id << c) | (id >> (64-c)), num_rows), c = hash_arg
+ *                 wrapping <<, ARITHMETIC >> on signed int64  commons/layers.py:174-185
+ *   QR_QUOTIENT   d = hash_arg; x = floor_mod(id, d*d); row = floor_mod(floor(x / d), d)
+ *   QR_REMAINDER  d = hash_arg; x = floor_mod(id, d*d); row = floor_mod(x, d)
+ *                                                             commons/layers.py:115-119
+ */
+enum recemb_hash {
+  RECEMB_HASH_IDENTITY = 0,
+  RECEMB_HASH_FLOORMOD = 1,
+  RECEMB_HASH_ROTL_FLOORMOD = 2,
+  RECEMB_HASH_QR_QUOTIENT = 3,
+  RECEMB_HASH_QR_REMAINDER = 4
+};
+
+/* forward epilogues */
+enum recemb_epilogue {
+  RECEMB_EPI_NONE = 0,
+  RECEMB_EPI_L2NORM = 1,   /* x / max(||x||_2, 1e-12)   F.normalize, commons/layers.py:60,:121,:168 */
+  RECEMB_EPI_RSQRT_K = 2   /* x / sqrt(num_shifts)      commons/layers.py:170 */
+};
+
+/* pooled-bag modes (nn.EmbeddingBag(mode='sum') at commons/transformers/layers.py:457;
+ * mean / last_n are the build-defined variants named by BASELINE.json north_star) */
+enum recemb_pool { RECEMB_POOL_SUM = 0, RECEMB_POOL_MEAN = 1 };
+
+/* what recemb_bwd_apply does with the de-duplicated per-row gradient sums */
+enum recemb_update {
+  RECEMB_UPD_DENSE_GRAD = 0,      /* grad_weight[row] = sum (torch-compatible .grad; caller zero-fills) */
+  RECEMB_UPD_SGD = 1,             /* torch.optim.SGD, no momentum */
+  RECEMB_UPD_ADAGRAD = 2,         /* torch.optim.Adagrad element-wise (embedding_module_gen.py:97,:137) */
+  RECEMB_UPD_ROWWISE_ADAGRAD = 3, /* state[num_rows]: s += mean_d(g^2); w -= lr*g/(sqrt(s)+eps) */
+  RECEMB_UPD_ADAM = 4,            /* lazy (touched-rows) Adam, L2 weight decay folded into g */
+  RECEMB_UPD_ADAMW = 5            /* lazy AdamW (models/lthm/sequence/wrapper.py:265), decoupled decay */
+};
+
+typedef struct recemb_optim_params {
+  float lr;           /* already includes lr_decay / schedule: the host passes clr */
+  float eps;
+  float weight_decay;
+  float beta1;
+  float beta2;
+  float bias_correction1; /* 1 - beta1^step (host-computed) */
+  float bias_correction2; /* 1 - beta2^step */
+  float reserved;
+} recemb_optim_params;
+
+/* ---- library info -------------------------------------------------------- */
+RECEMB_API int recemb_abi_version(void);
+RECEMB_API const char* recemb_last_error(void);
+/* number of kernels this library has launched since load (process-wide, monotonic) */
+RECEMB_API uint64_t recemb_launch_count(void);
+
+/* ---- index hashing (a2) -------------------------------------------------- */
+/* rows_out[i] = transform(ids[i]).  Replaces KShiftEmbedding.get_row_idx
+ * (commons/layers.py:174-185) and the torch.remainder at :57 / :116-118. */
+RECEMB_API int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, int64_t num_rows,
+                     int64_t hash_arg, int64_t* rows_out, int device, recemb_stream_t stream);
+
+/* ---- forward: sequence gather (a1, a4, a6) -------------------------------- */
+/* out[i, :] = epilogue(table[transform(ids[i]), :]).  Replaces F.embedding at
+ * commons/layers.py:58 (FlatEmbedding.forward).  If zero_pad != 0, positions
+ * with ids[i] == pad_id are written as zeros without reading the table (the
+ * fused form of ProductTower's `ids == 0` mask, product_tower.py:47-59).
+ * If table2 != NULL the row table2[transform2(ids[i])] is added before the
+ * epilogue (QREmbedding: emb_q(q) + emb_r(r), commons/layers.py:115-123):
+ * hash_mode applies to `table` and hash_mode2 to `table2`, both with hash_arg.
+ * inv_norm_out (optional, fp32 [n]) receives 1/max(||x||,1e-12) for the L2NORM backward. */
+RECEMB_API int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2, int64_t num_rows2,
+                      int32_t dim, int dtype, const int64_t* ids, int64_t n, int hash_mode,
+                      int hash_mode2, int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
+                      void* out, float* inv_norm_out, int device, recemb_stream_t stream);
+
+/* ---- forward: fused k-shift bag (a3) -------------------------------------- */
+/* out[i, :] = epilogue( sum_{c=0}^{k-1} table[rotl_floormod(ids[i], c), :] ), fp32
+ * accumulation in the order c = 0, 1, ... (bit-exact pre-epilogue vs. the
+ * reference's chain of adds).  Replaces KShiftEmbedding.forward
+ * (commons/layers.py:152-172): 2k-1 launches -> 1.  inv_norm_out (optional,
+ * fp32 [n]) receives 1/max(||x||,eps) for the L2NORM backward. */
+RECEMB_API int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                      const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue, void* out,
+                      float* inv_norm_out, int device, recemb_stream_t stream);
+
+/* ---- forward: pooled multi-hot bag (a5, a11) ------------------------------ */
+/* ids [num_bags, bag_size]; out[b, :] = pool_{p in window(b)} w[b,p] * table[transform(ids[b,p]), :]
+ * window(b): all p with (lengths == NULL || p < lengths[b]) and, if last_n > 0,
+ * p >= lengths[b] - last_n; slots with ids == pad_id are skipped when zero_pad != 0
+ * (EmbeddingBag padding_idx semantics).  fp32 accumulation in slot order (the CPU
+ * EmbeddingBag sum order).  MEAN divides by the number of pooled slots (>=1).
+ * Replaces nn.EmbeddingBag(mode='sum') at commons/transformers/layers.py:457,:469.
+ * per_slot_weight (optional fp32 [num_bags, bag_size]) = per_sample_weights. */
+RECEMB_API int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                    const int64_t* ids, int64_t num_bags, int32_t bag_size, const int32_t* lengths,
+                    int32_t last_n, const float* per_slot_weight, int hash_mode, int64_t hash_arg,
+                    int pool_mode, int zero_pad, int64_t pad_id, void* out, int device,
+                    recemb_stream_t stream);
+
+/* ---- backward: plan = sort-based dedup (a8, K5/K6) ------------------------ */
+/* A plan turns the lookup slots of one forward call into (row, slot) pairs
+ * sorted by row (stable in slot): the input of the segmented reduction.
+ * Slot s in [0, n_ids * slots_per_id):
+ *   slots_per_id == 1 : row = transform(ids[s])                       (gather / pooled bag)
+ *   slots_per_id == k : row = rotl_floormod(ids[s / k], s % k)        (k-shift; hash_mode must be ROTL_FLOORMOD)
+ * A slot is dropped from the plan when: zero_pad && id == pad_id; row == pad_row
+ * (nn.Embedding padding_idx: that row never receives gradient, commons/layers.py:51);
+ * bag_size > 0 and the slot is outside its bag's window (lengths / last_n as in
+ * recemb_pool_fwd).
+ * The plan lives in caller memory of recemb_bwd_plan_bytes(n_slots, num_rows). */
+RECEMB_API size_t recemb_bwd_plan_bytes(int64_t n_slots, int64_t num_rows);
+
+RECEMB_API int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_per_id, int hash_mode,
+                    int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
+                    int64_t pad_row, int32_t bag_size, const int32_t* lengths, int32_t last_n,
+                    void* plan, size_t plan_bytes, int device, recemb_stream_t stream);
+
+/* Device-side views into a built plan (valid until the plan memory is reused). */
+RECEMB_API int recemb_plan_views(const void* plan, size_t plan_bytes, const uint32_t** sorted_rows,
+                      const uint32_t** sorted_slots, const int64_t** counters /* [0]=n_valid, [1]=n_unique */,
+                      int64_t* n_slots_host);
+
+/* ---- backward: segmented reduction + update (a8, a9, K5-K7) ---------------- */
+/* For every distinct row r in the plan: g = sum over its slots s (ascending) of
+ *     slot_weight[s] * grad_row_scale[s / slots_per_grad_row] * grad[s / slots_per_grad_row, :]
+ * (both scale arrays optional, fp32) accumulated in fp32, then `update` is
+ * applied to row r of `table` (and state1/state2).  Deterministic: fixed
+ * chunking, no atomics.  Workspace: recemb_bwd_apply_workspace_bytes().
+ *   DENSE_GRAD        table = grad_weight (dtype `dtype`), states unused
+ *   SGD               states unused
+ *   ADAGRAD           state1 = sum of squares, fp32 [num_rows, dim]
+ *   ROWWISE_ADAGRAD   state1 = fp32 [num_rows]
+ *   ADAM / ADAMW      state1 = exp_avg, state2 = exp_avg_sq, fp32 [num_rows, dim]
+ * Replaces autograd's embedding_dense_backward + torch.optim.*.step
+ * (embedding_module_gen.py:113-114, :152-153). */
+RECEMB_API size_t recemb_bwd_apply_workspace_bytes(int64_t n_slots, int32_t dim);
+
+RECEMB_API int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void* grad, int grad_dtype,
+                     int64_t grad_rows, int32_t dim, int32_t slots_per_grad_row,
+                     const float* slot_weight, const float* grad_row_scale, int update,
+                     void* table, int dtype, int64_t num_rows, void* state1, void* state2,
+                     const recemb_optim_params* hp_host, void* workspace, size_t workspace_bytes,
+                     int device, recemb_stream_t stream);
+
+/* ---- backward of the k-shift / pooled epilogues ---------------------------- */
+/* dx[i,:] for y = epilogue(x): L2NORM: (g - y (y.g)) * inv_norm[i]; RSQRT_K: g / sqrt(k).
+ * (autograd of commons/layers.py:167-170).  dx is fp32 [n, dim]. */
+RECEMB_API int recemb_epilogue_bwd(const void* grad_out, const void* out, int dtype, const float* inv_norm,
+                        int64_t n, int32_t dim, int epilogue, int32_t num_shifts, float* dx,
+                        int device, recemb_stream_t stream);
+
+/* ---- ranker pairwise dot interaction (a11) --------------------------------- */
+/* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:
+ * the strictly-lower triangle of feats[b] @ feats[b]^T, fp32 accumulation on the
+ * tcgen05 tensor cores (num_feats <= 32, dim % 64 == 0).  No reference code
+ * exists (models/ranker/fdlrm/ is empty): canonical DLRM interaction. */
+RECEMB_API int recemb_dot_interaction_fwd(const void* feats, int64_t batch, int32_t num_feats, int32_t dim,
+                               void* out, int device, recemb_stream_t stream);
+/* grad_feats[b] = (G + G^T) @ feats[b] with G the lower-triangular unpack of grad_out[b]. */
+RECEMB_API int recemb_dot_interaction_bwd(const void* feats, const void* grad_out, int64_t batch,
+                               int32_t num_feats, int32_t dim, void* grad_feats, int device,
+                               recemb_stream_t stream);
+
+/* ---- host-buffer entry points (end-to-end path) ---------------------------- */
+/* One fused training step of a FlatEmbedding-style table with HOST ids:
+ * H2D copy of ids_host (pinned or pageable) into ids_dev_scratch, forward gather
+ * into out, backward plan + fused update with grad (device, fp32/bf16 [n, dim]),
+ * then counters_host[0..1] = {n_valid, n_unique} are copied back (async on
+ * `stream`; the caller synchronises the stream before reading them). */
+RECEMB_API int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t* ids_dev_scratch,
+                          void* table, int64_t num_rows, int32_t dim, int dtype, void* out,
+                          const void* grad, int update, void* state1, void* state2,
+                          const recemb_optim_params* hp_host, void* plan, size_t plan_bytes,
+                          void* workspace, size_t workspace_bytes, int64_t* counters_host,
+                          int device, recemb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECEMB_B200_H_ */

@@ -1,0 +1,16 @@
+"""recommendations_b200: B200 (sm_100a) embedding hot path behind the reference's
+nn.Module API (commons/layers.py, commons/transformers/layers.py).
+
+The compute lives in recommendations_b200/lib/librecemb_b200.so (hand-written CUDA,
+C ABI in include/recemb_b200.h).  Importing the package does not need a GPU; calling
+any op does, and a missing library raises instead of falling back.
+"""
+from . import _native
+from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PooledEmbeddingBag,
+                     QREmbedding)
+from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
+
+__all__ = [
+    "CosineVectorEmbedding", "EmbeddingTable", "FlatEmbedding", "FusedEmbeddingOptimizer",
+    "FusedOptimizerConfig", "KShiftEmbedding", "PooledEmbeddingBag", "QREmbedding",
+]

@@ -1,0 +1,152 @@
+"""ctypes binding of include/recemb_b200.h (librecemb_b200.so).
+
+This is the only place that touches the C ABI.  There is no CPU fallback: if
+the library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "librecemb_b200.so"
+
+# enums (mirror include/recemb_b200.h)
+F32, BF16 = 0, 1
+HASH_IDENTITY, HASH_FLOORMOD, HASH_ROTL_FLOORMOD, HASH_QR_QUOTIENT, HASH_QR_REMAINDER = range(5)
+EPI_NONE, EPI_L2NORM, EPI_RSQRT_K = range(3)
+POOL_SUM, POOL_MEAN = 0, 1
+UPD_DENSE_GRAD, UPD_SGD, UPD_ADAGRAD, UPD_ROWWISE_ADAGRAD, UPD_ADAM, UPD_ADAMW = range(6)
+
+UPDATE_BY_NAME = {
+    "dense_grad": UPD_DENSE_GRAD,
+    "sgd": UPD_SGD,
+    "adagrad": UPD_ADAGRAD,
+    "rowwise_adagrad": UPD_ROWWISE_ADAGRAD,
+    "adam": UPD_ADAM,
+    "adamw": UPD_ADAMW,
+}
+
+
+class OptimParams(C.Structure):
+    _fields_ = [
+        ("lr", C.c_float),
+        ("eps", C.c_float),
+        ("weight_decay", C.c_float),
+        ("beta1", C.c_float),
+        ("beta2", C.c_float),
+        ("bias_correction1", C.c_float),
+        ("bias_correction2", C.c_float),
+        ("reserved", C.c_float),
+    ]
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_P, _I64, _I32, _INT, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/recemb_b200.h declares
+SIGNATURES = {
+    "recemb_abi_version": (_INT, []),
+    "recemb_last_error": (C.c_char_p, []),
+    "recemb_launch_count": (C.c_uint64, []),
+    "recemb_row_index": (_INT, [_P, _I64, _INT, _I64, _I64, _P, _INT, _P]),
+    "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, _INT, _INT, _I64, _INT,
+                                 _INT, _I64, _P, _P, _INT, _P]),
+    "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _P, _P, _INT, _P]),
+    "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,
+                               _INT, _I64, _P, _INT, _P]),
+    "recemb_bwd_plan_bytes": (_SZ, [_I64, _I64]),
+    "recemb_bwd_plan": (_INT, [_P, _I64, _I32, _INT, _I64, _I64, _INT, _I64, _I64, _I32, _P, _I32,
+                               _P, _SZ, _INT, _P]),
+    "recemb_plan_views": (_INT, [_P, _SZ, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                 C.POINTER(_I64)]),
+    "recemb_bwd_apply_workspace_bytes": (_SZ, [_I64, _I32]),
+    "recemb_bwd_apply": (_INT, [_P, _SZ, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
+                                _P, _P, C.POINTER(OptimParams), _P, _SZ, _INT, _P]),
+    "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
+    "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
+    "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
+    "recemb_flat_step_host": (_INT, [_P, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
+                                     C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _INT, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and type every entry point.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing: build it with `python -m recommendations_b200.build_native` "
+                "(there is no CPU / PyTorch fallback for the embedding hot path)")
+        lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_LOCAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.recemb_abi_version() != 1:
+            raise NativeError("librecemb_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().recemb_last_error().decode(errors="replace")
+        raise NativeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().recemb_launch_count())
+
+
+# ------------------------------------------------------------------ helpers ----
+def dtype_code(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return F32
+    if t == torch.bfloat16:
+        return BF16
+    raise NativeError(f"unsupported table dtype {t}: the kernels take float32 or bfloat16")
+
+
+def require_cuda(*tensors: torch.Tensor) -> int:
+    """All tensors must live on one CUDA device and be contiguous; returns the device index."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NativeError(
+                "recommendations_b200 runs on CUDA (sm_100a) only: got a tensor on "
+                f"{t.device}; there is no CPU fallback")
+        if not t.is_contiguous():
+            raise NativeError("non-contiguous tensor passed to the native layer")
+        if dev is None:
+            dev = t.device.index
+        elif dev != t.device.index:
+            raise NativeError("tensors on different CUDA devices")
+    return 0 if dev is None else int(dev)
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: int) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

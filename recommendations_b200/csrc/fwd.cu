@@ -1,0 +1,680 @@
+// Forward kernels of the embedding hot path (sm_100a):
+//   row_index_kernel  - id -> row hashing                     (a2; commons/layers.py:174-185)
+//   gather_kernel     - sequence gather, optional 2nd table   (a1, a4, a6; commons/layers.py:56-61, :115-123)
+//   kshift_kernel     - fused k-shift bag                     (a3; commons/layers.py:152-172)
+//   pool_kernel       - pooled multi-hot bag sum/mean/last-N  (a5, a11; commons/transformers/layers.py:457-469)
+//
+// All of them are HBM-bound byte movers: a row is moved as 16-byte vectors by a
+// group of G consecutive lanes (G*V vectors per row), id tiles are staged into
+// shared memory by the TMA engine's 1-D bulk copy (cp.async.bulk -> UBLKCP)
+// double-buffered against the gather, table rows are read with
+// ld.global.nc.L1::no_allocate and write-once outputs leave with st.global.cs.
+#include "common.cuh"
+
+namespace recemb {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTileIds = 1024;  // ids per staged tile (8 KB)
+
+// ------------------------------------------------------------ id staging ----
+// Double-buffered id tiles.  Thread 0 issues the bulk copy of the NEXT tile
+// while the CTA gathers the current one.  If the id pointer is not 16-byte
+// aligned the CTA falls back to cooperative plain loads (same results).
+struct IdStager {
+  int64_t* buf[2];
+  uint64_t* bar;  // [2]
+  uint32_t phase[2];
+  bool bulk;
+
+  __device__ __forceinline__ void init(int64_t* b0, int64_t* b1, uint64_t* bars, bool use_bulk) {
+    buf[0] = b0;
+    buf[1] = b1;
+    bar = bars;
+    phase[0] = phase[1] = 0;
+    bulk = use_bulk;
+    if (bulk && threadIdx.x == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // thread 0 only (bulk mode); `count` ids starting at `src`
+  __device__ __forceinline__ void issue(int b, const int64_t* src, int count) {
+    if (!bulk || threadIdx.x != 0) return;
+    fence_proxy_async();  // earlier generic-proxy accesses to buf[b] are ordered before the async write
+    const int even = count & ~1;
+    if (count & 1) buf[b][count - 1] = src[count - 1];
+    mbar_expect_tx(&bar[b], (uint32_t)even * 8u);
+    if (even) bulk_g2s(buf[b], src, (uint32_t)even * 8u, &bar[b]);
+  }
+  // all threads
+  __device__ __forceinline__ void acquire(int b, const int64_t* src, int count) {
+    if (bulk) {
+      mbar_wait(&bar[b], phase[b]);
+      phase[b] ^= 1;
+    } else {
+      for (int i = threadIdx.x; i < count; i += kThreads) buf[b][i] = src[i];
+      __syncthreads();
+    }
+  }
+};
+
+// ------------------------------------------------------------- row index ----
+__global__ void __launch_bounds__(kThreads) row_index_kernel(const int64_t* __restrict__ ids,
+                                                             int64_t n, HashSpec h,
+                                                             int64_t* __restrict__ rows) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (; i < n; i += stride) rows[i] = row_of(ids[i], h);
+}
+
+// ----------------------------------------------------------------- gather ----
+struct GatherArgs {
+  const uint4* table;
+  const uint4* table2;
+  const int64_t* ids;
+  uint4* out;
+  float* inv_norm;
+  int64_t n;
+  int32_t row_vecs;
+  HashSpec h1, h2;
+  int zero_pad;
+  int64_t pad_id;
+  int bulk_ok;
+};
+
+template <int G, int V, typename T, int EPI, bool TWO>
+__global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
+  constexpr int RPW = 32 / G;                  // rows per warp pass
+  constexpr int UNROLL = (V >= 4) ? 2 : (V == 2 ? 2 : 4);
+  constexpr int E = Vec16<T>::kElems;
+  __shared__ alignas(16) int64_t s_ids[2][kTileIds];
+  __shared__ alignas(16) int64_t s_rows2[TWO ? kTileIds : 1];
+  __shared__ alignas(8) uint64_t s_bar[2];
+
+  const int64_t num_tiles = (a.n + kTileIds - 1) / kTileIds;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lig = lane % G, gi = lane / G;
+
+  IdStager st;
+  st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
+
+  int64_t tile = blockIdx.x;
+  int b = 0;
+  auto tile_count = [&](int64_t t) { return (int)min((int64_t)kTileIds, a.n - t * kTileIds); };
+  if (tile < num_tiles) st.issue(0, a.ids + tile * kTileIds, tile_count(tile));
+
+  for (; tile < num_tiles; tile += gridDim.x, b ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < num_tiles) st.issue(b ^ 1, a.ids + next * kTileIds, tile_count(next));
+    const int cnt = tile_count(tile);
+    st.acquire(b, a.ids + tile * kTileIds, cnt);
+
+    // hash in place: s_ids[b][i] <- row (or -1 for a zero-filled pad position)
+    int64_t* rows = s_ids[b];
+    for (int i = threadIdx.x; i < cnt; i += kThreads) {
+      const int64_t id = rows[i];
+      const bool pad = a.zero_pad && id == a.pad_id;
+      if (TWO) s_rows2[i] = pad ? -1 : row_of(id, a.h2);
+      rows[i] = pad ? -1 : row_of(id, a.h1);
+    }
+    __syncthreads();
+
+    uint4* out_tile = a.out + tile * kTileIds * (int64_t)a.row_vecs;
+    for (int base = warp * RPW; base < cnt; base += kWarps * RPW * UNROLL) {
+      uint4 v[UNROLL][V];
+      uint4 w[TWO ? UNROLL : 1][TWO ? V : 1];
+      int l[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        l[u] = base + u * kWarps * RPW + gi;
+        const int64_t r = (l[u] < cnt) ? rows[l[u]] : -1;
+        const int64_t r2 = (TWO && l[u] < cnt) ? s_rows2[l[u]] : -1;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int vec = j * G + lig;
+          v[u][j] = make_uint4(0, 0, 0, 0);
+          if (r >= 0 && vec < a.row_vecs) v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+          if (TWO) {
+            w[u][j] = make_uint4(0, 0, 0, 0);
+            if (r2 >= 0 && vec < a.row_vecs) w[u][j] = ldg_nc_v4(a.table2 + r2 * a.row_vecs + vec);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (TWO || EPI == RECEMB_EPI_L2NORM) {
+          float f[V][E];
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            Vec16<T>::unpack(v[u][j], f[j]);
+            if (TWO) {
+              float g[E];
+              Vec16<T>::unpack(w[u][j], g);
+#pragma unroll
+              for (int e = 0; e < E; ++e) f[j][e] += g[e];
+              if (sizeof(T) == 2) {  // the reference add rounds to the table dtype
+                uint4 t = Vec16<T>::pack(f[j]);
+                Vec16<T>::unpack(t, f[j]);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) ss += f[j][e] * f[j][e];
+          }
+          if (EPI == RECEMB_EPI_L2NORM) {
+            ss = group_sum<G>(ss);
+            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+#pragma unroll
+              for (int e = 0; e < E; ++e) f[j][e] = f[j][e] / denom;
+            if (a.inv_norm && l[u] < cnt && lig == 0)
+              a.inv_norm[tile * kTileIds + l[u]] = 1.f / denom;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[u][j] = Vec16<T>::pack(f[j]);
+        }
+        if (l[u] < cnt) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const int vec = j * G + lig;
+            if (vec < a.row_vecs) stg_cs_v4(out_tile + (int64_t)l[u] * a.row_vecs + vec, v[u][j]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // tile fully consumed before its buffer is refilled
+  }
+}
+
+// ------------------------------------------------------------ k-shift bag ----
+struct KShiftArgs {
+  const uint4* table;
+  const int64_t* ids;
+  uint4* out;
+  float* inv_norm;
+  int64_t n;
+  int32_t row_vecs;
+  int32_t k;
+  ModN mod_rows;
+  int epilogue;
+  float sqrt_k;
+  int bulk_ok;
+};
+
+template <int G, int V, typename T>
+__global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
+  constexpr int RPW = 32 / G;
+  constexpr int E = Vec16<T>::kElems;
+  constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);  // row loads in flight per lane
+  __shared__ alignas(16) int64_t s_ids[2][kTileIds];
+  __shared__ alignas(8) uint64_t s_bar[2];
+
+  const int64_t num_tiles = (a.n + kTileIds - 1) / kTileIds;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lig = lane % G, gi = lane / G;
+
+  IdStager st;
+  st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
+  int64_t tile = blockIdx.x;
+  int b = 0;
+  auto tile_count = [&](int64_t t) { return (int)min((int64_t)kTileIds, a.n - t * kTileIds); };
+  if (tile < num_tiles) st.issue(0, a.ids + tile * kTileIds, tile_count(tile));
+
+  for (; tile < num_tiles; tile += gridDim.x, b ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < num_tiles) st.issue(b ^ 1, a.ids + next * kTileIds, tile_count(next));
+    const int cnt = tile_count(tile);
+    st.acquire(b, a.ids + tile * kTileIds, cnt);
+    if (!a.bulk_ok) {
+    }  // acquire() already synchronised
+    const int64_t* ids = s_ids[b];
+
+    for (int base = warp * RPW; base < cnt; base += kWarps * RPW) {
+      const int l = base + gi;
+      const bool live = l < cnt;
+      const int64_t id = live ? ids[l] : 0;
+      float acc[V][E];
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[j][e] = 0.f;
+
+      // shifts are hashed G at a time (lane `lig` hashes shift c0+lig) and
+      // broadcast inside the group; rows are then loaded BATCH at a time and
+      // added in the order c = 0, 1, ... (the reference's order of adds).
+      for (int c0 = 0; c0 < a.k; c0 += G) {
+        const int my_c = c0 + lig;
+        const int64_t my_row = (my_c < a.k) ? kshift_row(id, my_c, a.mod_rows) : 0;
+        const int span = min(G, a.k - c0);
+        for (int cb = 0; cb < span; cb += BATCH) {
+          uint4 v[BATCH][V];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int cc = cb + u;
+            const int64_t r = __shfl_sync(0xffffffffu, my_row, gi * G + (cc < G ? cc : 0));
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const int vec = j * G + lig;
+              v[u][j] = make_uint4(0, 0, 0, 0);
+              if (live && cc < span && vec < a.row_vecs)
+                v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            if (cb + u < span) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                float f[E];
+                Vec16<T>::unpack(v[u][j], f);
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[j][e] += f[e];
+              }
+            }
+          }
+        }
+      }
+
+      if (a.epilogue == RECEMB_EPI_L2NORM) {
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int e = 0; e < E; ++e) ss += acc[j][e] * acc[j][e];
+        ss = group_sum<G>(ss);
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / denom;
+        if (a.inv_norm && live && lig == 0) a.inv_norm[tile * kTileIds + l] = 1.f / denom;
+      } else if (a.epilogue == RECEMB_EPI_RSQRT_K) {
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / a.sqrt_k;
+      }
+      if (live) {
+        uint4* dst = a.out + (tile * kTileIds + l) * (int64_t)a.row_vecs;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int vec = j * G + lig;
+          if (vec < a.row_vecs) stg_cs_v4(dst + vec, Vec16<T>::pack(acc[j]));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------- pooled bag ----
+struct PoolArgs {
+  const uint4* table;
+  const int64_t* ids;
+  const int32_t* lengths;
+  const float* slot_weight;
+  uint4* out;
+  int64_t num_bags;
+  int32_t bag_size;
+  int32_t last_n;
+  int32_t row_vecs;
+  int32_t bags_per_tile;
+  HashSpec h;
+  int pool_mode;
+  int zero_pad;
+  int64_t pad_id;
+  int bulk_ok;
+};
+
+constexpr int kPoolTileIds = 2048;
+
+template <int G, int V, typename T>
+__global__ void __launch_bounds__(kThreads) pool_kernel(const PoolArgs a) {
+  constexpr int RPW = 32 / G;
+  constexpr int E = Vec16<T>::kElems;
+  constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);
+  __shared__ alignas(16) int64_t s_ids[2][kPoolTileIds];
+  __shared__ alignas(8) uint64_t s_bar[2];
+
+  const int64_t num_tiles = (a.num_bags + a.bags_per_tile - 1) / a.bags_per_tile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lig = lane % G, gi = lane / G;
+  const int P = a.bag_size;
+
+  IdStager st;
+  st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
+  int64_t tile = blockIdx.x;
+  int b = 0;
+  auto tile_bags = [&](int64_t t) {
+    return (int)min((int64_t)a.bags_per_tile, a.num_bags - t * a.bags_per_tile);
+  };
+  if (tile < num_tiles)
+    st.issue(0, a.ids + tile * a.bags_per_tile * (int64_t)P, tile_bags(tile) * P);
+
+  for (; tile < num_tiles; tile += gridDim.x, b ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < num_tiles)
+      st.issue(b ^ 1, a.ids + next * a.bags_per_tile * (int64_t)P, tile_bags(next) * P);
+    const int nb = tile_bags(tile);
+    st.acquire(b, a.ids + tile * a.bags_per_tile * (int64_t)P, nb * P);
+    const int64_t* ids = s_ids[b];
+
+    for (int base = warp * RPW; base < nb; base += kWarps * RPW) {
+      const int lb = base + gi;  // bag inside the tile
+      const bool live = lb < nb;
+      const int64_t bag = tile * a.bags_per_tile + lb;
+      int hi = P, lo = 0;
+      if (live && a.lengths) hi = min(max(a.lengths[bag], 0), P);
+      if (a.last_n > 0) lo = max(0, hi - a.last_n);
+      if (!live) hi = lo = 0;
+      // the two groups of a warp may have different windows: iterate to the warp max
+      int span = hi - lo;
+#pragma unroll
+      for (int o = 16; o >= G && o > 0; o >>= 1) span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
+
+      float acc[V][E];
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[j][e] = 0.f;
+      int pooled = 0;
+
+      for (int p0 = 0; p0 < span; p0 += G) {
+        // lane `lig` hashes slot lo+p0+lig
+        const int my_p = lo + p0 + lig;
+        const bool my_ok = live && my_p < hi;
+        const int64_t my_id = my_ok ? ids[lb * P + my_p] : 0;
+        const bool my_use = my_ok && !(a.zero_pad && my_id == a.pad_id);
+        const int64_t my_row = my_use ? row_of(my_id, a.h) : -1;
+        float my_w = 1.f;
+        if (my_use && a.slot_weight) my_w = a.slot_weight[bag * P + my_p];
+        const int sub = min(G, span - p0);
+        for (int cb = 0; cb < sub; cb += BATCH) {
+          uint4 v[BATCH][V];
+          float wt[BATCH];
+          bool use[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int cc = cb + u;
+            const int src = gi * G + (cc < G ? cc : 0);
+            const int64_t r = __shfl_sync(0xffffffffu, my_row, src);
+            wt[u] = __shfl_sync(0xffffffffu, my_w, src);
+            use[u] = (cc < sub) && r >= 0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const int vec = j * G + lig;
+              v[u][j] = make_uint4(0, 0, 0, 0);
+              if (use[u] && vec < a.row_vecs) v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            if (use[u]) {
+              ++pooled;
+#pragma unroll
+              for (int j = 0; j < V; ++j) {
+                float f[E];
+                Vec16<T>::unpack(v[u][j], f);
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[j][e] += wt[u] * f[e];
+              }
+            }
+          }
+        }
+      }
+      if (a.pool_mode == RECEMB_POOL_MEAN && pooled > 0) {
+        const float cntf = (float)pooled;
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / cntf;
+      }
+      if (live) {
+        uint4* dst = a.out + bag * (int64_t)a.row_vecs;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int vec = j * G + lig;
+          if (vec < a.row_vecs) stg_cs_v4(dst + vec, Vec16<T>::pack(acc[j]));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------- dispatch ----
+// rows of row_vecs 16-byte vectors are moved by G lanes x V vectors
+struct RowShape {
+  int G, V;
+};
+static bool pick_shape(int row_vecs, RowShape* s) {
+  int g = 1;
+  while (g < 32 && g < row_vecs) g <<= 1;
+  int v = (row_vecs + g - 1) / g;
+  int vp = 1;
+  while (vp < v) vp <<= 1;
+  if (vp > 8) return false;
+  s->G = g;
+  s->V = vp;
+  return true;
+}
+
+static int grid_for(int device, int64_t tiles, int ctas_per_sm) {
+  int64_t g = (int64_t)sm_count(device) * ctas_per_sm;
+  if (tiles < g) g = tiles;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define DISPATCH_GV(G_, V_, ...)                                         \
+  if (shape.G == G_ && shape.V == V_) {                                  \
+    constexpr int G = G_;                                                \
+    constexpr int V = V_;                                                \
+    __VA_ARGS__;                                                         \
+    launched = true;                                                     \
+  }
+#define DISPATCH_SHAPES(...)       \
+  DISPATCH_GV(1, 1, __VA_ARGS__)   \
+  DISPATCH_GV(2, 1, __VA_ARGS__)   \
+  DISPATCH_GV(4, 1, __VA_ARGS__)   \
+  DISPATCH_GV(8, 1, __VA_ARGS__)   \
+  DISPATCH_GV(16, 1, __VA_ARGS__)  \
+  DISPATCH_GV(32, 1, __VA_ARGS__)  \
+  DISPATCH_GV(32, 2, __VA_ARGS__)  \
+  DISPATCH_GV(32, 4, __VA_ARGS__)  \
+  DISPATCH_GV(32, 8, __VA_ARGS__)
+
+template <typename T>
+static int launch_gather(const GatherArgs& a, RowShape shape, int epilogue, bool two, int grid,
+                         cudaStream_t s) {
+  bool launched = false;
+  if (!two && epilogue == RECEMB_EPI_NONE) {
+    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_NONE, false><<<grid, kThreads, 0, s>>>(a)))
+  } else if (!two) {
+    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_L2NORM, false><<<grid, kThreads, 0, s>>>(a)))
+  } else if (epilogue == RECEMB_EPI_NONE) {
+    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_NONE, true><<<grid, kThreads, 0, s>>>(a)))
+  } else {
+    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_L2NORM, true><<<grid, kThreads, 0, s>>>(a)))
+  }
+  if (!launched) {
+    set_error("gather: no kernel for G=%d V=%d", shape.G, shape.V);
+    return RECEMB_ERR_UNSUPPORTED;
+  }
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+template <typename T>
+static int launch_kshift(const KShiftArgs& a, RowShape shape, int grid, cudaStream_t s) {
+  bool launched = false;
+  DISPATCH_SHAPES((kshift_kernel<G, V, T><<<grid, kThreads, 0, s>>>(a)))
+  if (!launched) {
+    set_error("kshift: no kernel for G=%d V=%d", shape.G, shape.V);
+    return RECEMB_ERR_UNSUPPORTED;
+  }
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+template <typename T>
+static int launch_pool(const PoolArgs& a, RowShape shape, int grid, cudaStream_t s) {
+  bool launched = false;
+  DISPATCH_SHAPES((pool_kernel<G, V, T><<<grid, kThreads, 0, s>>>(a)))
+  if (!launched) {
+    set_error("pool: no kernel for G=%d V=%d", shape.G, shape.V);
+    return RECEMB_ERR_UNSUPPORTED;
+  }
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+static int row_vecs_of(int32_t dim, int dtype, int* row_vecs) {
+  RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "dtype %d unknown", dtype);
+  const int64_t bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED(dim > 0 && bytes % 16 == 0,
+                     "row of %d elements (%lld bytes) is not a multiple of 16 bytes", dim,
+                     (long long)bytes);
+  *row_vecs = (int)(bytes / 16);
+  return RECEMB_OK;
+}
+
+}  // namespace recemb
+
+using namespace recemb;
+
+extern "C" int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, int64_t num_rows,
+                                int64_t hash_arg, int64_t* rows_out, int device,
+                                recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(ids && rows_out, "null pointer");
+  HashSpec h;
+  int rc = make_hash_spec(hash_mode, num_rows, hash_arg, &h);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  const int grid = grid_for(device, (n + kThreads - 1) / kThreads, 8);
+  row_index_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(ids, n, h, rows_out);
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2,
+                                 int64_t num_rows2, int32_t dim, int dtype, const int64_t* ids,
+                                 int64_t n, int hash_mode, int hash_mode2, int64_t hash_arg,
+                                 int epilogue, int zero_pad, int64_t pad_id, void* out,
+                                 float* inv_norm_out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(table && ids && out, "null pointer");
+  RECEMB_CHECK_ARG(epilogue == RECEMB_EPI_NONE || epilogue == RECEMB_EPI_L2NORM,
+                   "gather epilogue must be NONE or L2NORM");
+  RECEMB_CHECK_ARG(((uintptr_t)table | (uintptr_t)out | (uintptr_t)table2) % 16 == 0,
+                   "table/out must be 16-byte aligned");
+  GatherArgs a;
+  int rc = row_vecs_of(dim, dtype, &a.row_vecs);
+  if (rc) return rc;
+  RowShape shape;
+  RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
+  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1);
+  if (rc) return rc;
+  a.h2 = a.h1;
+  if (table2) {
+    rc = make_hash_spec(hash_mode2, num_rows2, hash_arg, &a.h2);
+    if (rc) return rc;
+  }
+  a.table = (const uint4*)table;
+  a.table2 = (const uint4*)table2;
+  a.ids = ids;
+  a.out = (uint4*)out;
+  a.inv_norm = inv_norm_out;
+  a.n = n;
+  a.zero_pad = zero_pad;
+  a.pad_id = pad_id;
+  a.bulk_ok = ((uintptr_t)ids % 16 == 0);
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  const int grid = grid_for(device, (n + kTileIds - 1) / kTileIds, 8);
+  if (dtype == RECEMB_F32)
+    return launch_gather<float>(a, shape, epilogue, table2 != nullptr, grid, (cudaStream_t)stream);
+  return launch_gather<__nv_bfloat16>(a, shape, epilogue, table2 != nullptr, grid,
+                                      (cudaStream_t)stream);
+}
+
+extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                                 const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue,
+                                 void* out, float* inv_norm_out, int device,
+                                 recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(table && ids && out, "null pointer");
+  RECEMB_CHECK_ARG(num_shifts >= 1 && num_shifts <= 63, "num_shifts %d out of [1, 63]", num_shifts);
+  RECEMB_CHECK_ARG(num_rows >= 1, "num_rows < 1");
+  RECEMB_CHECK_ARG(((uintptr_t)table | (uintptr_t)out) % 16 == 0, "table/out must be 16-byte aligned");
+  KShiftArgs a;
+  int rc = row_vecs_of(dim, dtype, &a.row_vecs);
+  if (rc) return rc;
+  RowShape shape;
+  RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
+  a.table = (const uint4*)table;
+  a.ids = ids;
+  a.out = (uint4*)out;
+  a.inv_norm = inv_norm_out;
+  a.n = n;
+  a.k = num_shifts;
+  a.mod_rows = make_modn((uint64_t)num_rows);
+  a.epilogue = epilogue;
+  a.sqrt_k = (float)sqrt((double)num_shifts);
+  a.bulk_ok = ((uintptr_t)ids % 16 == 0);
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  const int grid = grid_for(device, (n + kTileIds - 1) / kTileIds, 6);
+  if (dtype == RECEMB_F32) return launch_kshift<float>(a, shape, grid, (cudaStream_t)stream);
+  return launch_kshift<__nv_bfloat16>(a, shape, grid, (cudaStream_t)stream);
+}
+
+extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                               const int64_t* ids, int64_t num_bags, int32_t bag_size,
+                               const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
+                               int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad,
+                               int64_t pad_id, void* out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(num_bags >= 0, "num_bags < 0");
+  if (num_bags == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(table && ids && out, "null pointer");
+  RECEMB_CHECK_ARG(bag_size >= 1, "bag_size < 1");
+  RECEMB_UNSUPPORTED(bag_size <= kPoolTileIds, "bag_size %d > %d", bag_size, kPoolTileIds);
+  RECEMB_CHECK_ARG(pool_mode == RECEMB_POOL_SUM || pool_mode == RECEMB_POOL_MEAN, "bad pool_mode");
+  RECEMB_CHECK_ARG(((uintptr_t)table | (uintptr_t)out) % 16 == 0, "table/out must be 16-byte aligned");
+  PoolArgs a;
+  int rc = row_vecs_of(dim, dtype, &a.row_vecs);
+  if (rc) return rc;
+  RowShape shape;
+  RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
+  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h);
+  if (rc) return rc;
+  a.table = (const uint4*)table;
+  a.ids = ids;
+  a.lengths = lengths;
+  a.slot_weight = per_slot_weight;
+  a.out = (uint4*)out;
+  a.num_bags = num_bags;
+  a.bag_size = bag_size;
+  a.last_n = last_n;
+  a.bags_per_tile = kPoolTileIds / bag_size;
+  a.pool_mode = pool_mode;
+  a.zero_pad = zero_pad;
+  a.pad_id = pad_id;
+  // every tile start must be 16-byte aligned and every tile an even id count
+  a.bulk_ok = ((uintptr_t)ids % 16 == 0) && (((int64_t)a.bags_per_tile * bag_size) % 2 == 0);
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  const int64_t tiles = (num_bags + a.bags_per_tile - 1) / a.bags_per_tile;
+  const int grid = grid_for(device, tiles, 4);
+  if (dtype == RECEMB_F32) return launch_pool<float>(a, shape, grid, (cudaStream_t)stream);
+  return launch_pool<__nv_bfloat16>(a, shape, grid, (cudaStream_t)stream);
+}

@@ -1,0 +1,104 @@
+// Library-level plumbing of recemb_b200: error text, launch counter, hash-spec
+// construction, and the host-buffer end-to-end entry point.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace recemb {
+
+static thread_local char t_error[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count(int device) {
+  static std::mutex mu;
+  static int cached[64];
+  if (device < 0 || device >= 64) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0)
+      v = 148;
+    cached[device] = v;
+  }
+  return cached[device];
+}
+
+int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out) {
+  HashSpec h;
+  h.mode = hash_mode;
+  h.shift = 0;
+  h.mod_rows = make_modn(1);
+  h.mod_sq = make_modn(1);
+  switch (hash_mode) {
+    case RECEMB_HASH_IDENTITY:
+      break;
+    case RECEMB_HASH_FLOORMOD:
+      RECEMB_CHECK_ARG(num_rows >= 1, "FLOORMOD needs num_rows >= 1");
+      h.mod_rows = make_modn((uint64_t)num_rows);
+      break;
+    case RECEMB_HASH_ROTL_FLOORMOD:
+      RECEMB_CHECK_ARG(num_rows >= 1, "ROTL_FLOORMOD needs num_rows >= 1");
+      RECEMB_CHECK_ARG(hash_arg >= 0 && hash_arg <= 63, "rotation %lld out of [0, 63]",
+                       (long long)hash_arg);
+      h.shift = (int)hash_arg;
+      h.mod_rows = make_modn((uint64_t)num_rows);
+      break;
+    case RECEMB_HASH_QR_QUOTIENT:
+    case RECEMB_HASH_QR_REMAINDER:
+      RECEMB_CHECK_ARG(hash_arg >= 1 && hash_arg < (1ll << 31), "QR divisor %lld out of range",
+                       (long long)hash_arg);
+      h.mod_rows = make_modn((uint64_t)hash_arg);
+      h.mod_sq = make_modn((uint64_t)hash_arg * (uint64_t)hash_arg);
+      break;
+    default:
+      set_error("unknown hash mode %d", hash_mode);
+      return RECEMB_ERR_INVALID;
+  }
+  *out = h;
+  return RECEMB_OK;
+}
+
+}  // namespace recemb
+
+using namespace recemb;
+
+extern "C" int recemb_abi_version(void) { return RECEMB_ABI_VERSION; }
+extern "C" const char* recemb_last_error(void) { return t_error; }
+extern "C" uint64_t recemb_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t* ids_dev_scratch,
+                                     void* table, int64_t num_rows, int32_t dim, int dtype,
+                                     void* out, const void* grad, int update, void* state1,
+                                     void* state2, const recemb_optim_params* hp_host, void* plan,
+                                     size_t plan_bytes, void* workspace, size_t workspace_bytes,
+                                     int64_t* counters_host, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(ids_host && ids_dev_scratch, "null ids");
+  RECEMB_CHECK_ARG(n >= 0, "n < 0");
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n > 0)
+    RECEMB_CUDA(cudaMemcpyAsync(ids_dev_scratch, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
+                             RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
+                             stream);
+  if (rc) return rc;
+  rc = recemb_bwd_plan(ids_dev_scratch, n, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0, 0, -1, 0,
+                       nullptr, 0, plan, plan_bytes, device, stream);
+  if (rc) return rc;
+  rc = recemb_bwd_apply(plan, plan_bytes, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
+                        dtype, num_rows, state1, state2, hp_host, workspace, workspace_bytes, device,
+                        stream);
+  if (rc) return rc;
+  if (counters_host)
+    RECEMB_CUDA(cudaMemcpyAsync(counters_host, plan, 16, cudaMemcpyDeviceToHost, s));
+  return RECEMB_OK;
+}

@@ -1,0 +1,292 @@
+"""B200 drop-ins for the reference's embedding modules.
+
+Same constructors, forward signatures and state_dict keys as
+commons/layers.py (FlatEmbedding :44-61, KShiftEmbedding :125-185, QREmbedding
+:102-123) and commons/transformers/layers.py (CosineVectorEmbedding :443-471),
+with every lookup / pooling / backward / optimizer step running in the
+hand-written sm_100a kernels behind include/recemb_b200.h.  Keyword-only
+extras (dtype, device, fused optimizer) extend, never change, the reference
+signatures.  CUDA only: a CPU tensor raises (no fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as N
+from . import ops
+from .table import EmbeddingTable, FusedOptimizerConfig
+
+
+# ---------------------------------------------------------- autograd glue ----
+class _GatherFn(torch.autograd.Function):
+    """out = epilogue(table[h(ids)] (+ table2[h2(ids)])); backward = plan + segmented reduce."""
+
+    @staticmethod
+    def forward(ctx, anchor, anchor2, ids, holder, holder2, hash_mode, hash_mode2, hash_arg,
+                epilogue, zero_pad, pad_id):
+        need_grad = anchor.requires_grad or (anchor2 is not None and anchor2.requires_grad)
+        out, inv = ops.gather_fwd(
+            holder.weight.detach(), ids, hash_mode=hash_mode, hash_arg=hash_arg,
+            table2=None if holder2 is None else holder2.weight.detach(), hash_mode2=hash_mode2,
+            epilogue=epilogue, zero_pad=zero_pad, pad_id=pad_id, want_inv_norm=need_grad)
+        ctx.holder, ctx.holder2 = holder, holder2
+        ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
+        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, inv, out = ctx.saved_tensors
+        hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id = ctx.cfg
+        dim = grad_out.shape[-1]
+        g = grad_out.contiguous().view(-1, dim)
+        if epilogue == N.EPI_L2NORM:
+            g = ops.epilogue_bwd(g, out, inv, N.EPI_L2NORM)
+        grads = [None, None]
+        for i, (holder, mode, needs) in enumerate(((ctx.holder, hash_mode, ctx.needs_input_grad[0]),
+                                                   (ctx.holder2, hash_mode2, ctx.needs_input_grad[1]))):
+            if holder is None or not needs:
+                continue
+            if holder.sparse and holder.fused is None:
+                rows = ops.row_index(ids.view(-1), mode, holder.num_embeddings, hash_arg)
+                vals = g.to(holder.weight.dtype)
+                grads[i] = _coo(rows, vals, holder)
+                continue
+            plan = ops.BackwardPlan.build(
+                ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
+                zero_pad=zero_pad, pad_id=pad_id,
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx)
+            grads[i] = holder.consume(plan, g)
+        return (grads[0], grads[1]) + (None,) * 9
+
+
+def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable) -> torch.Tensor:
+    """The uncoalesced COO gradient nn.Embedding(sparse=True) produces (nnz == lookups)."""
+    if holder.padding_idx is not None:
+        keep = rows != holder.padding_idx
+        rows, vals = rows[keep], vals[keep]
+    return torch.sparse_coo_tensor(rows.view(1, -1), vals, holder.weight.shape)
+
+
+class _KShiftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, ids, holder, num_shifts, epilogue):
+        out, inv = ops.kshift_fwd(holder.weight.detach(), ids, num_shifts, epilogue,
+                                  want_inv_norm=anchor.requires_grad)
+        ctx.holder, ctx.k, ctx.epilogue = holder, num_shifts, epilogue
+        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, inv, out = ctx.saved_tensors
+        holder, k = ctx.holder, ctx.k
+        dim = grad_out.shape[-1]
+        dx = ops.epilogue_bwd(grad_out.contiguous().view(-1, dim), out, inv, ctx.epilogue, k)
+        if holder.sparse and holder.fused is None:
+            flat = ids.contiguous().view(-1)
+            rows = torch.cat([ops.row_index(flat, N.HASH_ROTL_FLOORMOD, holder.num_embeddings, c)
+                              for c in range(k)])
+            vals = dx.to(holder.weight.dtype).repeat(k, 1)
+            return (_coo(rows, vals, holder), None, None, None, None)
+        plan = ops.BackwardPlan.build(
+            ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx)
+        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None)
+
+
+class _PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, per_slot_weight, holder, hash_mode, hash_arg, pool_mode,
+                last_n, zero_pad, pad_id):
+        out = ops.pool_fwd(holder.weight.detach(), ids, lengths=lengths, last_n=last_n,
+                           per_slot_weight=per_slot_weight, hash_mode=hash_mode, hash_arg=hash_arg,
+                           pool_mode=pool_mode, zero_pad=zero_pad, pad_id=pad_id)
+        ctx.holder = holder
+        ctx.cfg = (hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id)
+        ctx.save_for_backward(ids, lengths, per_slot_weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, lengths, per_slot_weight = ctx.saved_tensors
+        holder = ctx.holder
+        hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id = ctx.cfg
+        m, p = ids.shape
+        plan = ops.BackwardPlan.build(
+            ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
+            zero_pad=zero_pad, pad_id=pad_id,
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=p,
+            lengths=lengths, last_n=last_n)
+        scale = None
+        if pool_mode == N.POOL_MEAN:
+            scale = 1.0 / pooled_counts(ids, lengths, last_n, zero_pad, pad_id).clamp_(min=1).float()
+        gw = holder.consume(plan, grad_out.contiguous().view(m, -1), slots_per_grad_row=p,
+                            slot_weight=per_slot_weight, grad_row_scale=scale)
+        return (gw,) + (None,) * 10
+
+
+def pooled_counts(ids, lengths, last_n, zero_pad, pad_id) -> torch.Tensor:
+    """Number of slots each bag pools (the MEAN divisor); tiny index arithmetic on the device."""
+    m, p = ids.shape
+    pos = torch.arange(p, device=ids.device).unsqueeze(0)
+    hi = torch.full((m, 1), p, device=ids.device) if lengths is None else \
+        lengths.to(torch.int64).clamp(0, p).unsqueeze(1)
+    lo = (hi - last_n).clamp(min=0) if last_n > 0 else torch.zeros_like(hi)
+    ok = (pos >= lo) & (pos < hi)
+    if zero_pad:
+        ok &= ids != pad_id
+    return ok.sum(dim=1)
+
+
+# ------------------------------------------------------------------ modules ----
+class FlatEmbedding(nn.Module):
+    """commons/layers.py:44-61: row = floor_mod(id, N); out = table[row]; optional L2 norm.
+
+    state_dict key: `_emb_table.weight`.  `fused_pad_mask=True` additionally zero-fills
+    positions whose id is 0 without reading the table (the `ids == 0` mask of
+    models/lthm/sequence/product_tower.py:47-59 folded into the gather)."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, padding_idx: int = None,
+                 zero_init: bool = False, normalize_output: bool = False, *,
+                 dtype: torch.dtype = torch.float32, device=None, sparse: bool = False,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None,
+                 fused_pad_mask: bool = False):
+        super().__init__()
+        self._num_embeddings = num_embeddings
+        self._emb_dim = emb_dim
+        self.padding_idx = padding_idx
+        self._emb_table = EmbeddingTable(num_embeddings, emb_dim, padding_idx=padding_idx,
+                                         sparse=sparse, dtype=dtype, device=device)
+        self._normalize_output = normalize_output
+        self._fused_pad_mask = fused_pad_mask
+        if zero_init:
+            self._emb_table.weight.data.fill_(0.0)
+        if fused_optimizer is not None:
+            self._emb_table.enable_fused_optimizer(fused_optimizer)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        t = self._emb_table
+        return _GatherFn.apply(t.grad_anchor(), None, x, t, None, N.HASH_FLOORMOD, 0, 0,
+                               N.EPI_L2NORM if self._normalize_output else N.EPI_NONE,
+                               self._fused_pad_mask, 0)
+
+
+class KShiftEmbedding(nn.Module):
+    """commons/layers.py:125-185: k hashed lookups into one shared table, summed in the
+    order c = 0..k-1, then L2-normalised or scaled by 1/sqrt(k).  One kernel instead of
+    2k-1 launches.  state_dict key: `emb.weight`."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, num_shifts: int = 8,
+                 normalize_output: bool = False, sparse: bool = False, *,
+                 dtype: torch.dtype = torch.float32, device=None,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+        super().__init__()
+        self.emb = EmbeddingTable(num_embeddings, emb_dim, sparse=sparse, dtype=dtype, device=device)
+        self._num_embeddings = num_embeddings
+        self._num_shifts = num_shifts
+        self._num_bits = 64
+        self._normalize_output = normalize_output
+        if fused_optimizer is not None:
+            self.emb.enable_fused_optimizer(fused_optimizer)
+
+    def forward(self, id_: torch.Tensor) -> torch.Tensor:
+        return _KShiftFn.apply(self.emb.grad_anchor(), id_, self.emb, self._num_shifts,
+                               N.EPI_L2NORM if self._normalize_output else N.EPI_RSQRT_K)
+
+    def get_row_idx(self, x: torch.Tensor, col_idx: int) -> torch.Tensor:
+        """Bit-exact commons/layers.py:174-185 (wrapping <<, arithmetic >>, floor-mod)."""
+        return ops.row_index(x, N.HASH_ROTL_FLOORMOD, self._num_embeddings, col_idx)
+
+
+class QREmbedding(nn.Module):
+    """commons/layers.py:102-123 (the reference constructor forgets super().__init__();
+    semantics otherwise identical): d = floor(sqrt(N)); x' = id mod d^2;
+    out = emb_q[x' // d] + emb_r[x' mod d].  state_dict keys: `emb_q.weight`, `emb_r.weight`."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, normalize_output: bool, *,
+                 dtype: torch.dtype = torch.float32, device=None,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+        super().__init__()
+        self._div = int(math.sqrt(num_embeddings))
+        self.num_embeddings = self._div * self._div
+        self.emb_dim = emb_dim
+        self.emb_q = EmbeddingTable(self._div, emb_dim, dtype=dtype, device=device)
+        self.emb_r = EmbeddingTable(self._div, emb_dim, dtype=dtype, device=device)
+        self.normalize_output = normalize_output
+        if fused_optimizer is not None:
+            self.emb_q.enable_fused_optimizer(fused_optimizer)
+            self.emb_r.enable_fused_optimizer(FusedOptimizerConfig(**vars(fused_optimizer)))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _GatherFn.apply(self.emb_q.grad_anchor(), self.emb_r.grad_anchor(), x, self.emb_q,
+                               self.emb_r, N.HASH_QR_QUOTIENT, N.HASH_QR_REMAINDER, self._div,
+                               N.EPI_L2NORM if self.normalize_output else N.EPI_NONE, False, 0)
+
+
+class PooledEmbeddingBag(nn.Module):
+    """Multi-hot pooled lookup (north_star item 1; the op behind nn.EmbeddingBag(mode='sum')
+    at commons/transformers/layers.py:457).  ids [num_bags, bag_size] int64, optional
+    per-bag valid `lengths`, `last_n` window, per_sample_weights; sum or mean; padding ids
+    (`pad_id`, default 0 = CATEGORICAL_VAR_HASH_PAD_TOKEN, commons/feature_utils.py:8) are
+    skipped when `skip_pad`.  state_dict key: `emb.weight`."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, mode: str = "sum", *, last_n: int = 0,
+                 hash_ids: bool = True, skip_pad: bool = False, pad_id: int = 0,
+                 padding_idx: Optional[int] = None, dtype: torch.dtype = torch.float32, device=None,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+        super().__init__()
+        if mode not in ("sum", "mean"):
+            raise ValueError("mode must be 'sum' or 'mean' (use last_n for the last-N window)")
+        self.emb = EmbeddingTable(num_embeddings, emb_dim, padding_idx=padding_idx, dtype=dtype,
+                                  device=device)
+        self.mode, self.last_n = mode, int(last_n)
+        self.hash_ids, self.skip_pad, self.pad_id = hash_ids, skip_pad, pad_id
+        if fused_optimizer is not None:
+            self.emb.enable_fused_optimizer(fused_optimizer)
+
+    def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                per_sample_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return _PoolFn.apply(self.emb.grad_anchor(), ids, lengths, per_sample_weights, self.emb,
+                             N.HASH_FLOORMOD if self.hash_ids else N.HASH_IDENTITY, 0,
+                             N.POOL_SUM if self.mode == "sum" else N.POOL_MEAN, self.last_n,
+                             self.skip_pad, self.pad_id)
+
+
+class CosineVectorEmbedding(nn.Module):
+    """commons/transformers/layers.py:443-471: project -> bucketize -> fixed-size-bag sum.
+    The projection matmul and bucketize stay on torch (dense math, out of scope); the bag
+    sum over n_proj rows and its backward run in the pooled-bag kernels.
+    state_dict: `projection_mat`, `grid`, `pos_offset`, `emb.weight`."""
+
+    def __init__(self, inp_dim: int, emb_dim: int, n_proj: int = 16, num_bins: int = 20, *,
+                 device=None, fused_optimizer: Optional[FusedOptimizerConfig] = None):
+        super().__init__()
+        proj = F.normalize(torch.randn((inp_dim, n_proj)), p=2.0, dim=0)
+        self.register_buffer("projection_mat", proj.to(device), persistent=True)
+        resolution = 2.0 / float(num_bins)
+        grid = torch.linspace(-1.0, 1.0, steps=num_bins + 1)[:-1] + 0.5 * resolution
+        self.register_buffer("grid", grid.to(device), persistent=True)
+        pos_offset = ((num_bins + 1) * torch.arange(0, n_proj, dtype=torch.long)).reshape(n_proj)
+        self.register_buffer("pos_offset", pos_offset.to(device), persistent=True)
+        # nn.EmbeddingBag initialises N(0, 1) like nn.Embedding
+        self.emb = EmbeddingTable((num_bins + 1) * n_proj, emb_dim, device=device)
+        self.emb_dim, self.n_proj, self.num_bins = emb_dim, n_proj, num_bins
+        if fused_optimizer is not None:
+            self.emb.enable_fused_optimizer(fused_optimizer)
+
+    def bucket_indices(self, x: torch.Tensor) -> torch.Tensor:
+        z = F.normalize(x, p=2.0, dim=-1) @ self.projection_mat
+        return (torch.bucketize(z, self.grid).view(-1, self.n_proj) + self.pos_offset.unsqueeze(0))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        bs, seq_len, _ = x.size()
+        idxs = self.bucket_indices(x)
+        out = _PoolFn.apply(self.emb.grad_anchor(), idxs, None, None, self.emb, N.HASH_IDENTITY, 0,
+                            N.POOL_SUM, 0, False, 0)
+        return out.view(bs, seq_len, self.emb_dim)

@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI (include/recemb_b200.h).
+
+Each function takes CUDA tensors, launches on torch's current stream of the
+tensors' device and returns CUDA tensors.  No function here computes on the
+CPU or falls back to torch ops: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def _flat_ids(ids: torch.Tensor) -> torch.Tensor:
+    if ids.dtype != torch.int64:
+        # the reference asserts int64 history ids (models/lthm/sequence/wrapper.py:52)
+        raise N.NativeError(f"ids must be int64, got {ids.dtype}")
+    return ids.contiguous().view(-1)
+
+
+# ------------------------------------------------------------------ hashing ----
+def row_index(ids: torch.Tensor, hash_mode: int, num_rows: int, hash_arg: int = 0) -> torch.Tensor:
+    """rows = transform(ids); same shape, int64.  (commons/layers.py:174-185, :57)"""
+    flat = _flat_ids(ids)
+    dev = N.require_cuda(flat)
+    out = torch.empty_like(flat)
+    N.check(N.load().recemb_row_index(N.ptr(flat), flat.numel(), hash_mode, num_rows, hash_arg,
+                                      N.ptr(out), dev, N.stream_ptr(dev)), "recemb_row_index")
+    return out.view(ids.shape)
+
+
+# ------------------------------------------------------------------ forward ----
+def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HASH_FLOORMOD,
+               hash_arg: int = 0, table2: Optional[torch.Tensor] = None,
+               hash_mode2: int = N.HASH_FLOORMOD, epilogue: int = N.EPI_NONE,
+               zero_pad: bool = False, pad_id: int = 0,
+               want_inv_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    flat = _flat_ids(ids)
+    dev = N.require_cuda(table, table2, flat)
+    n, dim = flat.numel(), table.shape[1]
+    out = torch.empty((n, dim), dtype=table.dtype, device=table.device)
+    inv = None
+    if want_inv_norm and epilogue == N.EPI_L2NORM:
+        inv = torch.empty((n,), dtype=torch.float32, device=table.device)
+    N.check(N.load().recemb_gather_fwd(
+        N.ptr(table), table.shape[0], N.ptr(table2), 0 if table2 is None else table2.shape[0], dim,
+        N.dtype_code(table.dtype), N.ptr(flat), n, hash_mode, hash_mode2, hash_arg, epilogue,
+        int(zero_pad), pad_id, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_gather_fwd")
+    return out.view(*ids.shape, dim), inv
+
+
+def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue: int,
+               want_inv_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    flat = _flat_ids(ids)
+    dev = N.require_cuda(table, flat)
+    n, dim = flat.numel(), table.shape[1]
+    out = torch.empty((n, dim), dtype=table.dtype, device=table.device)
+    inv = None
+    if want_inv_norm and epilogue == N.EPI_L2NORM:
+        inv = torch.empty((n,), dtype=torch.float32, device=table.device)
+    N.check(N.load().recemb_kshift_fwd(
+        N.ptr(table), table.shape[0], dim, N.dtype_code(table.dtype), N.ptr(flat), n, num_shifts,
+        epilogue, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_kshift_fwd")
+    return out.view(*ids.shape, dim), inv
+
+
+def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.Tensor] = None,
+             last_n: int = 0, per_slot_weight: Optional[torch.Tensor] = None,
+             hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0, pool_mode: int = N.POOL_SUM,
+             zero_pad: bool = False, pad_id: int = 0) -> torch.Tensor:
+    if ids.dim() != 2:
+        raise N.NativeError("pooled bags take ids of shape [num_bags, bag_size]")
+    ids = ids.contiguous()
+    if ids.dtype != torch.int64:
+        raise N.NativeError(f"ids must be int64, got {ids.dtype}")
+    if lengths is not None:
+        lengths = lengths.to(torch.int32).contiguous()
+    if per_slot_weight is not None:
+        per_slot_weight = per_slot_weight.to(torch.float32).contiguous()
+    dev = N.require_cuda(table, ids, lengths, per_slot_weight)
+    m, p = ids.shape
+    dim = table.shape[1]
+    out = torch.empty((m, dim), dtype=table.dtype, device=table.device)
+    N.check(N.load().recemb_pool_fwd(
+        N.ptr(table), table.shape[0], dim, N.dtype_code(table.dtype), N.ptr(ids), m, p,
+        N.ptr(lengths), last_n, N.ptr(per_slot_weight), hash_mode, hash_arg, pool_mode,
+        int(zero_pad), pad_id, N.ptr(out), dev, N.stream_ptr(dev)), "recemb_pool_fwd")
+    return out
+
+
+# ----------------------------------------------------------------- backward ----
+@dataclass
+class BackwardPlan:
+    """Sorted (row, slot) pairs of one forward call: the dedup half of backward."""
+    buf: torch.Tensor  # uint8 device buffer holding the plan
+    n_slots: int
+    num_rows: int
+    slots_per_id: int
+
+    @staticmethod
+    def build(ids: torch.Tensor, *, num_rows: int, hash_mode: int = N.HASH_FLOORMOD,
+              hash_arg: int = 0, slots_per_id: int = 1, zero_pad: bool = False, pad_id: int = 0,
+              pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
+              last_n: int = 0, buf: Optional[torch.Tensor] = None) -> "BackwardPlan":
+        flat = _flat_ids(ids)
+        if lengths is not None:
+            lengths = lengths.to(torch.int32).contiguous()
+        dev = N.require_cuda(flat, lengths)
+        n_slots = flat.numel() * slots_per_id
+        lib = N.load()
+        need = int(lib.recemb_bwd_plan_bytes(n_slots, num_rows))
+        if need == 0:
+            N.check(-2, "recemb_bwd_plan_bytes")
+        if buf is None or buf.numel() < need:
+            buf = torch.empty((need,), dtype=torch.uint8, device=flat.device)
+        N.check(lib.recemb_bwd_plan(N.ptr(flat), flat.numel(), slots_per_id, hash_mode, num_rows,
+                                    hash_arg, int(zero_pad), pad_id, pad_row, bag_size,
+                                    N.ptr(lengths), last_n, N.ptr(buf), buf.numel(), dev,
+                                    N.stream_ptr(dev)), "recemb_bwd_plan")
+        return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=num_rows, slots_per_id=slots_per_id)
+
+    def _arr(self, which: int) -> torch.Tensor:
+        arr_bytes = (self.n_slots * 4 + 255) // 256 * 256
+        off = 256 + which * arr_bytes
+        return self.buf[off:off + self.n_slots * 4].view(torch.int32)
+
+    @property
+    def sorted_rows(self) -> torch.Tensor:
+        """int64 copy of the sorted row keys (num_rows marks a dropped slot)."""
+        return self._arr(2).to(torch.int64) & 0xFFFFFFFF
+
+    @property
+    def sorted_slots(self) -> torch.Tensor:
+        return self._arr(3).to(torch.int64) & 0xFFFFFFFF
+
+    @property
+    def counters(self) -> torch.Tensor:
+        """device int64 [2] = (valid slots, distinct rows)."""
+        return self.buf[:16].view(torch.int64)
+
+
+def make_optim_params(lr: float = 0.0, eps: float = 0.0, weight_decay: float = 0.0,
+                      beta1: float = 0.9, beta2: float = 0.999, step: int = 1) -> N.OptimParams:
+    return N.OptimParams(lr=lr, eps=eps, weight_decay=weight_decay, beta1=beta1, beta2=beta2,
+                         bias_correction1=1.0 - beta1 ** step, bias_correction2=1.0 - beta2 ** step,
+                         reserved=0.0)
+
+
+def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, update: int,
+              slots_per_grad_row: int = 1, state1: Optional[torch.Tensor] = None,
+              state2: Optional[torch.Tensor] = None, hp: Optional[N.OptimParams] = None,
+              slot_weight: Optional[torch.Tensor] = None,
+              grad_row_scale: Optional[torch.Tensor] = None,
+              workspace: Optional[torch.Tensor] = None) -> None:
+    """Segmented reduction of `grad` rows over the plan + `update` on `table` (in place)."""
+    dim = table.shape[1]
+    grad2d = grad.contiguous().view(-1, dim)
+    if grad2d.shape[0] * slots_per_grad_row != plan.n_slots:
+        raise N.NativeError(
+            f"grad has {grad2d.shape[0]} rows x {slots_per_grad_row} slots, plan has {plan.n_slots}")
+    dev = N.require_cuda(plan.buf, grad2d, table, state1, state2, slot_weight, grad_row_scale)
+    lib = N.load()
+    need = int(lib.recemb_bwd_apply_workspace_bytes(plan.n_slots, dim))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=table.device)
+    hp = hp or make_optim_params()
+    N.check(lib.recemb_bwd_apply(
+        N.ptr(plan.buf), plan.buf.numel(), N.ptr(grad2d), N.dtype_code(grad2d.dtype),
+        grad2d.shape[0], dim, slots_per_grad_row, N.ptr(slot_weight), N.ptr(grad_row_scale), update,
+        N.ptr(table), N.dtype_code(table.dtype), table.shape[0], N.ptr(state1), N.ptr(state2),
+        C.byref(hp), N.ptr(workspace), workspace.numel(), dev, N.stream_ptr(dev)),
+        "recemb_bwd_apply")
+
+
+def epilogue_bwd(grad_out: torch.Tensor, out: Optional[torch.Tensor],
+                 inv_norm: Optional[torch.Tensor], epilogue: int, num_shifts: int = 1) -> torch.Tensor:
+    """fp32 [n, dim] gradient w.r.t. the pre-epilogue sum (autograd of commons/layers.py:167-170)."""
+    dim = grad_out.shape[-1]
+    g = grad_out.contiguous().view(-1, dim)
+    o = None if out is None else out.contiguous().view(-1, dim)
+    dev = N.require_cuda(g, o, inv_norm)
+    dx = torch.empty(g.shape, dtype=torch.float32, device=g.device)
+    N.check(N.load().recemb_epilogue_bwd(N.ptr(g), N.ptr(o), N.dtype_code(g.dtype), N.ptr(inv_norm),
+                                         g.shape[0], dim, epilogue, num_shifts, N.ptr(dx), dev,
+                                         N.stream_ptr(dev)), "recemb_epilogue_bwd")
+    return dx
+
+
+# --------------------------------------------------------- dot interaction ----
+def dot_interaction_fwd(feats: torch.Tensor) -> torch.Tensor:
+    if feats.dim() != 3 or feats.dtype != torch.bfloat16:
+        raise N.NativeError("dot interaction takes bf16 [batch, num_feats, dim]")
+    feats = feats.contiguous()
+    dev = N.require_cuda(feats)
+    b, f, d = feats.shape
+    out = torch.empty((b, f * (f - 1) // 2), dtype=torch.bfloat16, device=feats.device)
+    N.check(N.load().recemb_dot_interaction_fwd(N.ptr(feats), b, f, d, N.ptr(out), dev,
+                                                N.stream_ptr(dev)), "recemb_dot_interaction_fwd")
+    return out
+
+
+def dot_interaction_bwd(feats: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    feats = feats.contiguous()
+    grad_out = grad_out.contiguous()
+    dev = N.require_cuda(feats, grad_out)
+    b, f, d = feats.shape
+    gf = torch.empty_like(feats)
+    N.check(N.load().recemb_dot_interaction_bwd(N.ptr(feats), N.ptr(grad_out), b, f, d, N.ptr(gf),
+                                                dev, N.stream_ptr(dev)), "recemb_dot_interaction_bwd")
+    return gf

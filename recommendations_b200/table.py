@@ -1,0 +1,184 @@
+"""EmbeddingTable: the weight holder behind every embedding module of this package.
+
+It keeps the reference's state_dict key (`<name>.weight`, as nn.Embedding /
+nn.EmbeddingBag would) and offers the two gradient modes of SURVEY.md section 8(b):
+
+  torch-compatible   weight is an nn.Parameter; backward produces the dense
+                     (or, sparse=True, uncoalesced COO) gradient nn.Embedding
+                     would, so the reference's optim_group /
+                     optimizers_for_param_groups flow
+                     (commons/base_model_wrapper.py:51-72) keeps working.
+  fused              weight is a buffer (hidden from parameters(), so the loops at
+                     accelerate_training_strategy.py:355, :360-362, :378 do not
+                     scan it); backward applies the optimizer to the touched rows
+                     inside the segmented-reduction kernel.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import ops
+
+
+@dataclass
+class FusedOptimizerConfig:
+    """Hyper-parameters of the in-kernel update.  Defaults follow torch.optim."""
+    kind: str = "adagrad"  # sgd | adagrad | rowwise_adagrad | adam | adamw
+    lr: float = 0.5        # embedding_module_gen.py:97, :137 use Adagrad(lr=5e-1)
+    eps: float = 1e-10
+    weight_decay: float = 0.0
+    betas: Tuple[float, float] = (0.9, 0.999)
+    lr_decay: float = 0.0
+    initial_accumulator_value: float = 0.0
+
+    def __post_init__(self):
+        if self.kind not in ("sgd", "adagrad", "rowwise_adagrad", "adam", "adamw"):
+            raise ValueError(f"unknown fused optimizer kind {self.kind!r}")
+
+
+class EmbeddingTable(nn.Module):
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: Optional[int] = None,
+                 sparse: bool = False, dtype: torch.dtype = torch.float32, device=None,
+                 _weight: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.num_embeddings = int(num_embeddings)
+        self.embedding_dim = int(embedding_dim)
+        if padding_idx is not None and padding_idx < 0:
+            padding_idx = self.num_embeddings + padding_idx
+        self.padding_idx = padding_idx
+        self.sparse = bool(sparse)
+        if _weight is None:
+            # nn.Embedding.reset_parameters: N(0, 1), padding row zeroed
+            w = torch.empty((self.num_embeddings, self.embedding_dim), dtype=torch.float32)
+            nn.init.normal_(w)
+            if padding_idx is not None:
+                with torch.no_grad():
+                    w[padding_idx].fill_(0)
+            w = w.to(dtype=dtype, device=device)
+        else:
+            w = _weight
+        self.weight = nn.Parameter(w)
+        self.fused: Optional[FusedOptimizerConfig] = None
+        self.fused_step = 0
+        self._anchor: Optional[torch.Tensor] = None
+
+    # ---------------------------------------------------------------- modes ----
+    def enable_fused_optimizer(self, config: Optional[FusedOptimizerConfig] = None, **kw) -> "EmbeddingTable":
+        """Turn the Parameter into a buffer and apply `config` inside backward."""
+        cfg = config or FusedOptimizerConfig(**kw)
+        w = self.weight.detach()
+        if "weight" in self._parameters:
+            del self._parameters["weight"]
+            self.register_buffer("weight", w, persistent=True)
+        self.fused = cfg
+        self.fused_step = 0
+        for name in ("opt_state1", "opt_state2"):
+            if name in self._buffers:
+                del self._buffers[name]
+        return self
+
+    def _ensure_state(self) -> None:
+        cfg = self.fused
+        w = self.weight
+        if cfg.kind == "adagrad" and "opt_state1" not in self._buffers:
+            self.register_buffer("opt_state1", torch.full(w.shape, cfg.initial_accumulator_value,
+                                                          dtype=torch.float32, device=w.device),
+                                 persistent=False)
+        elif cfg.kind == "rowwise_adagrad" and "opt_state1" not in self._buffers:
+            self.register_buffer("opt_state1", torch.full((w.shape[0],), cfg.initial_accumulator_value,
+                                                          dtype=torch.float32, device=w.device),
+                                 persistent=False)
+        elif cfg.kind in ("adam", "adamw") and "opt_state1" not in self._buffers:
+            self.register_buffer("opt_state1", torch.zeros(w.shape, dtype=torch.float32, device=w.device),
+                                 persistent=False)
+            self.register_buffer("opt_state2", torch.zeros(w.shape, dtype=torch.float32, device=w.device),
+                                 persistent=False)
+
+    def grad_anchor(self) -> torch.Tensor:
+        """The tensor a lookup Function differentiates against."""
+        if self.fused is None:
+            return self.weight
+        dev = self.weight.device
+        if self._anchor is None or self._anchor.device != dev:
+            self._anchor = torch.zeros((), device=dev, requires_grad=True)
+        return self._anchor
+
+    # ------------------------------------------------------------- backward ----
+    def consume(self, plan: ops.BackwardPlan, grad2d: torch.Tensor, slots_per_grad_row: int = 1,
+                slot_weight: Optional[torch.Tensor] = None,
+                grad_row_scale: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """Reduce grad rows over `plan`; fused: update in place and return None,
+        torch-compatible: return the dense gradient of `weight`."""
+        w = self.weight
+        if w.dtype == torch.float32 and grad2d.dtype != torch.float32:
+            grad2d = grad2d.float()
+        if self.fused is None:
+            gw = torch.zeros_like(w)
+            ops.bwd_apply(plan, grad2d, table=gw, update=N.UPD_DENSE_GRAD,
+                          slots_per_grad_row=slots_per_grad_row, slot_weight=slot_weight,
+                          grad_row_scale=grad_row_scale)
+            return gw
+        cfg = self.fused
+        self._ensure_state()
+        self.fused_step += 1
+        lr = cfg.lr
+        if cfg.kind in ("adagrad", "rowwise_adagrad"):
+            lr = cfg.lr / (1.0 + (self.fused_step - 1) * cfg.lr_decay)
+        hp = ops.make_optim_params(lr=lr, eps=cfg.eps, weight_decay=cfg.weight_decay,
+                                   beta1=cfg.betas[0], beta2=cfg.betas[1], step=self.fused_step)
+        with torch.no_grad():
+            ops.bwd_apply(plan, grad2d, table=w.data, update=N.UPDATE_BY_NAME[cfg.kind],
+                          slots_per_grad_row=slots_per_grad_row,
+                          state1=self._buffers.get("opt_state1"),
+                          state2=self._buffers.get("opt_state2"), hp=hp, slot_weight=slot_weight,
+                          grad_row_scale=grad_row_scale)
+        return None
+
+    def extra_repr(self) -> str:
+        mode = "torch-grad" if self.fused is None else f"fused-{self.fused.kind}"
+        return (f"{self.num_embeddings}, {self.embedding_dim}, padding_idx={self.padding_idx}, "
+                f"dtype={self.weight.dtype}, mode={mode}")
+
+
+class FusedEmbeddingOptimizer(torch.optim.Optimizer):
+    """Facade returned from optimizers_for_param_groups
+    (commons/base_model_wrapper.py:64-72) for tables in fused mode: the update has
+    already happened inside backward, so step() / zero_grad() do nothing; the
+    object carries the hyper-parameters and exposes the optimizer state."""
+
+    def __init__(self, tables, **overrides):
+        self.tables = [t for t in tables if isinstance(t, EmbeddingTable)]
+        if not self.tables:
+            raise ValueError("FusedEmbeddingOptimizer needs at least one EmbeddingTable")
+        for t in self.tables:
+            if t.fused is None:
+                t.enable_fused_optimizer(FusedOptimizerConfig(**overrides))
+            else:
+                for k, v in overrides.items():
+                    setattr(t.fused, k, v)
+        params = [t.grad_anchor() for t in self.tables]
+        super().__init__(params, dict(lr=self.tables[0].fused.lr))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        # a scheduler may have rewritten param_groups[*]['lr']: push it to the tables
+        for group in self.param_groups:
+            for t in self.tables:
+                t.fused.lr = float(group["lr"])
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        for t in self.tables:
+            if t._anchor is not None:
+                t._anchor.grad = None
+
+    def fused_state_dict(self):
+        return {i: {"step": t.fused_step,
+                    "state1": t._buffers.get("opt_state1"),
+                    "state2": t._buffers.get("opt_state2")} for i, t in enumerate(self.tables)}

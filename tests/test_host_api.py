@@ -1,0 +1,72 @@
+"""Host-side mirror of the reference module surface: constructors,
+state_dict keys, parameter visibility in the two gradient modes, loud failure on CPU."""
+import pytest
+import torch
+
+import recommendations_b200 as R
+from recommendations_b200 import _native as N
+
+
+def test_state_dict_keys_match_reference():
+    assert list(R.FlatEmbedding(10, 4).state_dict()) == ["_emb_table.weight"]
+    assert list(R.KShiftEmbedding(10, 4).state_dict()) == ["emb.weight"]
+    assert list(R.QREmbedding(100, 4, False).state_dict()) == ["emb_q.weight", "emb_r.weight"]
+    assert sorted(R.CosineVectorEmbedding(8, 4, n_proj=4, num_bins=6).state_dict()) == \
+        ["emb.weight", "grid", "pos_offset", "projection_mat"]
+
+
+def test_reference_constructor_signatures():
+    m = R.FlatEmbedding(10, 4, 0, True, True)
+    assert m.padding_idx == 0 and m._normalize_output and float(m._emb_table.weight.abs().sum()) == 0.0
+    k = R.KShiftEmbedding(10, 4, 16, True, True)
+    assert k._num_shifts == 16 and k._normalize_output and k.emb.sparse and k._num_bits == 64
+    q = R.QREmbedding(10007, 4, True)
+    assert q._div == 100 and q.num_embeddings == 10000 and q.emb_q.weight.shape == (100, 4)
+    c = R.CosineVectorEmbedding(32, 512, n_proj=32, num_bins=12)
+    assert c.emb.weight.shape == (13 * 32, 512) and c.pos_offset.tolist()[:3] == [0, 13, 26]
+
+
+def test_init_matches_nn_embedding_under_same_seed():
+    torch.manual_seed(7)
+    a = R.FlatEmbedding(50, 8, padding_idx=3)
+    torch.manual_seed(7)
+    b = torch.nn.Embedding(50, 8, padding_idx=3)
+    assert torch.equal(a._emb_table.weight, b.weight)
+    assert a._emb_table.weight[3].abs().sum() == 0
+
+
+def test_load_state_dict_roundtrip_from_reference_shaped_dict():
+    src = {"emb.weight": torch.randn(10, 4)}
+    k = R.KShiftEmbedding(10, 4)
+    k.load_state_dict(src)
+    assert torch.equal(k.emb.weight, src["emb.weight"])
+    k.emb.enable_fused_optimizer(kind="adagrad", lr=0.5)
+    k.load_state_dict(src)  # same key in fused (buffer) mode
+    assert list(k.state_dict()) == ["emb.weight"]
+
+
+def test_fused_mode_hides_table_from_parameters():
+    k = R.KShiftEmbedding(10, 4, fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad"))
+    assert list(k.parameters()) == []
+    f = R.FlatEmbedding(10, 4)
+    assert [n for n, _ in f.named_parameters()] == ["_emb_table.weight"]
+    opt = R.FusedEmbeddingOptimizer([f._emb_table], kind="adagrad", lr=0.25)
+    assert list(f.parameters()) == [] and f._emb_table.fused.lr == 0.25
+    opt.param_groups[0]["lr"] = 0.125  # a scheduler would do this
+    opt.step()
+    opt.zero_grad()
+    assert f._emb_table.fused.lr == 0.125
+
+
+def test_cpu_tensors_raise_instead_of_falling_back():
+    with pytest.raises(N.NativeError, match="no CPU fallback"):
+        R.FlatEmbedding(10, 4)(torch.tensor([[1, 2]]))
+    with pytest.raises(N.NativeError):
+        R.KShiftEmbedding(10, 4).get_row_idx(torch.tensor([1, 2]), 1)
+
+
+def test_bad_config_is_rejected():
+    with pytest.raises(ValueError):
+        R.FusedOptimizerConfig(kind="lion")
+    with pytest.raises(ValueError):
+        R.PooledEmbeddingBag(10, 4, mode="max")
