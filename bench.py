@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- embedding lookups/sec fwd+bwd on BASELINE.json configs[1]:
+"LTHM embedding fwd+bwd on 1xB200, batch 8192, history len 200, 10 tables of 1Mx64 fp32".
+
+A step = one pass of the hot path over one synthetic batch: for each of the 10 tables a
+sequence gather of [8192, 200] ids (FlatEmbedding semantics, commons/layers.py:56-61) and its
+backward with the reference's optimizer fused (element-wise Adagrad lr 0.5,
+embedding_module_gen.py:137): sort-based dedup plan + segmented reduction + update.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 (torchrun, one rank per GPU): tables of this size are replicated by the reference
+(pure data parallel) -- every rank runs the same per-GPU workload on its own
+batch (weak scaling, no data-path collective); the row-wise sharded large-vocab path is
+measured by --workload cfg5.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T_TABLES, BATCH, HIST, ROWS, DIM = 10, 8192, 200, 1_000_000, 64
+LR, EPS = 0.5, 1e-10
+METRIC = "embedding_lookups_per_sec_fwd_bwd"
+UNIT = "lookups/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def host_ids(t: int, rank: int = 0) -> torch.Tensor:
+    g = torch.Generator().manual_seed(1000 + t + 100 * rank)
+    return torch.randint(-2 ** 63, 2 ** 63 - 1, (BATCH * HIST,), generator=g, dtype=torch.int64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU baseline ----
+def cpu_baseline_run(steps: int, warmup: int, ids: torch.Tensor, weight: torch.Tensor,
+                     grad: torch.Tensor):
+    """The reference's own CPU path for one table: remainder -> F.embedding -> autograd ->
+    torch.optim.Adagrad(lr=0.5) with dense gradients (oracle port; all host threads)."""
+    from oracle import embedding_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    mod = O.FlatTableCPU(weight)
+    opt = torch.optim.Adagrad(mod.parameters(), lr=LR)
+    ids2 = ids.view(BATCH, HIST)
+    g3 = grad.view(BATCH, HIST, DIM)
+    for _ in range(warmup):
+        O.cpu_train_step(mod, opt, ids2, g3)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.cpu_train_step(mod, opt, ids2, g3)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, since the
+    reference is pure Python over torch and cannot travel), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ids = host_ids(0)
+    torch.manual_seed(1234)
+    weight = torch.randn(ROWS, DIM)
+    grad = torch.randn(BATCH * HIST, DIM, generator=torch.Generator().manual_seed(4321))
+    times = cpu_baseline_run(args.steps, args.warmup, ids, weight, grad)
+    total = sum(times)
+    value = BATCH * HIST * args.steps / total
+    sample = (f"1 of {T_TABLES} tables per step (FlatEmbedding {ROWS}x{DIM} fp32, ids [{BATCH},{HIST}]), "
+              f"fwd + dense bwd + torch.optim.Adagrad, {args.warmup} warm-up + {args.steps} timed")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: LTHM embedding fwd+bwd, batch 8192, history 200, 10 tables 1Mx64 fp32 "
+                               "(CPU arm: bounded sample = one table per step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------- B200 arm ----
+def run_b200(args):
+    import torch.distributed as dist
+
+    import recommendations_b200  # noqa: F401
+    from recommendations_b200 import _native as N
+    from recommendations_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    lib = N.load()
+    n = BATCH * HIST
+
+    # ---- resident state: tables, Adagrad state, ids, upstream gradients, outputs ----
+    gen = torch.Generator(device=dev)
+    tables, states = [], []
+    for t in range(T_TABLES):
+        gen.manual_seed(1234 + t)
+        tables.append(torch.randn(ROWS, DIM, device=dev, generator=gen))
+        states.append(torch.zeros(ROWS, DIM, device=dev))
+    ids_host = [host_ids(t, rank).pin_memory() for t in range(T_TABLES)]
+    ids_dev = [h.to(dev) for h in ids_host]
+    gen.manual_seed(4321)
+    grads = [torch.randn(n, DIM, device=dev, generator=gen) for _ in range(T_TABLES)]
+    outs = [torch.empty(n, DIM, device=dev) for _ in range(T_TABLES)]
+    plan_bytes = int(lib.recemb_bwd_plan_bytes(n, ROWS))
+    ws_bytes = int(lib.recemb_bwd_apply_workspace_bytes(n, DIM))
+    plan_bufs = [torch.empty(plan_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ws_bufs = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    hp = ops.make_optim_params(lr=LR, eps=EPS)
+
+    ev_apply = []  # (start, stop) around the level-0 segmented-reduction launches
+    ev_gather = []
+
+    def step(timed: bool):
+        for t in range(T_TABLES):
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            ops.gather_fwd(tables[t], ids_dev[t], out=outs[t])
+            if timed:
+                b.record()
+                ev_gather.append((a, b))
+        for t in range(T_TABLES):
+            plan = ops.BackwardPlan.build(ids_dev[t], num_rows=ROWS, buf=plan_bufs[t % 2])
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()  # creates the underlying cudaEvent_t; the library re-records both
+                b.record()  # around its level-0 launch
+                lib.recemb_time_next_apply(a.cuda_event, b.cuda_event)
+                ev_apply.append((a, b))
+            ops.bwd_apply(plan, grads[t], table=tables[t], update=N.UPD_ADAGRAD, state1=states[t], hp=hp,
+                          workspace=ws_bufs[t % 2])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step(True)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = N.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    value = world * n * T_TABLES * args.steps / (ms_total * 1e-3)
+
+    # unique rows per table (for the algorithmic byte count of the dominant kernel)
+    uniq = []
+    for t in range(T_TABLES):
+        plan = ops.BackwardPlan.build(ids_dev[t], num_rows=ROWS, buf=plan_bufs[0])
+        uniq.append(int(plan.counters.cpu()[1]))
+    row_bytes = DIM * 4
+    apply_ms = [a.elapsed_time(b) for a, b in ev_apply]
+    gather_ms = [a.elapsed_time(b) for a, b in ev_gather]
+    apply_bytes = n * (8 + row_bytes) + (sum(uniq) / T_TABLES) * (2 * row_bytes + 2 * DIM * 4)
+    gather_bytes = n * (8 + 2 * row_bytes)
+    peak, peak_kind = peaks()
+    apply_gbs = apply_bytes / (statistics.mean(apply_ms) * 1e-3) / 1e9
+    gather_gbs = gather_bytes / (statistics.mean(gather_ms) * 1e-3) / 1e9
+    step_bytes = T_TABLES * (gather_bytes + apply_bytes)
+    roofline = {
+        "bound": "hbm", "kernel": "seg_kernel<16,1,float,float,true> (segmented reduce + fused Adagrad)",
+        "achieved": apply_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+        "frac": apply_gbs / peak, "traffic": None,
+        "algorithmic_bytes_per_launch": apply_bytes, "avg_launch_ms": statistics.mean(apply_ms),
+        "gather_kernel": {"achieved": gather_gbs, "frac": gather_gbs / peak,
+                          "algorithmic_bytes_per_launch": gather_bytes,
+                          "avg_launch_ms": statistics.mean(gather_ms)},
+        "whole_step": {"algorithmic_bytes": step_bytes,
+                       "achieved": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
+                       "frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- end to end: HOST ids -> C-ABI host entry point -> device result read back ----
+    e2e = run_e2e(args, lib, N, ops, dev, world, tables, states, ids_host, grads, outs, plan_bufs,
+                  ws_bufs, hp, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        w_cpu = tables[0].cpu()
+        times = cpu_baseline_run(3, 1, ids_host[0], w_cpu, grads[0].cpu())
+        best = min(times)
+        cpu = {"value": n / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 of {T_TABLES} tables (same ids / weights / grads as the GPU run), fwd + dense bwd + "
+                         f"torch.optim.Adagrad on CPU, 1 warm-up + 3 timed, best; os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: LTHM embedding fwd+bwd, batch 8192 x history 200, 10 tables "
+                                   "1Mx64 fp32, sequence gather + fused element-wise Adagrad(lr=0.5)",
+                       "lookups_per_step_per_gpu": n * T_TABLES, "unique_rows_per_table": uniq,
+                       "l2": "inputs larger than L2: 419 MB out + 419 MB grad + 256 MB table per table vs 126 MB",
+                       "multi_gpu": "replicas (tables replicated as in the reference), weak scaling"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, lib, N, ops, dev, world, tables, states, ids_host, grads, outs, plan_bufs, ws_bufs,
+            hp, barrier):
+    """Same step through recemb_flat_step_host: ids start in PINNED HOST memory every step; two
+    streams alternate tables so the H2D copy of table t+1 overlaps the kernels of table t; the
+    step's result (valid / unique counters per table) is read back to the host."""
+    import ctypes as C
+    import torch.distributed as dist
+    n = BATCH * HIST
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    scratch = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    counters = torch.zeros(T_TABLES, 2, dtype=torch.int64).pin_memory()
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def step():
+        for t in range(T_TABLES):
+            s = streams[t % 2]
+            s.wait_event(done[t % 2])  # scratch / plan / workspace of this slot are free again
+            N.check(lib.recemb_flat_step_host(
+                ids_host[t].data_ptr(), n, scratch[t % 2].data_ptr(), tables[t].data_ptr(), ROWS, DIM,
+                N.F32, outs[t].data_ptr(), grads[t].data_ptr(), N.UPD_ADAGRAD, states[t].data_ptr(),
+                None, C.byref(hp), plan_bufs[t % 2].data_ptr(), plan_bufs[t % 2].numel(),
+                ws_bufs[t % 2].data_ptr(), ws_bufs[t % 2].numel(), counters[t].data_ptr(), dev.index,
+                s.cuda_stream), "recemb_flat_step_host")
+            done[t % 2].record(s)
+        for s in streams:
+            s.synchronize()  # the host reads the counters: device->host result of the step
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), 0.0)
+    ms = max(ms, wall * 1e3 * 0.0)  # device clock is the figure; wall kept for the record below
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    assert int(counters[:, 0].min()) == n, "e2e step did not process every lookup"
+    return {"value": world * n * T_TABLES * args.steps / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": T_TABLES * n * 8, "d2h_bytes_per_step": T_TABLES * 16,
+            "ms_per_step": ms / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
+            "api": "recemb_flat_step_host (C ABI, pinned host ids, 2 streams)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print(f"[bench] note: warmup {args.warmup} < 3", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -194,6 +194,10 @@ RECEMB_API int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
                      const recemb_optim_params* hp_host, void* workspace, size_t workspace_bytes,
                      int device, recemb_stream_t stream);
 
+/* Measurement hook: the next recemb_bwd_apply on this thread records the two CUDA events
+ * (cudaEvent_t) around its level-0 segmented-reduction launch, then disarms the hook. */
+RECEMB_API int recemb_time_next_apply(void* start_event, void* stop_event);
+
 /* ---- backward of the k-shift / pooled epilogues ---------------------------- */
 /* dx[i,:] for y = epilogue(x): L2NORM: (g - y (y.g)) * inv_norm[i]; RSQRT_K: g / sqrt(k).
  * (autograd of commons/layers.py:167-170).  dx is fp32 [n, dim]. */

@@ -72,6 +72,7 @@ SIGNATURES = {
     "recemb_bwd_apply_workspace_bytes": (_SZ, [_I64, _I32]),
     "recemb_bwd_apply": (_INT, [_P, _SZ, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
                                 _P, _P, C.POINTER(OptimParams), _P, _SZ, _INT, _P]),
+    "recemb_time_next_apply": (_INT, [_P, _P]),
     "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),

@@ -488,6 +488,9 @@ static int level_sizes(int64_t n0, int64_t* sizes, int max_levels) {
 }
 constexpr int kMaxLevels = 16;
 
+// measurement hook: events recorded around the level-0 launch of the next bwd_apply
+static thread_local cudaEvent_t t_ev_start = nullptr, t_ev_stop = nullptr;
+
 // ------------------------------------------------------- epilogue backward ----
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads)
@@ -705,6 +708,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
     a.out_keys = out_keys;
     a.out_partials = out_part;
     int rc;
+    if (l == 0 && t_ev_start) cudaEventRecord(t_ev_start, s);
     if (l == 0) {
       if (grad_dtype == RECEMB_F32 && dtype == RECEMB_F32)
         rc = launch_seg<float, float, true>(a, shape, s);
@@ -716,11 +720,19 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
       if (dtype == RECEMB_F32) rc = launch_seg<float, float, false>(a, shape, s);
       else rc = launch_seg<float, __nv_bfloat16, false>(a, shape, s);
     }
+    if (l == 0 && t_ev_stop) cudaEventRecord(t_ev_stop, s);
+    if (l == 0) t_ev_start = t_ev_stop = nullptr;
     if (rc) return rc;
     in_keys = out_keys;
     in_slots = nullptr;
     in_grad = out_part;
   }
+  return RECEMB_OK;
+}
+
+extern "C" int recemb_time_next_apply(void* start_event, void* stop_event) {
+  t_ev_start = (cudaEvent_t)start_event;
+  t_ev_stop = (cudaEvent_t)stop_event;
   return RECEMB_OK;
 }
 

@@ -38,12 +38,15 @@ def row_index(ids: torch.Tensor, hash_mode: int, num_rows: int, hash_arg: int = 
 def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HASH_FLOORMOD,
                hash_arg: int = 0, table2: Optional[torch.Tensor] = None,
                hash_mode2: int = N.HASH_FLOORMOD, epilogue: int = N.EPI_NONE,
-               zero_pad: bool = False, pad_id: int = 0,
-               want_inv_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               zero_pad: bool = False, pad_id: int = 0, want_inv_norm: bool = False,
+               out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     flat = _flat_ids(ids)
-    dev = N.require_cuda(table, table2, flat)
+    dev = N.require_cuda(table, table2, flat, out)
     n, dim = flat.numel(), table.shape[1]
-    out = torch.empty((n, dim), dtype=table.dtype, device=table.device)
+    if out is None:
+        out = torch.empty((n, dim), dtype=table.dtype, device=table.device)
+    elif out.numel() != n * dim or out.dtype != table.dtype:
+        raise N.NativeError("preallocated `out` has the wrong size / dtype")
     inv = None
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
