@@ -119,10 +119,13 @@ RECEMB_API int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, in
  * If table2 != NULL the row table2[transform2(ids[i])] is added before the
  * epilogue (QREmbedding: emb_q(q) + emb_r(r), commons/layers.py:115-123):
  * hash_mode applies to `table` and hash_mode2 to `table2`, both with hash_arg.
- * inv_norm_out (optional, fp32 [n]) receives 1/max(||x||,1e-12) for the L2NORM backward. */
+ * inv_norm_out (optional, fp32 [n]) receives 1/max(||x||,1e-12) for the L2NORM backward.
+ * Table-batched mode (ids_per_table > 0): `table` is T tables of num_rows rows stacked as
+ * [T * num_rows, dim]; lookup i belongs to table i / ids_per_table and reads row
+ * (i / ids_per_table) * num_rows + transform(ids[i]) -- all T tables in one launch. */
 RECEMB_API int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2, int64_t num_rows2,
-                      int32_t dim, int dtype, const int64_t* ids, int64_t n, int hash_mode,
-                      int hash_mode2, int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
+                      int32_t dim, int dtype, const int64_t* ids, int64_t n, int64_t ids_per_table,
+                      int hash_mode, int hash_mode2, int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
                       void* out, float* inv_norm_out, int device, recemb_stream_t stream);
 
 /* ---- forward: fused k-shift bag (a3) -------------------------------------- */
@@ -159,13 +162,21 @@ RECEMB_API int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
  * (nn.Embedding padding_idx: that row never receives gradient, commons/layers.py:51);
  * bag_size > 0 and the slot is outside its bag's window (lengths / last_n as in
  * recemb_pool_fwd).
- * The plan lives in caller memory of recemb_bwd_plan_bytes(n_slots, num_rows). */
+ * Table-batched mode (ids_per_table > 0, as in recemb_gather_fwd): num_rows is per table and
+ * the sorted keys are rows of the stacked table, t * num_rows + row; one sort for all tables.
+ * The plan lives in caller memory of recemb_bwd_plan_bytes(n_slots, total_rows), with
+ * total_rows = num_rows * number_of_tables (also the num_rows to pass to recemb_bwd_apply). */
 RECEMB_API size_t recemb_bwd_plan_bytes(int64_t n_slots, int64_t num_rows);
 
-RECEMB_API int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_per_id, int hash_mode,
-                    int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
+RECEMB_API int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_per_table,
+                    int32_t slots_per_id, int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
                     int64_t pad_row, int32_t bag_size, const int32_t* lengths, int32_t last_n,
                     void* plan, size_t plan_bytes, int device, recemb_stream_t stream);
+
+/* Fills the plan's two device counters {valid slots, distinct rows} (int64[2] at the start of
+ * the plan buffer).  Separate from recemb_bwd_plan because the update path does not need them. */
+RECEMB_API int recemb_plan_count(void* plan, size_t plan_bytes, int64_t n_slots, int64_t num_rows,
+                      int device, recemb_stream_t stream);
 
 /* Device-side views into a built plan (valid until the plan memory is reused). */
 RECEMB_API int recemb_plan_views(const void* plan, size_t plan_bytes, const uint32_t** sorted_rows,
@@ -222,8 +233,10 @@ RECEMB_API int recemb_dot_interaction_bwd(const void* feats, const void* grad_ou
  * H2D copy of ids_host (pinned or pageable) into ids_dev_scratch, forward gather
  * into out, backward plan + fused update with grad (device, fp32/bf16 [n, dim]),
  * then counters_host[0..1] = {n_valid, n_unique} are copied back (async on
- * `stream`; the caller synchronises the stream before reading them). */
-RECEMB_API int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t* ids_dev_scratch,
+ * `stream`; the caller synchronises the stream before reading them).  ids_per_table > 0
+ * selects the table-batched mode of recemb_gather_fwd (num_rows per table, stacked table). */
+RECEMB_API int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t ids_per_table,
+                          int64_t* ids_dev_scratch,
                           void* table, int64_t num_rows, int32_t dim, int dtype, void* out,
                           const void* grad, int update, void* state1, void* state2,
                           const recemb_optim_params* hp_host, void* plan, size_t plan_bytes,

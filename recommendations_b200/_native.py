@@ -59,14 +59,15 @@ SIGNATURES = {
     "recemb_last_error": (C.c_char_p, []),
     "recemb_launch_count": (C.c_uint64, []),
     "recemb_row_index": (_INT, [_P, _I64, _INT, _I64, _I64, _P, _INT, _P]),
-    "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, _INT, _INT, _I64, _INT,
-                                 _INT, _I64, _P, _P, _INT, _P]),
+    "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, _I64, _INT, _INT, _I64,
+                                 _INT, _INT, _I64, _P, _P, _INT, _P]),
     "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _P, _P, _INT, _P]),
     "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,
                                _INT, _I64, _P, _INT, _P]),
     "recemb_bwd_plan_bytes": (_SZ, [_I64, _I64]),
-    "recemb_bwd_plan": (_INT, [_P, _I64, _I32, _INT, _I64, _I64, _INT, _I64, _I64, _I32, _P, _I32,
-                               _P, _SZ, _INT, _P]),
+    "recemb_bwd_plan": (_INT, [_P, _I64, _I64, _I32, _INT, _I64, _I64, _INT, _I64, _I64, _I32, _P,
+                               _I32, _P, _SZ, _INT, _P]),
+    "recemb_plan_count": (_INT, [_P, _SZ, _I64, _I64, _INT, _P]),
     "recemb_plan_views": (_INT, [_P, _SZ, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                  C.POINTER(_I64)]),
     "recemb_bwd_apply_workspace_bytes": (_SZ, [_I64, _I32]),
@@ -76,7 +77,7 @@ SIGNATURES = {
     "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
-    "recemb_flat_step_host": (_INT, [_P, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
+    "recemb_flat_step_host": (_INT, [_P, _I64, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
                                      C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _INT, _P]),
 }
 

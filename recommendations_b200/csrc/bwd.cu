@@ -9,7 +9,7 @@
 //            embedding_module_gen.py:97, :137, :153)
 //
 // The segmented reduction is load-balanced by construction: every group of G
-// lanes owns a chunk of kChunk consecutive sorted entries whatever the run
+// lanes owns a chunk of kChunk0 consecutive sorted entries whatever the run
 // lengths are (the k-shift collapse puts ~50 % of a shift's lookups on a
 // handful of rows).  Runs closed inside a chunk are applied
 // directly; runs that cross a chunk boundary leave (row, partial sum) records
@@ -18,12 +18,14 @@
 // atomics.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace recemb {
 
 constexpr int kBwdThreads = 256;
-constexpr int kChunk = 32;
 constexpr uint32_t kNoKey = 0xffffffffu;
 constexpr size_t kCounterBytes = 256;
 
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
     if (ok) {
       const int64_t row =
           a.slots_per_id > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
-      if (row != a.pad_row) key = (uint32_t)row;
+      if (row != a.pad_row) key = (uint32_t)(row + table_offset(id_idx, a.h));
     }
     a.keys[s] = key;
     a.vals[s] = (uint32_t)s;
@@ -216,6 +218,8 @@ struct SegArgs {
   recemb_optim_params hp;
   uint32_t* out_keys;     // [2 * chunks]
   float* out_partials;    // [2 * chunks, dim]
+  const uint32_t* flag_in;  // level >= 1: non-zero iff the previous level emitted a record
+  uint32_t* flag_out;
 };
 
 template <int G>
@@ -223,6 +227,21 @@ __device__ __forceinline__ float masked_group_sum(float v, uint32_t mask) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
+}
+
+// The optimizer math is a few flops per 16 bytes moved, but at HBM speed the SM has only
+// ~96 issue slots per 512-byte warp access: IEEE sqrt/div sequences (~20 instructions per
+// element) would make the update instruction-bound.  MUFU-based sqrt / reciprocal are
+// accurate to ~2 ulp, far inside the 1e-5 parity tolerance on updated weights.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 template <int G, int V, typename WT>
@@ -269,7 +288,7 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           s[e] += g[j][e] * g[j][e];
-          w[j][e] += (-hp.lr * g[j][e]) / (sqrtf(s[e]) + hp.eps);
+          w[j][e] += fast_div(-hp.lr * g[j][e], fast_sqrt(s[e]) + hp.eps);
         }
         store_quad<float>(srow + q * 4, s);
       }
@@ -282,18 +301,18 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
       for (int e = 0; e < 4; ++e) ss += g[j][e] * g[j][e];  // lanes past the row hold zeros
     ss = masked_group_sum<G>(ss, gmask) / (float)a.dim;
     const float s_new = a.state1[row] + ss;
-    const float denom = sqrtf(s_new) + hp.eps;
+    const float inv = fast_div(-hp.lr, fast_sqrt(s_new) + hp.eps);
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[j][e] += (-hp.lr * g[j][e]) / denom;
+      for (int e = 0; e < 4; ++e) w[j][e] += g[j][e] * inv;
     __syncwarp(gmask);  // every lane has read state1[row] before lane 0 overwrites it
     if (lig == 0) a.state1[row] = s_new;
   } else {  // ADAM / ADAMW, lazy: only touched rows move
     float* mrow = a.state1 + (int64_t)row * a.dim;
     float* vrow = a.state2 + (int64_t)row * a.dim;
     const float step_size = hp.lr / hp.bias_correction1;
-    const float bc2_sqrt = sqrtf(hp.bias_correction2);
+    const float inv_bc2_sqrt = 1.f / sqrtf(hp.bias_correction2);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int q = j * G + lig;
@@ -306,8 +325,8 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
           if (a.update == RECEMB_UPD_ADAMW) w[j][e] *= (1.f - hp.lr * hp.weight_decay);
           m[e] = hp.beta1 * m[e] + (1.f - hp.beta1) * g[j][e];
           v[e] = hp.beta2 * v[e] + (1.f - hp.beta2) * g[j][e] * g[j][e];
-          const float denom = sqrtf(v[e]) / bc2_sqrt + hp.eps;
-          w[j][e] -= step_size * (m[e] / denom);
+          const float denom = fast_sqrt(v[e]) * inv_bc2_sqrt + hp.eps;
+          w[j][e] -= step_size * fast_div(m[e], denom);
         }
         store_quad<float>(mrow + q * 4, m);
         store_quad<float>(vrow + q * 4, v);
@@ -321,25 +340,87 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
   }
 }
 
-template <int G, int V, typename GT, typename WT, bool L0>
-__global__ void __launch_bounds__(kBwdThreads, (V == 1) ? 3 : (V == 2 ? 2 : 1)) seg_kernel(const SegArgs a) {
-  constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);
+// One group of G lanes walks CH consecutive sorted entries B at a time.  While batch b is
+// being reduced, the rows batch b+1 will touch (its gradient rows and, for every run that
+// ends inside it, the table / optimizer-state rows) are pulled into L2 with prefetch.global.L2,
+// so the dependent loads of the walk hit L2 instead of paying a DRAM round trip each.
+//
+// Records: chunk c leaves at most two (row, partial) records for the next level --
+// leading(c) at index 2c-1 (its first run continues from chunk c-1) and trailing(c) at 2c
+// (its last run continues into chunk c+1).  The two halves of a run cut by ONE boundary are
+// therefore the aligned pair (2c, 2c+1): the next level closes them inside one chunk, and
+// only runs longer than a chunk reach the levels above (which exit on an empty-level flag).
+template <int G, int V, typename GT, typename WT, bool L0, int CH, int B, int MINB>
+__global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a) {
+  if (!L0 && *a.flag_in == 0) return;  // the previous level emitted nothing
   constexpr int GROUPS = kBwdThreads / G;
   const int lane = threadIdx.x & 31;
   const int lig = lane % G;
   const int gi_warp = lane / G;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi_warp * G));
   const int64_t chunk = (int64_t)blockIdx.x * GROUPS + threadIdx.x / G;
-  const int64_t start = chunk * kChunk;
+  const int64_t start = chunk * CH;
   if (start >= a.n) return;
-  const int64_t end = min(start + (int64_t)kChunk, a.n);
+  const int64_t end = min(start + (int64_t)CH, a.n);
+  const int64_t num_chunks = (a.n + CH - 1) / CH;
 
   if (lig == 0) {
+    if (chunk > 0) a.out_keys[2 * chunk - 1] = kNoKey;
     a.out_keys[2 * chunk] = kNoKey;
-    a.out_keys[2 * chunk + 1] = kNoKey;
+    if (chunk == num_chunks - 1) a.out_keys[2 * chunk + 1] = kNoKey;
   }
 
-  uint32_t cur = a.keys[start];
+  const GT* grad = reinterpret_cast<const GT*>(a.grad);
+  const WT* table = reinterpret_cast<const WT*>(a.table);
+  const bool pf_w = a.update != RECEMB_UPD_DENSE_GRAD;
+  const bool pf_s1 = a.update == RECEMB_UPD_ADAGRAD || a.update >= RECEMB_UPD_ADAM;
+  const bool pf_s2 = a.update >= RECEMB_UPD_ADAM;
+
+  // keys of entries [e0, e0+B] (one look-ahead) and slots of [e0, e0+B)
+  auto load_meta = [&](int64_t e0, uint32_t(&kk)[B + 1], uint32_t(&ss)[B]) {
+#pragma unroll
+    for (int u = 0; u <= B; ++u) {
+      const int64_t i = e0 + u;
+      const bool in = (u < B) ? (i < end) : (i < a.n);
+      kk[u] = in ? a.keys[i] : kNoKey;
+      if (u < B) ss[u] = (L0 && in) ? a.slots[i] : 0u;
+    }
+  };
+  auto grad_row_of = [&](int64_t i, uint32_t slot) -> int64_t {
+    if (!L0) return i;
+    return a.slots_per_grad_row > 1 ? (int64_t)(slot / (uint32_t)a.slots_per_grad_row) : (int64_t)slot;
+  };
+  auto prefetch_batch = [&](int64_t e0, const uint32_t(&kk)[B + 1], const uint32_t(&ss)[B]) {
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      if (kk[u] < a.sentinel) {
+        const GT* src = grad + grad_row_of(e0 + u, ss[u]) * a.dim;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int q = j * G + lig;
+          if (q < a.quads) prefetch_l2(src + q * 4);
+        }
+        if (pf_w && kk[u + 1] != kk[u]) {  // this run ends here: its row will be updated
+          const int64_t off = (int64_t)kk[u] * a.dim;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const int q = j * G + lig;
+            if (q < a.quads) {
+              prefetch_l2(table + off + q * 4);
+              if (pf_s1) prefetch_l2(a.state1 + off + q * 4);
+              if (pf_s2) prefetch_l2(a.state2 + off + q * 4);
+            }
+          }
+        }
+      }
+    }
+  };
+
+  uint32_t k[B + 1], sl[B];
+  load_meta(start, k, sl);
+  prefetch_batch(start, k, sl);
+
+  uint32_t cur = k[0];
   const bool left_open = start > 0 && a.keys[start - 1] == cur;
   bool first = true;
   float acc[V][4];
@@ -354,14 +435,17 @@ __global__ void __launch_bounds__(kBwdThreads, (V == 1) ? 3 : (V == 2 ? 2 : 1)) 
       apply_row<G, V, WT>(a, key, acc, lig, gmask);
       return;
     }
-    const int64_t rec = 2 * chunk + (leading ? 0 : 1);
+    const int64_t rec = leading ? 2 * chunk - 1 : 2 * chunk;
     float* dst = a.out_partials + rec * a.dim;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int q = j * G + lig;
       if (q < a.quads) store_quad<float>(dst + q * 4, acc[j]);
     }
-    if (lig == 0) a.out_keys[rec] = key;
+    if (lig == 0) {
+      a.out_keys[rec] = key;
+      *a.flag_out = 1u;
+    }
     if (leading && trailing) {  // the whole chunk is one run open on both sides
       float z[4] = {0.f, 0.f, 0.f, 0.f};
       float* dst2 = a.out_partials + (rec + 1) * a.dim;
@@ -374,31 +458,31 @@ __global__ void __launch_bounds__(kBwdThreads, (V == 1) ? 3 : (V == 2 ? 2 : 1)) 
     }
   };
 
-  for (int64_t e0 = start; e0 < end; e0 += BATCH) {
-    uint32_t k[BATCH];
-    float g[BATCH][V][4];
-    float wt[BATCH];
+  for (int64_t e0 = start; e0 < end; e0 += B) {
+    // (a) meta-data of the next batch (L1 hits: 32 keys share a line) and its L2 prefetch
+    uint32_t kn[B + 1], sn[B];
+    const bool more = e0 + B < end;
+    if (more) {
+      load_meta(e0 + B, kn, sn);
+      prefetch_batch(e0 + B, kn, sn);
+    }
+    // (b) gradient rows of this batch (L2 hits after the first batch)
+    float g[B][V][4];
+    float wt[B];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
-      const int64_t i = e0 + u;
-      k[u] = (i < end) ? a.keys[i] : kNoKey;
+    for (int u = 0; u < B; ++u) {
       wt[u] = 1.f;
 #pragma unroll
       for (int j = 0; j < V; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) g[u][j][e] = 0.f;
       if (k[u] < a.sentinel) {
-        int64_t grow;
+        const int64_t grow = grad_row_of(e0 + u, sl[u]);
         if (L0) {
-          const uint32_t slot = a.slots[i];
-          grow = (a.slots_per_grad_row > 1) ? (int64_t)(slot / (uint32_t)a.slots_per_grad_row)
-                                            : (int64_t)slot;
-          if (a.slot_weight) wt[u] = a.slot_weight[slot];
+          if (a.slot_weight) wt[u] = a.slot_weight[sl[u]];
           if (a.grad_row_scale) wt[u] *= a.grad_row_scale[grow];
-        } else {
-          grow = i;
         }
-        const GT* src = reinterpret_cast<const GT*>(a.grad) + grow * a.dim;
+        const GT* src = grad + grow * a.dim;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const int q = j * G + lig;
@@ -406,8 +490,9 @@ __global__ void __launch_bounds__(kBwdThreads, (V == 1) ? 3 : (V == 2 ? 2 : 1)) 
         }
       }
     }
+    // (c) walk
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
+    for (int u = 0; u < B; ++u) {
       if (e0 + u < end) {
         if (k[u] != cur) {
           flush(cur, first && left_open, false);
@@ -433,6 +518,12 @@ __global__ void __launch_bounds__(kBwdThreads, (V == 1) ? 3 : (V == 2 ? 2 : 1)) 
         }
       }
     }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u <= B; ++u) k[u] = kn[u];
+#pragma unroll
+      for (int u = 0; u < B; ++u) sl[u] = sn[u];
+    }
   }
   const bool right_open = end < a.n && a.keys[end] == cur;
   flush(cur, first && left_open, right_open);
@@ -453,18 +544,62 @@ static bool pick_quads(int quads, QuadShape* s) {
   return true;
 }
 
-#define SEG_GV(G_, V_)                                                                  \
-  if (shape.G == G_ && shape.V == V_) {                                                 \
-    const int64_t chunks = (a.n + kChunk - 1) / kChunk;                                 \
-    const int groups = kBwdThreads / G_;                                                \
-    const int64_t grid = (chunks + groups - 1) / groups;                                \
-    seg_kernel<G_, V_, GT, WT, L0><<<(unsigned)grid, kBwdThreads, 0, s>>>(a);           \
-    launched = true;                                                                    \
+#ifndef RECEMB_CHUNK0
+#define RECEMB_CHUNK0 64
+#endif
+constexpr int kChunk0 = RECEMB_CHUNK0;  // sorted entries per group at level 0
+constexpr int kChunkN = 32;  // records per group at levels >= 1
+
+#define SEG_GV(G_, V_)                                                                          \
+  if (shape.G == G_ && shape.V == V_) {                                                         \
+    constexpr int CH = L0 ? kChunk0 : kChunkN;                                                  \
+    constexpr int B = (V_ == 1) ? 2 : 1;                                                        \
+    constexpr int MINB = (V_ == 1) ? 4 : (V_ == 2 ? 2 : 1);                                     \
+    const int64_t chunks = (a.n + CH - 1) / CH;                                                 \
+    const int groups = kBwdThreads / G_;                                                        \
+    const int64_t grid = (chunks + groups - 1) / groups;                                        \
+    seg_kernel<G_, V_, GT, WT, L0, CH, B, MINB><<<(unsigned)grid, kBwdThreads, 0, s>>>(a);      \
+    launched = true;                                                                            \
   }
+
+// Tuning aid (RECEMB_SEG_TUNE="B,MINB,CH"): alternative instantiations of the headline shape
+// (256-byte fp32 rows, level 0) so one GPU session can compare them.  Unset = default.
+// NOTE: CH must equal kChunk0 for correctness of the level sizing, so CH variants are only
+// compiled when they match (the chunk sweep is done by rebuilding with another kChunk0).
+template <int B, int MINB>
+static void launch_tuned(const SegArgs& a, cudaStream_t s) {
+  const int64_t chunks = (a.n + kChunk0 - 1) / kChunk0;
+  const int64_t grid = (chunks + 15) / 16;
+  seg_kernel<16, 1, float, float, true, kChunk0, B, MINB><<<(unsigned)grid, kBwdThreads, 0, s>>>(a);
+}
+static bool try_tuned(const SegArgs& a, cudaStream_t s) {
+  static int tb = -1, tm = -1;
+  if (tb == -1) {
+    tb = 0;
+    const char* e = getenv("RECEMB_SEG_TUNE");
+    if (e && sscanf(e, "%d,%d", &tb, &tm) != 2) tb = 0;
+  }
+  if (tb == 0) return false;
+  if (tb == 4 && tm == 4) launch_tuned<4, 4>(a, s);
+  else if (tb == 4 && tm == 3) launch_tuned<4, 3>(a, s);
+  else if (tb == 2 && tm == 4) launch_tuned<2, 4>(a, s);
+  else if (tb == 2 && tm == 5) launch_tuned<2, 5>(a, s);
+  else if (tb == 2 && tm == 6) launch_tuned<2, 6>(a, s);
+  else if (tb == 1 && tm == 4) launch_tuned<1, 4>(a, s);
+  else if (tb == 1 && tm == 6) launch_tuned<1, 6>(a, s);
+  else if (tb == 1 && tm == 8) launch_tuned<1, 8>(a, s);
+  else return false;
+  return true;
+}
 
 template <typename GT, typename WT, bool L0>
 static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
   bool launched = false;
+  if (L0 && std::is_same<GT, float>::value && std::is_same<WT, float>::value && shape.G == 16 &&
+      shape.V == 1 && try_tuned(a, s)) {
+    RECEMB_LAUNCHED();
+    return RECEMB_OK;
+  }
   SEG_GV(1, 1) SEG_GV(2, 1) SEG_GV(4, 1) SEG_GV(8, 1) SEG_GV(16, 1) SEG_GV(32, 1) SEG_GV(32, 2)
   SEG_GV(32, 4) SEG_GV(32, 8)
   if (!launched) {
@@ -475,16 +610,22 @@ static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
   return RECEMB_OK;
 }
 
-// level sizes: n_0 = n_slots, n_{l+1} = 2 * ceil(n_l / kChunk), until n_l <= kChunk
+// level sizes: n_0 = n_slots, n_1 = 2*ceil(n_0/kChunk0), n_{l+1} = 2*ceil(n_l/kChunkN);
+// the last level is a single chunk (no boundary => nothing can stay open).
 static int level_sizes(int64_t n0, int64_t* sizes, int max_levels) {
   int L = 0;
   int64_t n = n0;
   sizes[L++] = n;
-  while (n > kChunk && L < max_levels) {
-    n = 2 * ((n + kChunk - 1) / kChunk);
+  while (n > (L == 1 ? kChunk0 : kChunkN) && L < max_levels) {
+    const int ch = (L == 1) ? kChunk0 : kChunkN;
+    n = 2 * ((n + ch - 1) / ch);
     sizes[L++] = n;
   }
   return L;
+}
+static int64_t records_of(int64_t n, int level) {
+  const int ch = level == 0 ? kChunk0 : kChunkN;
+  return 2 * ((n + ch - 1) / ch);
 }
 constexpr int kMaxLevels = 16;
 
@@ -534,8 +675,8 @@ extern "C" size_t recemb_bwd_plan_bytes(int64_t n_slots, int64_t num_rows) {
   return L.total;
 }
 
-extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_per_id,
-                               int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad,
+extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_per_table,
+                               int32_t slots_per_id, int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad,
                                int64_t pad_id, int64_t pad_row, int32_t bag_size,
                                const int32_t* lengths, int32_t last_n, void* plan,
                                size_t plan_bytes, int device, recemb_stream_t stream) {
@@ -543,8 +684,11 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_
   RECEMB_CHECK_ARG(plan != nullptr && plan_bytes >= kCounterBytes, "plan buffer missing");
   RECEMB_CHECK_ARG((uintptr_t)plan % 256 == 0, "plan buffer must be 256-byte aligned");
   RECEMB_CHECK_ARG(num_rows >= 1, "num_rows < 1");
-  RECEMB_UNSUPPORTED(num_rows < 0xfffffff0ll, "num_rows %lld does not fit 32-bit sort keys",
-                     (long long)num_rows);
+  RECEMB_CHECK_ARG(ids_per_table >= 0, "ids_per_table < 0");
+  const int64_t n_tables = ids_per_table > 0 ? (n_ids + ids_per_table - 1) / ids_per_table : 1;
+  const int64_t total_rows = num_rows * (n_tables > 0 ? n_tables : 1);
+  RECEMB_UNSUPPORTED(total_rows < 0xfffffff0ll, "%lld rows do not fit 32-bit sort keys",
+                     (long long)total_rows);
   const int64_t n = n_ids * slots_per_id;
   RECEMB_UNSUPPORTED(n < 0x7fffffffll, "%lld slots do not fit 32-bit slot ids", (long long)n);
   RECEMB_CHECK_ARG(slots_per_id == 1 || hash_mode == RECEMB_HASH_ROTL_FLOORMOD,
@@ -555,11 +699,10 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_
   RECEMB_CUDA(g.err);
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)plan;
-  RECEMB_CUDA(cudaMemsetAsync(base, 0, kCounterBytes, s));
   if (n == 0) return RECEMB_OK;
   RECEMB_CHECK_ARG(ids != nullptr, "ids null");
   PlanLayout L;
-  RECEMB_CUDA(plan_layout(n, num_rows, &L));
+  RECEMB_CUDA(plan_layout(n, total_rows, &L));
   if (plan_bytes < L.total) {
     set_error("plan buffer %zu < required %zu", plan_bytes, L.total);
     return RECEMB_ERR_WORKSPACE;
@@ -568,7 +711,7 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_
   a.ids = ids;
   a.n_slots = n;
   a.slots_per_id = slots_per_id;
-  int rc = make_hash_spec(hash_mode, num_rows, slots_per_id > 1 ? 0 : hash_arg, &a.h);
+  int rc = make_hash_spec(hash_mode, num_rows, slots_per_id > 1 ? 0 : hash_arg, &a.h, ids_per_table);
   if (rc) return rc;
   a.zero_pad = zero_pad;
   a.pad_id = pad_id;
@@ -576,7 +719,7 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_
   a.bag_size = bag_size;
   a.lengths = lengths;
   a.last_n = last_n;
-  a.sentinel = (uint32_t)num_rows;
+  a.sentinel = (uint32_t)total_rows;
   a.keys = (uint32_t*)(base + L.off_keys_in);
   a.vals = (uint32_t*)(base + L.off_vals_in);
   const int sms = sm_count(device);
@@ -589,8 +732,26 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int32_t slots_
       base + L.off_temp, temp, (const uint32_t*)a.keys, (uint32_t*)(base + L.off_keys_out),
       (const uint32_t*)a.vals, (uint32_t*)(base + L.off_vals_out), (int64_t)n, 0, L.key_bits, s));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);  // the sort is >= 1 launch; counted once
+  return RECEMB_OK;
+}
+
+extern "C" int recemb_plan_count(void* plan, size_t plan_bytes, int64_t n_slots, int64_t num_rows,
+                                 int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(plan != nullptr && n_slots >= 0, "bad plan / n_slots");
+  const size_t arr = align_up((size_t)n_slots * 4, 256);
+  RECEMB_CHECK_ARG(plan_bytes >= kCounterBytes + 4 * arr, "plan buffer too small for n_slots");
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  char* base = (char*)plan;
+  RECEMB_CUDA(cudaMemsetAsync(base, 0, kCounterBytes, s));
+  if (n_slots == 0) return RECEMB_OK;
+  int64_t grid = (n_slots + kBwdThreads - 1) / kBwdThreads;
+  const int64_t cap = (int64_t)sm_count(device) * 16;
+  if (grid > cap) grid = cap;
   plan_count_kernel<<<(unsigned)grid, kBwdThreads, 0, s>>>(
-      (const uint32_t*)(base + L.off_keys_out), n, a.sentinel, (unsigned long long*)base);
+      (const uint32_t*)(base + kCounterBytes + 2 * arr), n_slots, (uint32_t)num_rows,
+      (unsigned long long*)base);
   RECEMB_LAUNCHED();
   return RECEMB_OK;
 }
@@ -623,7 +784,7 @@ extern "C" size_t recemb_bwd_apply_workspace_bytes(int64_t n_slots, int32_t dim)
     total += align_up((size_t)sizes[l] * dim * 4, 256);
   }
   // the last level also writes (never-read) records
-  const int64_t last = 2 * ((sizes[L - 1] + kChunk - 1) / kChunk);
+  const int64_t last = records_of(sizes[L - 1], L - 1);
   total += align_up((size_t)last * 4, 256) + align_up((size_t)last * dim * 4, 256);
   return total;
 }
@@ -674,6 +835,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
 
   int64_t sizes[kMaxLevels];
   const int L = level_sizes(n, sizes, kMaxLevels);
+  RECEMB_CUDA(cudaMemsetAsync(workspace, 0, 256, s));  // per-level "records emitted" flags
   const char* pbase = (const char*)plan;
   char* w = (char*)workspace;
   size_t woff = 256;
@@ -696,7 +858,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
   const uint32_t* in_slots = (const uint32_t*)(pbase + kCounterBytes + 3 * arr);
   const void* in_grad = grad;
   for (int l = 0; l < L; ++l) {
-    const int64_t recs = 2 * ((sizes[l] + kChunk - 1) / kChunk);
+    const int64_t recs = records_of(sizes[l], l);
     uint32_t* out_keys = (uint32_t*)(w + woff);
     woff += align_up((size_t)recs * 4, 256);
     float* out_part = (float*)(w + woff);
@@ -707,6 +869,8 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
     a.grad = in_grad;
     a.out_keys = out_keys;
     a.out_partials = out_part;
+    a.flag_in = (const uint32_t*)w + l;  // flags live in the first 256 bytes of the workspace
+    a.flag_out = (uint32_t*)w + l + 1;
     int rc;
     if (l == 0 && t_ev_start) cudaEventRecord(t_ev_start, s);
     if (l == 0) {

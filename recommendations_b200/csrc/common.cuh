@@ -109,9 +109,18 @@ struct HashSpec {
   int shift;     // ROTL_FLOORMOD: rotation c
   ModN mod_rows; // FLOORMOD / ROTL: num_rows ; QR: d
   ModN mod_sq;   // QR: d*d
+  // table-batched lookups: lookup i belongs to table t = i / ids_per_table and its row is
+  // offset by t * rows_per_table into one stacked [T * rows_per_table, dim] table (0 = off)
+  uint32_t ids_per_table;
+  int64_t rows_per_table;
 };
 
-int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out);
+int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,
+                   int64_t ids_per_table = 0);
+
+__device__ __forceinline__ int64_t table_offset(int64_t i, const HashSpec& h) {
+  return h.ids_per_table ? (int64_t)((uint32_t)i / h.ids_per_table) * h.rows_per_table : 0;
+}
 
 // (x << c) | (x >> (64-c)) with wrapping << and ARITHMETIC >> on signed int64:
 // a true rotate only for x >= 0 (commons/layers.py:182).

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
       const int64_t id = rows[i];
       const bool pad = a.zero_pad && id == a.pad_id;
       if (TWO) s_rows2[i] = pad ? -1 : row_of(id, a.h2);
-      rows[i] = pad ? -1 : row_of(id, a.h1);
+      rows[i] = pad ? -1 : row_of(id, a.h1) + table_offset(tile * kTileIds + i, a.h1);
     }
     __syncthreads();
 
@@ -566,9 +566,10 @@ extern "C" int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, in
 
 extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2,
                                  int64_t num_rows2, int32_t dim, int dtype, const int64_t* ids,
-                                 int64_t n, int hash_mode, int hash_mode2, int64_t hash_arg,
-                                 int epilogue, int zero_pad, int64_t pad_id, void* out,
-                                 float* inv_norm_out, int device, recemb_stream_t stream) {
+                                 int64_t n, int64_t ids_per_table, int hash_mode, int hash_mode2,
+                                 int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
+                                 void* out, float* inv_norm_out, int device,
+                                 recemb_stream_t stream) {
   RECEMB_CHECK_ARG(n >= 0, "n < 0");
   if (n == 0) return RECEMB_OK;
   RECEMB_CHECK_ARG(table && ids && out, "null pointer");
@@ -581,7 +582,9 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   if (rc) return rc;
   RowShape shape;
   RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
-  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1);
+  RECEMB_CHECK_ARG(ids_per_table == 0 || table2 == nullptr, "table-batched lookups take one table");
+  RECEMB_UNSUPPORTED(ids_per_table == 0 || n < 0xffffffffll, "too many lookups for table-batched mode");
+  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1, ids_per_table);
   if (rc) return rc;
   a.h2 = a.h1;
   if (table2) {

@@ -31,10 +31,14 @@ int sm_count(int device) {
   return cached[device];
 }
 
-int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out) {
+int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,
+                   int64_t ids_per_table) {
   HashSpec h;
   h.mode = hash_mode;
   h.shift = 0;
+  RECEMB_CHECK_ARG(ids_per_table >= 0 && ids_per_table < 0xffffffffll, "ids_per_table out of range");
+  h.ids_per_table = (uint32_t)ids_per_table;
+  h.rows_per_table = num_rows;
   h.mod_rows = make_modn(1);
   h.mod_sq = make_modn(1);
   switch (hash_mode) {
@@ -74,7 +78,8 @@ extern "C" int recemb_abi_version(void) { return RECEMB_ABI_VERSION; }
 extern "C" const char* recemb_last_error(void) { return t_error; }
 extern "C" uint64_t recemb_launch_count(void) { return g_launch_count.load(); }
 
-extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t* ids_dev_scratch,
+extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t ids_per_table,
+                                     int64_t* ids_dev_scratch,
                                      void* table, int64_t num_rows, int32_t dim, int dtype,
                                      void* out, const void* grad, int update, void* state1,
                                      void* state2, const recemb_optim_params* hp_host, void* plan,
@@ -88,17 +93,22 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   if (n > 0)
     RECEMB_CUDA(cudaMemcpyAsync(ids_dev_scratch, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
   int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
-                             RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
+                             ids_per_table, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
                              stream);
   if (rc) return rc;
-  rc = recemb_bwd_plan(ids_dev_scratch, n, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0, 0, -1, 0,
-                       nullptr, 0, plan, plan_bytes, device, stream);
+  rc = recemb_bwd_plan(ids_dev_scratch, n, ids_per_table, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
+                       0, -1, 0, nullptr, 0, plan, plan_bytes, device, stream);
   if (rc) return rc;
+  const int64_t total_rows =
+      num_rows * (ids_per_table > 0 ? (n + ids_per_table - 1) / ids_per_table : 1);
   rc = recemb_bwd_apply(plan, plan_bytes, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
-                        dtype, num_rows, state1, state2, hp_host, workspace, workspace_bytes, device,
+                        dtype, total_rows, state1, state2, hp_host, workspace, workspace_bytes, device,
                         stream);
   if (rc) return rc;
-  if (counters_host)
+  if (counters_host) {
+    rc = recemb_plan_count(plan, plan_bytes, n, total_rows, device, stream);
+    if (rc) return rc;
     RECEMB_CUDA(cudaMemcpyAsync(counters_host, plan, 16, cudaMemcpyDeviceToHost, s));
+  }
   return RECEMB_OK;
 }

@@ -39,7 +39,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
                hash_arg: int = 0, table2: Optional[torch.Tensor] = None,
                hash_mode2: int = N.HASH_FLOORMOD, epilogue: int = N.EPI_NONE,
                zero_pad: bool = False, pad_id: int = 0, want_inv_norm: bool = False,
-               out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               out: Optional[torch.Tensor] = None, ids_per_table: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     flat = _flat_ids(ids)
     dev = N.require_cuda(table, table2, flat, out)
     n, dim = flat.numel(), table.shape[1]
@@ -50,9 +50,15 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
     inv = None
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
+    rows_per_table = table.shape[0]
+    if ids_per_table:
+        n_tables = -(-n // ids_per_table)
+        if table.shape[0] % n_tables:
+            raise N.NativeError("stacked table rows are not a multiple of the number of tables")
+        rows_per_table = table.shape[0] // n_tables
     N.check(N.load().recemb_gather_fwd(
-        N.ptr(table), table.shape[0], N.ptr(table2), 0 if table2 is None else table2.shape[0], dim,
-        N.dtype_code(table.dtype), N.ptr(flat), n, hash_mode, hash_mode2, hash_arg, epilogue,
+        N.ptr(table), rows_per_table, N.ptr(table2), 0 if table2 is None else table2.shape[0], dim,
+        N.dtype_code(table.dtype), N.ptr(flat), n, ids_per_table, hash_mode, hash_mode2, hash_arg, epilogue,
         int(zero_pad), pad_id, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_gather_fwd")
     return out.view(*ids.shape, dim), inv
 
@@ -109,23 +115,27 @@ class BackwardPlan:
     def build(ids: torch.Tensor, *, num_rows: int, hash_mode: int = N.HASH_FLOORMOD,
               hash_arg: int = 0, slots_per_id: int = 1, zero_pad: bool = False, pad_id: int = 0,
               pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
-              last_n: int = 0, buf: Optional[torch.Tensor] = None) -> "BackwardPlan":
+              last_n: int = 0, buf: Optional[torch.Tensor] = None,
+              ids_per_table: int = 0) -> "BackwardPlan":
+        """num_rows is rows PER TABLE; with ids_per_table > 0 the plan covers the stacked table
+        of ceil(n_ids / ids_per_table) tables and `self.num_rows` is the stacked total."""
         flat = _flat_ids(ids)
         if lengths is not None:
             lengths = lengths.to(torch.int32).contiguous()
         dev = N.require_cuda(flat, lengths)
         n_slots = flat.numel() * slots_per_id
         lib = N.load()
-        need = int(lib.recemb_bwd_plan_bytes(n_slots, num_rows))
+        total_rows = num_rows * (-(-flat.numel() // ids_per_table) if ids_per_table else 1)
+        need = int(lib.recemb_bwd_plan_bytes(n_slots, total_rows))
         if need == 0:
             N.check(-2, "recemb_bwd_plan_bytes")
         if buf is None or buf.numel() < need:
             buf = torch.empty((need,), dtype=torch.uint8, device=flat.device)
-        N.check(lib.recemb_bwd_plan(N.ptr(flat), flat.numel(), slots_per_id, hash_mode, num_rows,
+        N.check(lib.recemb_bwd_plan(N.ptr(flat), flat.numel(), ids_per_table, slots_per_id, hash_mode, num_rows,
                                     hash_arg, int(zero_pad), pad_id, pad_row, bag_size,
                                     N.ptr(lengths), last_n, N.ptr(buf), buf.numel(), dev,
                                     N.stream_ptr(dev)), "recemb_bwd_plan")
-        return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=num_rows, slots_per_id=slots_per_id)
+        return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=total_rows, slots_per_id=slots_per_id)
 
     def _arr(self, which: int) -> torch.Tensor:
         arr_bytes = (self.n_slots * 4 + 255) // 256 * 256
@@ -143,7 +153,10 @@ class BackwardPlan:
 
     @property
     def counters(self) -> torch.Tensor:
-        """device int64 [2] = (valid slots, distinct rows)."""
+        """device int64 [2] = (valid slots, distinct rows); counted on demand."""
+        dev = N.require_cuda(self.buf)
+        N.check(N.load().recemb_plan_count(N.ptr(self.buf), self.buf.numel(), self.n_slots,
+                                           self.num_rows, dev, N.stream_ptr(dev)), "recemb_plan_count")
         return self.buf[:16].view(torch.int64)
 
 
