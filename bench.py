@@ -44,6 +44,16 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    last `ncu --set full` capture committed under profiles/ (null if none)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())["seg_kernel_level0_dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def host_ids(t: int, rank: int = 0) -> torch.Tensor:
     g = torch.Generator().manual_seed(1000 + t + 100 * rank)
     return torch.randint(-2 ** 63, 2 ** 63 - 1, (BATCH * HIST,), generator=g, dtype=torch.int64)
@@ -59,7 +69,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -245,7 +255,7 @@ def run_b200(args):
         "bound": "hbm", "kernel": "seg_kernel<16,1,float,float,L0> (segmented reduce + fused Adagrad), "
                                   "one launch per step over all 10 tables",
         "achieved": apply_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-        "frac": apply_gbs / peak, "traffic": None,
+        "frac": apply_gbs / peak, "traffic": ncu_traffic(),
         "algorithmic_bytes_per_launch": apply_bytes, "avg_launch_ms": statistics.mean(apply_ms),
         "gather_kernel": {"achieved": gather_gbs, "frac": gather_gbs / peak,
                           "algorithmic_bytes_per_launch": gather_bytes,
@@ -286,61 +296,76 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier,
-            parts: int = 5):
-    """Same step through recemb_flat_step_host: ids start in PINNED HOST memory every step.  The
-    10 tables go through in `parts` table-batched calls alternating between two streams, so the
-    H2D copy of one part overlaps the kernels of the previous one; the step's result (valid /
-    unique counters per part) is read back to the host."""
+def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier):
+    """Same step through recemb_flat_step_host (one table-batched call per step): the step's ids
+    start in PINNED HOST memory and are copied inside the timed region; the step's result
+    (valid / unique counters) is read back by the host every step.  Two streams alternate
+    between steps so the H2D copy of step s+1 runs while step s computes
+    (wait_event_after_copy orders the kernels); `serial` is the same without that overlap."""
     import ctypes as C
     import torch.distributed as dist
     n = BATCH * HIST
-    tpp = T_TABLES // parts                      # tables per part
-    n_part, rows_part = tpp * n, tpp * ROWS
-    plan_bytes = int(lib.recemb_bwd_plan_bytes(n_part, rows_part))
-    ws_bytes = int(lib.recemb_bwd_apply_workspace_bytes(n_part, DIM))
+    n_all, rows_all = T_TABLES * n, T_TABLES * ROWS
+    plan_bytes = int(lib.recemb_bwd_plan_bytes(n_all, rows_all))
+    ws_bytes = int(lib.recemb_bwd_apply_workspace_bytes(n_all, DIM))
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    scratch = [torch.empty(n_part, dtype=torch.int64, device=dev) for _ in range(2)]
+    scratch = [torch.empty(n_all, dtype=torch.int64, device=dev) for _ in range(2)]
     plans = [torch.empty(plan_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-    counters = torch.zeros(parts, 2, dtype=torch.int64).pin_memory()
+    counters = torch.zeros(2, 2, dtype=torch.int64).pin_memory()
     done = [torch.cuda.Event() for _ in range(2)]
+    for i in range(2):
+        done[i].record(streams[i])  # materialise the cudaEvent_t handles
 
-    def step():
-        for p in range(parts):
-            s = streams[p % 2]
-            s.wait_event(done[p % 2])  # scratch / plan / workspace of this slot are free again
-            N.check(lib.recemb_flat_step_host(
-                ids_host[p * n_part:].data_ptr(), n_part, n, scratch[p % 2].data_ptr(),
-                table_all[p * rows_part:].data_ptr(), ROWS, DIM, N.F32, outs[p * n_part:].data_ptr(),
-                grads[p * n_part:].data_ptr(), N.UPD_ADAGRAD, state_all[p * rows_part:].data_ptr(), None,
-                C.byref(hp), plans[p % 2].data_ptr(), plan_bytes, wss[p % 2].data_ptr(), ws_bytes,
-                counters[p].data_ptr(), dev.index, s.cuda_stream), "recemb_flat_step_host")
-            done[p % 2].record(s)
-        for s in streams:
-            s.synchronize()  # the host reads the counters: device->host result of the step
+    def enqueue(s, overlap):
+        k = s % 2
+        N.check(lib.recemb_flat_step_host(
+            ids_host.data_ptr(), n_all, n, scratch[k].data_ptr(), table_all.data_ptr(), ROWS, DIM, N.F32,
+            outs.data_ptr(), grads.data_ptr(), N.UPD_ADAGRAD, state_all.data_ptr(), None, C.byref(hp),
+            plans[k].data_ptr(), plan_bytes, wss[k].data_ptr(), ws_bytes, counters[k].data_ptr(),
+            done[1 - k].cuda_event if overlap else None, dev.index, streams[k].cuda_stream),
+            "recemb_flat_step_host")
+        done[k].record(streams[k])
 
-    for _ in range(max(1, args.warmup)):
-        step()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    assert int(counters[:, 0].sum()) == n * T_TABLES, "e2e step did not process every lookup"
-    return {"value": world * n * T_TABLES * args.steps / (ms * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": T_TABLES * n * 8, "d2h_bytes_per_step": parts * 16,
+    def run(steps, overlap):
+        checked = 0
+        for s in range(steps):
+            if not overlap and s > 0:
+                streams[(s - 1) % 2].synchronize()
+            enqueue(s, overlap)
+            if overlap and s > 0:
+                streams[(s - 1) % 2].synchronize()  # host reads step s-1's result
+            if s > 0:
+                checked += int(counters[(s - 1) % 2, 0])
+        streams[(steps - 1) % 2].synchronize()
+        checked += int(counters[(steps - 1) % 2, 0])
+        return checked
+
+    out = {}
+    for name, overlap in (("serial", False), ("pipelined", True)):
+        run(max(2, args.warmup), overlap)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        checked = run(args.steps, overlap)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        assert checked == n_all * args.steps, "e2e steps did not process every lookup"
+        out[name] = (ms, wall)
+    ms, wall = out["pipelined"]
+    return {"value": world * n_all * args.steps / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": n_all * 8, "d2h_bytes_per_step": 16,
             "ms_per_step": ms / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
-            "api": f"recemb_flat_step_host (C ABI, pinned host ids, {parts} table-batched parts on 2 streams)"}
+            "serial_ms_per_step": out["serial"][0] / args.steps,
+            "api": "recemb_flat_step_host (C ABI; pinned host ids in, counters out, every step); H2D of "
+                   "step s+1 overlaps the kernels of step s on a second stream"}
 
 
 def main():

@@ -234,14 +234,17 @@ RECEMB_API int recemb_dot_interaction_bwd(const void* feats, const void* grad_ou
  * into out, backward plan + fused update with grad (device, fp32/bf16 [n, dim]),
  * then counters_host[0..1] = {n_valid, n_unique} are copied back (async on
  * `stream`; the caller synchronises the stream before reading them).  ids_per_table > 0
- * selects the table-batched mode of recemb_gather_fwd (num_rows per table, stacked table). */
+ * selects the table-batched mode of recemb_gather_fwd (num_rows per table, stacked table).
+ * wait_event_after_copy (optional cudaEvent_t): `stream` waits for it after the H2D copy and
+ * before the first kernel, so a caller alternating two streams can copy step s+1's ids while
+ * step s still computes without letting the two steps' kernels overlap. */
 RECEMB_API int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t ids_per_table,
                           int64_t* ids_dev_scratch,
                           void* table, int64_t num_rows, int32_t dim, int dtype, void* out,
                           const void* grad, int update, void* state1, void* state2,
                           const recemb_optim_params* hp_host, void* plan, size_t plan_bytes,
                           void* workspace, size_t workspace_bytes, int64_t* counters_host,
-                          int device, recemb_stream_t stream);
+                          void* wait_event_after_copy, int device, recemb_stream_t stream);
 
 #ifdef __cplusplus
 }

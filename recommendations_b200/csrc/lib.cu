@@ -84,7 +84,8 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
                                      void* out, const void* grad, int update, void* state1,
                                      void* state2, const recemb_optim_params* hp_host, void* plan,
                                      size_t plan_bytes, void* workspace, size_t workspace_bytes,
-                                     int64_t* counters_host, int device, recemb_stream_t stream) {
+                                     int64_t* counters_host, void* wait_event_after_copy, int device,
+                                     recemb_stream_t stream) {
   RECEMB_CHECK_ARG(ids_host && ids_dev_scratch, "null ids");
   RECEMB_CHECK_ARG(n >= 0, "n < 0");
   DeviceGuard g(device);
@@ -92,6 +93,10 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   if (n > 0)
     RECEMB_CUDA(cudaMemcpyAsync(ids_dev_scratch, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  // software pipelining across steps: the copy above may run while the previous step (on
+  // another stream) is still computing; the kernels below must not.
+  if (wait_event_after_copy)
+    RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
   int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
                              ids_per_table, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
                              stream);
