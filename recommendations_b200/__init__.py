@@ -6,11 +6,12 @@ C ABI in include/recemb_b200.h).  Importing the package does not need a GPU; cal
 any op does, and a missing library raises instead of falling back.
 """
 from . import _native
+from .interaction import DotInteraction, dot_interaction
 from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PooledEmbeddingBag,
                      QREmbedding)
 from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
 
 __all__ = [
-    "CosineVectorEmbedding", "EmbeddingTable", "FlatEmbedding", "FusedEmbeddingOptimizer",
+    "CosineVectorEmbedding", "DotInteraction", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
     "FusedOptimizerConfig", "KShiftEmbedding", "PooledEmbeddingBag", "QREmbedding",
 ]
