@@ -88,6 +88,22 @@ enum recemb_update {
   RECEMB_UPD_ADAMW = 5            /* lazy AdamW (models/lthm/sequence/wrapper.py:265), decoupled decay */
 };
 
+/* Where a lookup's row lives.  NULL / all-zero = one unsharded table.
+ *   table batching: T equal-shaped tables stacked as [T * rows, dim]; lookup i uses table
+ *     t = i / ids_per_table (wrapped modulo num_tables when num_tables > 0) and reads row
+ *     t * rows + transform(ids[i]) -- one launch for all tables.
+ *   row-wise sharding: global row r lives on rank r % shard_world at local row r / shard_world;
+ *     `table` is this rank's shard, num_rows stays the GLOBAL count used for hashing, lookups
+ *     owned by other ranks are skipped (forward) / dropped (plan).  With both, the stacked local
+ *     table is [T * local_rows, dim], local_rows = ceil((num_rows - shard_rank) / shard_world). */
+typedef struct recemb_layout {
+  int64_t ids_per_table;
+  int32_t num_tables;
+  int32_t shard_world;
+  int32_t shard_rank;
+  int32_t reserved;
+} recemb_layout;
+
 typedef struct recemb_optim_params {
   float lr;           /* already includes lr_decay / schedule: the host passes clr */
   float eps;
@@ -120,11 +136,9 @@ RECEMB_API int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, in
  * epilogue (QREmbedding: emb_q(q) + emb_r(r), commons/layers.py:115-123):
  * hash_mode applies to `table` and hash_mode2 to `table2`, both with hash_arg.
  * inv_norm_out (optional, fp32 [n]) receives 1/max(||x||,1e-12) for the L2NORM backward.
- * Table-batched mode (ids_per_table > 0): `table` is T tables of num_rows rows stacked as
- * [T * num_rows, dim]; lookup i belongs to table i / ids_per_table and reads row
- * (i / ids_per_table) * num_rows + transform(ids[i]) -- all T tables in one launch. */
+ * `layout` (optional) selects table batching / sharding, see recemb_layout. */
 RECEMB_API int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2, int64_t num_rows2,
-                      int32_t dim, int dtype, const int64_t* ids, int64_t n, int64_t ids_per_table,
+                      int32_t dim, int dtype, const int64_t* ids, int64_t n, const recemb_layout* layout,
                       int hash_mode, int hash_mode2, int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
                       void* out, float* inv_norm_out, int device, recemb_stream_t stream);
 
@@ -145,12 +159,15 @@ RECEMB_API int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
  * (EmbeddingBag padding_idx semantics).  fp32 accumulation in slot order (the CPU
  * EmbeddingBag sum order).  MEAN divides by the number of pooled slots (>=1).
  * Replaces nn.EmbeddingBag(mode='sum') at commons/transformers/layers.py:457,:469.
- * per_slot_weight (optional fp32 [num_bags, bag_size]) = per_sample_weights. */
+ * per_slot_weight (optional fp32 [num_bags, bag_size]) = per_sample_weights.
+ * `layout` (optional): table batching (slot index = bag * bag_size + p) and / or row-wise
+ * sharding -- with sharding `out` is this owner's PARTIAL pool (sum the partials of all owners,
+ * in owner order, for the full result: recemb_sum_partials). */
 RECEMB_API int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
                     const int64_t* ids, int64_t num_bags, int32_t bag_size, const int32_t* lengths,
                     int32_t last_n, const float* per_slot_weight, int hash_mode, int64_t hash_arg,
-                    int pool_mode, int zero_pad, int64_t pad_id, void* out, int device,
-                    recemb_stream_t stream);
+                    int pool_mode, int zero_pad, int64_t pad_id, const recemb_layout* layout,
+                    void* out, int device, recemb_stream_t stream);
 
 /* ---- backward: plan = sort-based dedup (a8, K5/K6) ------------------------ */
 /* A plan turns the lookup slots of one forward call into (row, slot) pairs
@@ -162,13 +179,15 @@ RECEMB_API int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
  * (nn.Embedding padding_idx: that row never receives gradient, commons/layers.py:51);
  * bag_size > 0 and the slot is outside its bag's window (lengths / last_n as in
  * recemb_pool_fwd).
- * Table-batched mode (ids_per_table > 0, as in recemb_gather_fwd): num_rows is per table and
- * the sorted keys are rows of the stacked table, t * num_rows + row; one sort for all tables.
- * The plan lives in caller memory of recemb_bwd_plan_bytes(n_slots, total_rows), with
- * total_rows = num_rows * number_of_tables (also the num_rows to pass to recemb_bwd_apply). */
+ * With a `layout` the sorted keys are rows of the stacked / local table (t * local_rows + local
+ * row); one sort covers all tables.  The plan lives in caller memory of
+ * recemb_bwd_plan_bytes(n_slots, total_rows) with total_rows = recemb_layout_total_rows(...)
+ * (also the num_rows to pass to recemb_bwd_apply). */
+RECEMB_API int64_t recemb_layout_total_rows(int64_t num_rows, const recemb_layout* layout, int64_t n_ids);
+
 RECEMB_API size_t recemb_bwd_plan_bytes(int64_t n_slots, int64_t num_rows);
 
-RECEMB_API int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_per_table,
+RECEMB_API int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, const recemb_layout* layout,
                     int32_t slots_per_id, int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
                     int64_t pad_row, int32_t bag_size, const int32_t* lengths, int32_t last_n,
                     void* plan, size_t plan_bytes, int device, recemb_stream_t stream);
@@ -215,6 +234,13 @@ RECEMB_API int recemb_time_next_apply(void* start_event, void* stop_event);
 RECEMB_API int recemb_epilogue_bwd(const void* grad_out, const void* out, int dtype, const float* inv_norm,
                         int64_t n, int32_t dim, int epilogue, int32_t num_shifts, float* dx,
                         int device, recemb_stream_t stream);
+
+/* ---- row-wise sharding: requester-side reduction (a12) ----------------------- */
+/* out[r, :] = row_scale[r] * sum_{s=0}^{world-1} parts[s, r, :] (fp32 accumulation in owner
+ * order; row_scale optional, e.g. 1/count for MEAN).  parts = the all-to-all receive buffer
+ * [world, rows, dim] of per-owner partial pools produced by recemb_pool_fwd(shard_world>1). */
+RECEMB_API int recemb_sum_partials(const void* parts, int32_t world, int64_t rows, int32_t dim, int dtype,
+                        const float* row_scale, void* out, int device, recemb_stream_t stream);
 
 /* ---- ranker pairwise dot interaction (a11) --------------------------------- */
 /* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:

@@ -43,6 +43,24 @@ class OptimParams(C.Structure):
     ]
 
 
+class Layout(C.Structure):
+    _fields_ = [
+        ("ids_per_table", C.c_int64),
+        ("num_tables", C.c_int32),
+        ("shard_world", C.c_int32),
+        ("shard_rank", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0):
+    """None when nothing is batched / sharded (the C side treats NULL as one plain table)."""
+    if not ids_per_table and shard_world <= 1:
+        return None
+    return Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=shard_world,
+                  shard_rank=shard_rank, reserved=0)
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -59,14 +77,15 @@ SIGNATURES = {
     "recemb_last_error": (C.c_char_p, []),
     "recemb_launch_count": (C.c_uint64, []),
     "recemb_row_index": (_INT, [_P, _I64, _INT, _I64, _I64, _P, _INT, _P]),
-    "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, _I64, _INT, _INT, _I64,
+    "recemb_layout_total_rows": (_I64, [_I64, C.POINTER(Layout), _I64]),
+    "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, C.POINTER(Layout), _INT, _INT, _I64,
                                  _INT, _INT, _I64, _P, _P, _INT, _P]),
     "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _P, _P, _INT, _P]),
     "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,
-                               _INT, _I64, _P, _INT, _P]),
+                               _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
     "recemb_bwd_plan_bytes": (_SZ, [_I64, _I64]),
-    "recemb_bwd_plan": (_INT, [_P, _I64, _I64, _I32, _INT, _I64, _I64, _INT, _I64, _I64, _I32, _P,
-                               _I32, _P, _SZ, _INT, _P]),
+    "recemb_bwd_plan": (_INT, [_P, _I64, C.POINTER(Layout), _I32, _INT, _I64, _I64, _INT, _I64, _I64, _I32,
+                               _P, _I32, _P, _SZ, _INT, _P]),
     "recemb_plan_count": (_INT, [_P, _SZ, _I64, _I64, _INT, _P]),
     "recemb_plan_views": (_INT, [_P, _SZ, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                  C.POINTER(_I64)]),
@@ -75,6 +94,7 @@ SIGNATURES = {
                                 _P, _P, C.POINTER(OptimParams), _P, _SZ, _INT, _P]),
     "recemb_time_next_apply": (_INT, [_P, _P]),
     "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
+    "recemb_sum_partials": (_INT, [_P, _I32, _I64, _I32, _INT, _P, _P, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_flat_step_host": (_INT, [_P, _I64, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,

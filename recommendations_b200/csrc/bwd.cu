@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
     }
     uint32_t key = a.sentinel;
     if (ok) {
-      const int64_t row =
-          a.slots_per_id > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
-      if (row != a.pad_row) key = (uint32_t)(row + table_offset(id_idx, a.h));
+      int64_t row = a.slots_per_id > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
+      if (row != a.pad_row) {
+        row = shard_local_row(row, a.h);  // -1: another rank owns this row
+        if (row >= 0) key = (uint32_t)(row + table_offset(id_idx, a.h));
+      }
     }
     a.keys[s] = key;
     a.vals[s] = (uint32_t)s;
@@ -203,11 +205,12 @@ __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloat16* p, cons
 struct SegArgs {
   const uint32_t* keys;   // sorted rows (level 0) or record rows (level >= 1)
   const uint32_t* slots;  // level 0 only
-  int64_t n;              // entries at this level
+  int32_t n;              // entries at this level (< 2^31)
   const void* grad;       // level 0: [grad_rows, dim] GT ; level >= 1: fp32 partials [n, dim]
-  int32_t dim;
+  uint32_t dim;
   int32_t quads;          // dim / 4
-  int32_t slots_per_grad_row;
+  uint32_t spg;           // slots per gradient row (k shifts / bag size), >= 1
+  uint32_t spg_magic;     // floor(2^32 / spg): slot / spg without an integer divide
   const float* slot_weight;
   const float* grad_row_scale;
   uint32_t sentinel;      // keys >= sentinel carry nothing
@@ -231,69 +234,73 @@ __device__ __forceinline__ float masked_group_sum(float v, uint32_t mask) {
 
 // The optimizer math is a few flops per 16 bytes moved, but at HBM speed the SM has only
 // ~96 issue slots per 512-byte warp access: IEEE sqrt/div sequences (~20 instructions per
-// element) would make the update instruction-bound.  MUFU-based sqrt / reciprocal are
-// accurate to ~2 ulp, far inside the 1e-5 parity tolerance on updated weights.
+// element) would make the update instruction-bound.  One MUFU each for sqrt and reciprocal
+// (~2 ulp) is far inside the 1e-5 parity tolerance on updated weights.
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int G, int V, typename WT>
+// UPD >= 0: the update kind is a compile-time constant (dead variants disappear);
+// UPD < 0: read a.update at run time.  EXACT: the row is exactly G*V quads.
+template <int G, int V, typename WT, int UPD, bool EXACT>
 __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float (&g)[V][4], int lig,
                                           uint32_t gmask) {
-  WT* wrow = reinterpret_cast<WT*>(a.table) + (int64_t)row * a.dim;
+  const int upd = UPD >= 0 ? UPD : a.update;
+  const size_t off = (size_t)row * a.dim + lig * 4;
+  WT* wrow = reinterpret_cast<WT*>(a.table) + off;
   const recemb_optim_params& hp = a.hp;
-  if (a.update == RECEMB_UPD_DENSE_GRAD) {
+  auto live = [&](int j) { return EXACT || (j * G + lig) < a.quads; };
+  if (upd == RECEMB_UPD_DENSE_GRAD) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const int q = j * G + lig;
-      if (q < a.quads) store_quad<WT>(wrow + q * 4, g[j]);
-    }
+    for (int j = 0; j < V; ++j)
+      if (live(j)) store_quad<WT>(wrow + j * G * 4, g[j]);
     return;
   }
   float w[V][4];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    const int q = j * G + lig;
 #pragma unroll
     for (int e = 0; e < 4; ++e) w[j][e] = 0.f;
-    if (q < a.quads) load_quad<WT>(wrow + q * 4, w[j]);
+    if (live(j)) load_quad<WT>(wrow + j * G * 4, w[j]);
   }
-  const bool l2_decay = hp.weight_decay != 0.f && a.update != RECEMB_UPD_ADAMW;
-  if (l2_decay) {
+  if (hp.weight_decay != 0.f && upd != RECEMB_UPD_ADAMW) {
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) g[j][e] += hp.weight_decay * w[j][e];
   }
-  if (a.update == RECEMB_UPD_SGD) {
+  if (upd == RECEMB_UPD_SGD) {
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) w[j][e] -= hp.lr * g[j][e];
-  } else if (a.update == RECEMB_UPD_ADAGRAD) {
-    float* srow = a.state1 + (int64_t)row * a.dim;
+  } else if (upd == RECEMB_UPD_ADAGRAD) {
+    float* srow = a.state1 + off;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int q = j * G + lig;
-      if (q < a.quads) {
+      if (live(j)) {
         float s[4];
-        load_quad<float>(srow + q * 4, s);
+        load_quad<float>(srow + j * G * 4, s);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           s[e] += g[j][e] * g[j][e];
-          w[j][e] += fast_div(-hp.lr * g[j][e], fast_sqrt(s[e]) + hp.eps);
+          w[j][e] += (-hp.lr * g[j][e]) * fast_rcp(fast_sqrt(s[e]) + hp.eps);
         }
-        store_quad<float>(srow + q * 4, s);
+        store_quad<float>(srow + j * G * 4, s);
       }
     }
-  } else if (a.update == RECEMB_UPD_ROWWISE_ADAGRAD) {
+  } else if (upd == RECEMB_UPD_ROWWISE_ADAGRAD) {
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j)
@@ -301,7 +308,7 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
       for (int e = 0; e < 4; ++e) ss += g[j][e] * g[j][e];  // lanes past the row hold zeros
     ss = masked_group_sum<G>(ss, gmask) / (float)a.dim;
     const float s_new = a.state1[row] + ss;
-    const float inv = fast_div(-hp.lr, fast_sqrt(s_new) + hp.eps);
+    const float inv = -hp.lr * fast_rcp(fast_sqrt(s_new) + hp.eps);
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
@@ -309,60 +316,69 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
     __syncwarp(gmask);  // every lane has read state1[row] before lane 0 overwrites it
     if (lig == 0) a.state1[row] = s_new;
   } else {  // ADAM / ADAMW, lazy: only touched rows move
-    float* mrow = a.state1 + (int64_t)row * a.dim;
-    float* vrow = a.state2 + (int64_t)row * a.dim;
+    float* mrow = a.state1 + off;
+    float* vrow = a.state2 + off;
     const float step_size = hp.lr / hp.bias_correction1;
     const float inv_bc2_sqrt = 1.f / sqrtf(hp.bias_correction2);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int q = j * G + lig;
-      if (q < a.quads) {
+      if (live(j)) {
         float m[4], v[4];
-        load_quad<float>(mrow + q * 4, m);
-        load_quad<float>(vrow + q * 4, v);
+        load_quad<float>(mrow + j * G * 4, m);
+        load_quad<float>(vrow + j * G * 4, v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (a.update == RECEMB_UPD_ADAMW) w[j][e] *= (1.f - hp.lr * hp.weight_decay);
+          if (upd == RECEMB_UPD_ADAMW) w[j][e] *= (1.f - hp.lr * hp.weight_decay);
           m[e] = hp.beta1 * m[e] + (1.f - hp.beta1) * g[j][e];
           v[e] = hp.beta2 * v[e] + (1.f - hp.beta2) * g[j][e] * g[j][e];
           const float denom = fast_sqrt(v[e]) * inv_bc2_sqrt + hp.eps;
-          w[j][e] -= step_size * fast_div(m[e], denom);
+          w[j][e] -= step_size * m[e] * fast_rcp(denom);
         }
-        store_quad<float>(mrow + q * 4, m);
-        store_quad<float>(vrow + q * 4, v);
+        store_quad<float>(mrow + j * G * 4, m);
+        store_quad<float>(vrow + j * G * 4, v);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const int q = j * G + lig;
-    if (q < a.quads) store_quad<WT>(wrow + q * 4, w[j]);
-  }
+  for (int j = 0; j < V; ++j)
+    if (live(j)) store_quad<WT>(wrow + j * G * 4, w[j]);
 }
 
+// Compile-time shape of one instantiation of the walk.
+//   B     entries per batch            PD   prefetch distance in batches
+//   UPD   update kind or -1 (runtime)  PLAIN  level 0, one slot per gradient row, no scales
+//   EXACT row is exactly G*V quads     MINB   min CTAs / SM (register cap)
+template <int B_, int PD_, int MINB_, int UPD_, bool PLAIN_, bool EXACT_>
+struct SegCfg {
+  static constexpr int B = B_, PD = PD_, MINB = MINB_, UPD = UPD_;
+  static constexpr bool PLAIN = PLAIN_, EXACT = EXACT_;
+};
+
 // One group of G lanes walks CH consecutive sorted entries B at a time.  While batch b is
-// being reduced, the rows batch b+1 will touch (its gradient rows and, for every run that
-// ends inside it, the table / optimizer-state rows) are pulled into L2 with prefetch.global.L2,
-// so the dependent loads of the walk hit L2 instead of paying a DRAM round trip each.
+// reduced, the rows batch b+PD will touch (its gradient rows and, for every run that ends
+// inside it, the table / optimizer-state rows) are pulled into L2 with prefetch.global.L2, so
+// the dependent loads of the walk hit L2 instead of paying a DRAM (+TLB) round trip each.
 //
 // Records: chunk c leaves at most two (row, partial) records for the next level --
 // leading(c) at index 2c-1 (its first run continues from chunk c-1) and trailing(c) at 2c
 // (its last run continues into chunk c+1).  The two halves of a run cut by ONE boundary are
 // therefore the aligned pair (2c, 2c+1): the next level closes them inside one chunk, and
 // only runs longer than a chunk reach the levels above (which exit on an empty-level flag).
-template <int G, int V, typename GT, typename WT, bool L0, int CH, int B, int MINB>
-__global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a) {
+template <int G, int V, typename GT, typename WT, bool L0, int CH, typename Cfg>
+__global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegArgs a) {
   if (!L0 && *a.flag_in == 0) return;  // the previous level emitted nothing
+  constexpr int B = Cfg::B, PD = Cfg::PD;
+  constexpr bool PLAIN = Cfg::PLAIN && L0, EXACT = Cfg::EXACT;
   constexpr int GROUPS = kBwdThreads / G;
   const int lane = threadIdx.x & 31;
   const int lig = lane % G;
   const int gi_warp = lane / G;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi_warp * G));
-  const int64_t chunk = (int64_t)blockIdx.x * GROUPS + threadIdx.x / G;
-  const int64_t start = chunk * CH;
-  if (start >= a.n) return;
-  const int64_t end = min(start + (int64_t)CH, a.n);
-  const int64_t num_chunks = (a.n + CH - 1) / CH;
+  const int chunk = blockIdx.x * GROUPS + threadIdx.x / G;
+  const int num_chunks = (a.n + CH - 1) / CH;
+  if (chunk >= num_chunks) return;
+  const int start = chunk * CH;
+  const int end = min(start + CH, a.n);
 
   if (lig == 0) {
     if (chunk > 0) a.out_keys[2 * chunk - 1] = kNoKey;
@@ -370,57 +386,62 @@ __global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a)
     if (chunk == num_chunks - 1) a.out_keys[2 * chunk + 1] = kNoKey;
   }
 
-  const GT* grad = reinterpret_cast<const GT*>(a.grad);
-  const WT* table = reinterpret_cast<const WT*>(a.table);
-  const bool pf_w = a.update != RECEMB_UPD_DENSE_GRAD;
-  const bool pf_s1 = a.update == RECEMB_UPD_ADAGRAD || a.update >= RECEMB_UPD_ADAM;
-  const bool pf_s2 = a.update >= RECEMB_UPD_ADAM;
+  const int upd = Cfg::UPD >= 0 ? Cfg::UPD : a.update;
+  const GT* gbase = reinterpret_cast<const GT*>(a.grad) + lig * 4;
+  const WT* tbase = reinterpret_cast<const WT*>(a.table) + lig * 4;
+  const bool pf_w = upd != RECEMB_UPD_DENSE_GRAD;
+  const bool pf_s1 = upd == RECEMB_UPD_ADAGRAD || upd >= RECEMB_UPD_ADAM;
+  const bool pf_s2 = upd >= RECEMB_UPD_ADAM;
+  auto live = [&](int j) { return EXACT || (j * G + lig) < a.quads; };
 
-  // keys of entries [e0, e0+B] (one look-ahead) and slots of [e0, e0+B)
-  auto load_meta = [&](int64_t e0, uint32_t(&kk)[B + 1], uint32_t(&ss)[B]) {
+  auto grad_row_of = [&](int i, uint32_t slot) -> uint32_t {
+    if (!L0) return (uint32_t)i;
+    if (PLAIN || a.spg == 1) return slot;
+    uint32_t q = __umulhi(slot, a.spg_magic);  // q in {floor(slot/spg) - 1, floor(slot/spg)}
+    if (slot - q * a.spg >= a.spg) ++q;
+    return q;
+  };
+  // keys of entries [e0, e0+B] (one look-ahead past the batch) and slots of [e0, e0+B)
+  auto load_meta = [&](int e0, uint32_t(&kk)[B + 1], uint32_t(&ss)[B]) {
 #pragma unroll
     for (int u = 0; u <= B; ++u) {
-      const int64_t i = e0 + u;
+      const int i = e0 + u;
       const bool in = (u < B) ? (i < end) : (i < a.n);
       kk[u] = in ? a.keys[i] : kNoKey;
       if (u < B) ss[u] = (L0 && in) ? a.slots[i] : 0u;
     }
   };
-  auto grad_row_of = [&](int64_t i, uint32_t slot) -> int64_t {
-    if (!L0) return i;
-    return a.slots_per_grad_row > 1 ? (int64_t)(slot / (uint32_t)a.slots_per_grad_row) : (int64_t)slot;
-  };
-  auto prefetch_batch = [&](int64_t e0, const uint32_t(&kk)[B + 1], const uint32_t(&ss)[B]) {
+  auto prefetch_batch = [&](int e0) {
+    if (e0 >= end) return;
+    uint32_t kk[B + 1], ss[B];
+    load_meta(e0, kk, ss);
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       if (kk[u] < a.sentinel) {
-        const GT* src = grad + grad_row_of(e0 + u, ss[u]) * a.dim;
+        const GT* src = gbase + (size_t)grad_row_of(e0 + u, ss[u]) * a.dim;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const int q = j * G + lig;
-          if (q < a.quads) prefetch_l2(src + q * 4);
-        }
+        for (int j = 0; j < V; ++j)
+          if (live(j)) prefetch_l2(src + j * G * 4);
         if (pf_w && kk[u + 1] != kk[u]) {  // this run ends here: its row will be updated
-          const int64_t off = (int64_t)kk[u] * a.dim;
+          const size_t off = (size_t)kk[u] * a.dim;
 #pragma unroll
           for (int j = 0; j < V; ++j) {
-            const int q = j * G + lig;
-            if (q < a.quads) {
-              prefetch_l2(table + off + q * 4);
-              if (pf_s1) prefetch_l2(a.state1 + off + q * 4);
-              if (pf_s2) prefetch_l2(a.state2 + off + q * 4);
+            if (live(j)) {
+              prefetch_l2(tbase + off + j * G * 4);
+              if (pf_s1) prefetch_l2(a.state1 + off + lig * 4 + j * G * 4);
+              if (pf_s2) prefetch_l2(a.state2 + off + lig * 4 + j * G * 4);
             }
           }
+          if (upd == RECEMB_UPD_ROWWISE_ADAGRAD && lig == 0) prefetch_l2(a.state1 + kk[u]);
         }
       }
     }
   };
 
-  uint32_t k[B + 1], sl[B];
-  load_meta(start, k, sl);
-  prefetch_batch(start, k, sl);
+#pragma unroll
+  for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
 
-  uint32_t cur = k[0];
+  uint32_t cur = a.keys[start];
   const bool left_open = start > 0 && a.keys[start - 1] == cur;
   bool first = true;
   float acc[V][4];
@@ -432,41 +453,31 @@ __global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a)
   auto flush = [&](uint32_t key, bool leading, bool trailing) {
     if (key >= a.sentinel) return;
     if (!leading && !trailing) {
-      apply_row<G, V, WT>(a, key, acc, lig, gmask);
+      apply_row<G, V, WT, Cfg::UPD, EXACT>(a, key, acc, lig, gmask);
       return;
     }
-    const int64_t rec = leading ? 2 * chunk - 1 : 2 * chunk;
-    float* dst = a.out_partials + rec * a.dim;
+    const int rec = leading ? 2 * chunk - 1 : 2 * chunk;
+    float* dst = a.out_partials + (size_t)rec * a.dim + lig * 4;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const int q = j * G + lig;
-      if (q < a.quads) store_quad<float>(dst + q * 4, acc[j]);
-    }
+    for (int j = 0; j < V; ++j)
+      if (live(j)) store_quad<float>(dst + j * G * 4, acc[j]);
     if (lig == 0) {
       a.out_keys[rec] = key;
       *a.flag_out = 1u;
     }
     if (leading && trailing) {  // the whole chunk is one run open on both sides
       float z[4] = {0.f, 0.f, 0.f, 0.f};
-      float* dst2 = a.out_partials + (rec + 1) * a.dim;
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const int q = j * G + lig;
-        if (q < a.quads) store_quad<float>(dst2 + q * 4, z);
-      }
+      for (int j = 0; j < V; ++j)
+        if (live(j)) store_quad<float>(dst + a.dim + j * G * 4, z);
       if (lig == 0) a.out_keys[rec + 1] = key;
     }
   };
 
-  for (int64_t e0 = start; e0 < end; e0 += B) {
-    // (a) meta-data of the next batch (L1 hits: 32 keys share a line) and its L2 prefetch
-    uint32_t kn[B + 1], sn[B];
-    const bool more = e0 + B < end;
-    if (more) {
-      load_meta(e0 + B, kn, sn);
-      prefetch_batch(e0 + B, kn, sn);
-    }
-    // (b) gradient rows of this batch (L2 hits after the first batch)
+  for (int e0 = start; e0 < end; e0 += B) {
+    prefetch_batch(e0 + PD * B);
+    uint32_t k[B + 1], sl[B];
+    load_meta(e0, k, sl);
     float g[B][V][4];
     float wt[B];
 #pragma unroll
@@ -477,20 +488,17 @@ __global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a)
 #pragma unroll
         for (int e = 0; e < 4; ++e) g[u][j][e] = 0.f;
       if (k[u] < a.sentinel) {
-        const int64_t grow = grad_row_of(e0 + u, sl[u]);
-        if (L0) {
+        const uint32_t grow = grad_row_of(e0 + u, sl[u]);
+        if (L0 && !PLAIN) {
           if (a.slot_weight) wt[u] = a.slot_weight[sl[u]];
           if (a.grad_row_scale) wt[u] *= a.grad_row_scale[grow];
         }
-        const GT* src = grad + grow * a.dim;
+        const GT* src = gbase + (size_t)grow * a.dim;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const int q = j * G + lig;
-          if (q < a.quads) load_quad_stream<GT>(src + q * 4, g[u][j]);
-        }
+        for (int j = 0; j < V; ++j)
+          if (live(j)) load_quad_stream<GT>(src + j * G * 4, g[u][j]);
       }
     }
-    // (c) walk
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       if (e0 + u < end) {
@@ -504,7 +512,7 @@ __global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a)
             for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
         }
         if (k[u] < a.sentinel) {
-          if (L0 && (a.slot_weight || a.grad_row_scale)) {
+          if (L0 && !PLAIN && (a.slot_weight || a.grad_row_scale)) {
 #pragma unroll
             for (int j = 0; j < V; ++j)
 #pragma unroll
@@ -517,12 +525,6 @@ __global__ void __launch_bounds__(kBwdThreads, MINB) seg_kernel(const SegArgs a)
           }
         }
       }
-    }
-    if (more) {
-#pragma unroll
-      for (int u = 0; u <= B; ++u) k[u] = kn[u];
-#pragma unroll
-      for (int u = 0; u < B; ++u) sl[u] = sn[u];
     }
   }
   const bool right_open = end < a.n && a.keys[end] == cur;
@@ -548,60 +550,88 @@ static bool pick_quads(int quads, QuadShape* s) {
 #define RECEMB_CHUNK0 64
 #endif
 constexpr int kChunk0 = RECEMB_CHUNK0;  // sorted entries per group at level 0
-constexpr int kChunkN = 32;  // records per group at levels >= 1
+constexpr int kChunkN = 32;             // records per group at levels >= 1
 
+template <int G, int V, typename GT, typename WT, bool L0, typename Cfg>
+static void launch_one(const SegArgs& a, cudaStream_t s) {
+  constexpr int CH = L0 ? kChunk0 : kChunkN;
+  const int chunks = (a.n + CH - 1) / CH;
+  const int groups = kBwdThreads / G;
+  seg_kernel<G, V, GT, WT, L0, CH, Cfg><<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
+}
+
+// generic instantiations: any shape / update / scale combination
 #define SEG_GV(G_, V_)                                                                          \
   if (shape.G == G_ && shape.V == V_) {                                                         \
-    constexpr int CH = L0 ? kChunk0 : kChunkN;                                                  \
-    constexpr int B = (V_ == 1) ? 2 : 1;                                                        \
-    constexpr int MINB = (V_ == 1) ? 4 : (V_ == 2 ? 2 : 1);                                     \
-    const int64_t chunks = (a.n + CH - 1) / CH;                                                 \
-    const int groups = kBwdThreads / G_;                                                        \
-    const int64_t grid = (chunks + groups - 1) / groups;                                        \
-    seg_kernel<G_, V_, GT, WT, L0, CH, B, MINB><<<(unsigned)grid, kBwdThreads, 0, s>>>(a);      \
+    using Cfg = SegCfg<(V_ == 1) ? 2 : 1, 2, (V_ == 1) ? 4 : (V_ == 2 ? 2 : 1), -1, false, false>; \
+    launch_one<G_, V_, GT, WT, L0, Cfg>(a, s);                                                  \
     launched = true;                                                                            \
   }
 
-// Tuning aid (RECEMB_SEG_TUNE="B,MINB,CH"): alternative instantiations of the headline shape
-// (256-byte fp32 rows, level 0) so one GPU session can compare them.  Unset = default.
-// NOTE: CH must equal kChunk0 for correctness of the level sizing, so CH variants are only
-// compiled when they match (the chunk sweep is done by rebuilding with another kChunk0).
-template <int B, int MINB>
-static void launch_tuned(const SegArgs& a, cudaStream_t s) {
-  const int64_t chunks = (a.n + kChunk0 - 1) / kChunk0;
-  const int64_t grid = (chunks + 15) / 16;
-  seg_kernel<16, 1, float, float, true, kChunk0, B, MINB><<<(unsigned)grid, kBwdThreads, 0, s>>>(a);
+// specialised level-0 instantiations for the rows the BASELINE configs use (256-byte rows:
+// D = 64 fp32 -> G = 16, D = 128 bf16 -> G = 32), update kind fixed at compile time
+template <int G, typename GT, typename WT, bool PLAIN, int B, int PD, int MINB>
+static bool launch_fast(const SegArgs& a, cudaStream_t s) {
+  switch (a.update) {
+    case RECEMB_UPD_ADAGRAD:
+      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ADAGRAD, PLAIN, true>>(a, s);
+      return true;
+    case RECEMB_UPD_ROWWISE_ADAGRAD:
+      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ROWWISE_ADAGRAD, PLAIN, true>>(a, s);
+      return true;
+    case RECEMB_UPD_SGD:
+      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_SGD, PLAIN, true>>(a, s);
+      return true;
+    case RECEMB_UPD_DENSE_GRAD:
+      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_DENSE_GRAD, PLAIN, true>>(a, s);
+      return true;
+    default:
+      return false;
+  }
 }
-static bool try_tuned(const SegArgs& a, cudaStream_t s) {
-  static int tb = -1, tm = -1;
+
+// RECEMB_SEG_TUNE="B,PD,MINB": tuning aid for the fp32 G = 16 fast path (one GPU session can
+// compare instantiations).  Unset = default.
+static void tune_params(int* b, int* pd, int* minb) {
+  static int tb = -1, tp = 0, tm = 0;
   if (tb == -1) {
     tb = 0;
     const char* e = getenv("RECEMB_SEG_TUNE");
-    if (e && sscanf(e, "%d,%d", &tb, &tm) != 2) tb = 0;
+    if (e && sscanf(e, "%d,%d,%d", &tb, &tp, &tm) != 3) tb = 0;
   }
-  if (tb == 0) return false;
-  if (tb == 4 && tm == 4) launch_tuned<4, 4>(a, s);
-  else if (tb == 4 && tm == 3) launch_tuned<4, 3>(a, s);
-  else if (tb == 2 && tm == 4) launch_tuned<2, 4>(a, s);
-  else if (tb == 2 && tm == 5) launch_tuned<2, 5>(a, s);
-  else if (tb == 2 && tm == 6) launch_tuned<2, 6>(a, s);
-  else if (tb == 1 && tm == 4) launch_tuned<1, 4>(a, s);
-  else if (tb == 1 && tm == 6) launch_tuned<1, 6>(a, s);
-  else if (tb == 1 && tm == 8) launch_tuned<1, 8>(a, s);
-  else return false;
-  return true;
+  *b = tb;
+  *pd = tp;
+  *minb = tm;
 }
 
 template <typename GT, typename WT, bool L0>
 static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
   bool launched = false;
-  if (L0 && std::is_same<GT, float>::value && std::is_same<WT, float>::value && shape.G == 16 &&
-      shape.V == 1 && try_tuned(a, s)) {
-    RECEMB_LAUNCHED();
-    return RECEMB_OK;
+  if (L0 && shape.V == 1 && a.quads == shape.G && (shape.G == 16 || shape.G == 32) &&
+      std::is_same<GT, WT>::value) {
+    const bool plain = a.spg == 1 && !a.slot_weight && !a.grad_row_scale;
+    if (shape.G == 16) {
+      int tb, tp, tm;
+      tune_params(&tb, &tp, &tm);
+      if (plain && tb == 2 && tp == 1 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 1, 4>(a, s);
+      else if (plain && tb == 2 && tp == 3 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 3, 4>(a, s);
+      else if (plain && tb == 2 && tp == 2 && tm == 5) launched = launch_fast<16, GT, WT, true, 2, 2, 5>(a, s);
+      else if (plain && tb == 4 && tp == 1 && tm == 4) launched = launch_fast<16, GT, WT, true, 4, 1, 4>(a, s);
+      else if (plain && tb == 1 && tp == 4 && tm == 5) launched = launch_fast<16, GT, WT, true, 1, 4, 5>(a, s);
+      else if (plain && tb == 2 && tp == 4 && tm == 5) launched = launch_fast<16, GT, WT, true, 2, 4, 5>(a, s);
+      else if (plain && tb == 2 && tp == 2 && tm == 6) launched = launch_fast<16, GT, WT, true, 2, 2, 6>(a, s);
+      else if (plain) launched = launch_fast<16, GT, WT, true, 2, 1, 4>(a, s);
+      else launched = launch_fast<16, GT, WT, false, 2, 1, 4>(a, s);
+    } else {
+      // one group per warp: half the rows in flight per warp -> prefetch further ahead
+      if (plain) launched = launch_fast<32, GT, WT, true, 2, 4, 4>(a, s);
+      else launched = launch_fast<32, GT, WT, false, 2, 4, 4>(a, s);
+    }
   }
-  SEG_GV(1, 1) SEG_GV(2, 1) SEG_GV(4, 1) SEG_GV(8, 1) SEG_GV(16, 1) SEG_GV(32, 1) SEG_GV(32, 2)
-  SEG_GV(32, 4) SEG_GV(32, 8)
+  if (!launched) {
+    SEG_GV(1, 1) SEG_GV(2, 1) SEG_GV(4, 1) SEG_GV(8, 1) SEG_GV(16, 1) SEG_GV(32, 1) SEG_GV(32, 2)
+    SEG_GV(32, 4) SEG_GV(32, 8)
+  }
   if (!launched) {
     set_error("bwd_apply: no kernel for G=%d V=%d", shape.G, shape.V);
     return RECEMB_ERR_UNSUPPORTED;
@@ -675,7 +705,7 @@ extern "C" size_t recemb_bwd_plan_bytes(int64_t n_slots, int64_t num_rows) {
   return L.total;
 }
 
-extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_per_table,
+extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, const recemb_layout* layout,
                                int32_t slots_per_id, int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad,
                                int64_t pad_id, int64_t pad_row, int32_t bag_size,
                                const int32_t* lengths, int32_t last_n, void* plan,
@@ -684,9 +714,10 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_pe
   RECEMB_CHECK_ARG(plan != nullptr && plan_bytes >= kCounterBytes, "plan buffer missing");
   RECEMB_CHECK_ARG((uintptr_t)plan % 256 == 0, "plan buffer must be 256-byte aligned");
   RECEMB_CHECK_ARG(num_rows >= 1, "num_rows < 1");
-  RECEMB_CHECK_ARG(ids_per_table >= 0, "ids_per_table < 0");
-  const int64_t n_tables = ids_per_table > 0 ? (n_ids + ids_per_table - 1) / ids_per_table : 1;
-  const int64_t total_rows = num_rows * (n_tables > 0 ? n_tables : 1);
+  // keys are rows of the stacked (table-batched) and / or local (sharded) table
+  const int64_t total_rows = layout_local_rows(num_rows, layout) * layout_tables(layout, n_ids);
+  RECEMB_CHECK_ARG(!(layout && layout->ids_per_table > 0) || slots_per_id == 1,
+                   "table batching and k-shift cannot be combined");
   RECEMB_UNSUPPORTED(total_rows < 0xfffffff0ll, "%lld rows do not fit 32-bit sort keys",
                      (long long)total_rows);
   const int64_t n = n_ids * slots_per_id;
@@ -711,7 +742,7 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, int64_t ids_pe
   a.ids = ids;
   a.n_slots = n;
   a.slots_per_id = slots_per_id;
-  int rc = make_hash_spec(hash_mode, num_rows, slots_per_id > 1 ? 0 : hash_arg, &a.h, ids_per_table);
+  int rc = make_hash_spec(hash_mode, num_rows, slots_per_id > 1 ? 0 : hash_arg, &a.h, layout);
   if (rc) return rc;
   a.zero_pad = zero_pad;
   a.pad_id = pad_id;
@@ -841,9 +872,10 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
   size_t woff = 256;
 
   SegArgs a;
-  a.dim = dim;
+  a.dim = (uint32_t)dim;
   a.quads = dim / 4;
-  a.slots_per_grad_row = slots_per_grad_row;
+  a.spg = (uint32_t)slots_per_grad_row;
+  a.spg_magic = (uint32_t)((1ull << 32) / (uint64_t)slots_per_grad_row);
   a.slot_weight = slot_weight;
   a.grad_row_scale = grad_row_scale;
   a.sentinel = (uint32_t)num_rows;
@@ -865,7 +897,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
     woff += align_up((size_t)recs * dim * 4, 256);
     a.keys = in_keys;
     a.slots = in_slots;
-    a.n = sizes[l];
+    a.n = (int32_t)sizes[l];
     a.grad = in_grad;
     a.out_keys = out_keys;
     a.out_partials = out_part;

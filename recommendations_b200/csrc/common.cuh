@@ -112,14 +112,33 @@ struct HashSpec {
   // table-batched lookups: lookup i belongs to table t = i / ids_per_table and its row is
   // offset by t * rows_per_table into one stacked [T * rows_per_table, dim] table (0 = off)
   uint32_t ids_per_table;
-  int64_t rows_per_table;
+  uint32_t num_tables;    // > 0: table index wraps modulo num_tables
+  int64_t rows_per_table; // LOCAL rows of one table
+  // row-wise sharding: global row r lives on rank r % shard_world at local row r / shard_world;
+  // a lookup whose row belongs to another rank is dropped (shard_world <= 1 = off)
+  uint32_t shard_world;
+  uint32_t shard_rank;
+  ModN mod_world;
 };
 
 int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,
-                   int64_t ids_per_table = 0);
+                   const recemb_layout* layout = nullptr);
+int64_t layout_local_rows(int64_t num_rows, const recemb_layout* layout);
+int64_t layout_tables(const recemb_layout* layout, int64_t n_ids);
+
+// global row -> local row on this shard, or -1 when another rank owns it
+__device__ __forceinline__ int64_t shard_local_row(int64_t row, const HashSpec& h) {
+  if (h.shard_world <= 1) return row;
+  uint64_t q;
+  const uint64_t r = udivmod((uint64_t)row, h.mod_world, &q);
+  return r == h.shard_rank ? (int64_t)q : -1;
+}
 
 __device__ __forceinline__ int64_t table_offset(int64_t i, const HashSpec& h) {
-  return h.ids_per_table ? (int64_t)((uint32_t)i / h.ids_per_table) * h.rows_per_table : 0;
+  if (!h.ids_per_table) return 0;
+  uint32_t t = (uint32_t)i / h.ids_per_table;
+  if (h.num_tables) t %= h.num_tables;
+  return (int64_t)t * h.rows_per_table;
 }
 
 // (x << c) | (x >> (64-c)) with wrapping << and ARITHMETIC >> on signed int64:

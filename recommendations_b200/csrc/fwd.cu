@@ -333,7 +333,7 @@ struct PoolArgs {
 constexpr int kPoolTileIds = 2048;
 
 template <int G, int V, typename T>
-__global__ void __launch_bounds__(kThreads) pool_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const PoolArgs a) {
   constexpr int RPW = 32 / G;
   constexpr int E = Vec16<T>::kElems;
   constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);
@@ -389,7 +389,9 @@ __global__ void __launch_bounds__(kThreads) pool_kernel(const PoolArgs a) {
         const bool my_ok = live && my_p < hi;
         const int64_t my_id = my_ok ? ids[lb * P + my_p] : 0;
         const bool my_use = my_ok && !(a.zero_pad && my_id == a.pad_id);
-        const int64_t my_row = my_use ? row_of(my_id, a.h) : -1;
+        int64_t my_row = my_use ? row_of(my_id, a.h) : -1;
+        if (my_row >= 0) my_row = shard_local_row(my_row, a.h);  // -1: another rank owns it
+        if (my_row >= 0) my_row += table_offset(bag * P + my_p, a.h);
         float my_w = 1.f;
         if (my_use && a.slot_weight) my_w = a.slot_weight[bag * P + my_p];
         const int sub = min(G, span - p0);
@@ -470,6 +472,21 @@ static int grid_for(int device, int64_t tiles, int ctas_per_sm) {
   return (int)g;
 }
 
+// Persistent kernels stride over tiles with a fixed grid: the grid must be exactly the number
+// of CTAs that are resident at once (SMs x occupancy).  A larger grid leaves a second, partial
+// wave of CTAs that start late and still own as many tiles as the first wave's.
+template <auto kernel, typename Args>
+static void launch_persistent(const Args& a, int64_t tiles, int device, cudaStream_t s) {
+  static int occ[64];  // per kernel instantiation (the kernel is a template argument), per device
+  const int d = (device >= 0 && device < 64) ? device : 0;
+  if (occ[d] == 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) != cudaSuccess || v < 1) v = 1;
+    occ[d] = v;
+  }
+  kernel<<<grid_for(device, tiles, occ[d]), kThreads, 0, s>>>(a);
+}
+
 #define DISPATCH_GV(G_, V_, ...)                                         \
   if (shape.G == G_ && shape.V == V_) {                                  \
     constexpr int G = G_;                                                \
@@ -489,17 +506,17 @@ static int grid_for(int device, int64_t tiles, int ctas_per_sm) {
   DISPATCH_GV(32, 8, __VA_ARGS__)
 
 template <typename T>
-static int launch_gather(const GatherArgs& a, RowShape shape, int epilogue, bool two, int grid,
-                         cudaStream_t s) {
+static int launch_gather(const GatherArgs& a, RowShape shape, int epilogue, bool two, int64_t tiles,
+                         int device, cudaStream_t s) {
   bool launched = false;
   if (!two && epilogue == RECEMB_EPI_NONE) {
-    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_NONE, false><<<grid, kThreads, 0, s>>>(a)))
+    DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_NONE, false>>(a, tiles, device, s)))
   } else if (!two) {
-    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_L2NORM, false><<<grid, kThreads, 0, s>>>(a)))
+    DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_L2NORM, false>>(a, tiles, device, s)))
   } else if (epilogue == RECEMB_EPI_NONE) {
-    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_NONE, true><<<grid, kThreads, 0, s>>>(a)))
+    DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_NONE, true>>(a, tiles, device, s)))
   } else {
-    DISPATCH_SHAPES((gather_kernel<G, V, T, RECEMB_EPI_L2NORM, true><<<grid, kThreads, 0, s>>>(a)))
+    DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_L2NORM, true>>(a, tiles, device, s)))
   }
   if (!launched) {
     set_error("gather: no kernel for G=%d V=%d", shape.G, shape.V);
@@ -510,9 +527,9 @@ static int launch_gather(const GatherArgs& a, RowShape shape, int epilogue, bool
 }
 
 template <typename T>
-static int launch_kshift(const KShiftArgs& a, RowShape shape, int grid, cudaStream_t s) {
+static int launch_kshift(const KShiftArgs& a, RowShape shape, int64_t tiles, int device, cudaStream_t s) {
   bool launched = false;
-  DISPATCH_SHAPES((kshift_kernel<G, V, T><<<grid, kThreads, 0, s>>>(a)))
+  DISPATCH_SHAPES((launch_persistent<kshift_kernel<G, V, T>>(a, tiles, device, s)))
   if (!launched) {
     set_error("kshift: no kernel for G=%d V=%d", shape.G, shape.V);
     return RECEMB_ERR_UNSUPPORTED;
@@ -522,9 +539,9 @@ static int launch_kshift(const KShiftArgs& a, RowShape shape, int grid, cudaStre
 }
 
 template <typename T>
-static int launch_pool(const PoolArgs& a, RowShape shape, int grid, cudaStream_t s) {
+static int launch_pool(const PoolArgs& a, RowShape shape, int64_t tiles, int device, cudaStream_t s) {
   bool launched = false;
-  DISPATCH_SHAPES((pool_kernel<G, V, T><<<grid, kThreads, 0, s>>>(a)))
+  DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T>>(a, tiles, device, s)))
   if (!launched) {
     set_error("pool: no kernel for G=%d V=%d", shape.G, shape.V);
     return RECEMB_ERR_UNSUPPORTED;
@@ -566,7 +583,7 @@ extern "C" int recemb_row_index(const int64_t* ids, int64_t n, int hash_mode, in
 
 extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void* table2,
                                  int64_t num_rows2, int32_t dim, int dtype, const int64_t* ids,
-                                 int64_t n, int64_t ids_per_table, int hash_mode, int hash_mode2,
+                                 int64_t n, const recemb_layout* layout, int hash_mode, int hash_mode2,
                                  int64_t hash_arg, int epilogue, int zero_pad, int64_t pad_id,
                                  void* out, float* inv_norm_out, int device,
                                  recemb_stream_t stream) {
@@ -582,9 +599,11 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   if (rc) return rc;
   RowShape shape;
   RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
-  RECEMB_CHECK_ARG(ids_per_table == 0 || table2 == nullptr, "table-batched lookups take one table");
-  RECEMB_UNSUPPORTED(ids_per_table == 0 || n < 0xffffffffll, "too many lookups for table-batched mode");
-  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1, ids_per_table);
+  const bool batched = layout && layout->ids_per_table > 0;
+  RECEMB_CHECK_ARG(!batched || table2 == nullptr, "table-batched lookups take one table");
+  RECEMB_UNSUPPORTED(!batched || n < 0xffffffffll, "too many lookups for table-batched mode");
+  RECEMB_UNSUPPORTED(!layout || layout->shard_world <= 1, "sharded sequence gather is not implemented");
+  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1, layout);
   if (rc) return rc;
   a.h2 = a.h1;
   if (table2) {
@@ -602,10 +621,10 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
-  const int grid = grid_for(device, (n + kTileIds - 1) / kTileIds, 8);
+  const int64_t tiles = (n + kTileIds - 1) / kTileIds;
   if (dtype == RECEMB_F32)
-    return launch_gather<float>(a, shape, epilogue, table2 != nullptr, grid, (cudaStream_t)stream);
-  return launch_gather<__nv_bfloat16>(a, shape, epilogue, table2 != nullptr, grid,
+    return launch_gather<float>(a, shape, epilogue, table2 != nullptr, tiles, device, (cudaStream_t)stream);
+  return launch_gather<__nv_bfloat16>(a, shape, epilogue, table2 != nullptr, tiles, device,
                                       (cudaStream_t)stream);
 }
 
@@ -636,16 +655,17 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
-  const int grid = grid_for(device, (n + kTileIds - 1) / kTileIds, 6);
-  if (dtype == RECEMB_F32) return launch_kshift<float>(a, shape, grid, (cudaStream_t)stream);
-  return launch_kshift<__nv_bfloat16>(a, shape, grid, (cudaStream_t)stream);
+  const int64_t tiles = (n + kTileIds - 1) / kTileIds;
+  if (dtype == RECEMB_F32) return launch_kshift<float>(a, shape, tiles, device, (cudaStream_t)stream);
+  return launch_kshift<__nv_bfloat16>(a, shape, tiles, device, (cudaStream_t)stream);
 }
 
 extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
                                const int64_t* ids, int64_t num_bags, int32_t bag_size,
                                const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
                                int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad,
-                               int64_t pad_id, void* out, int device, recemb_stream_t stream) {
+                               int64_t pad_id, const recemb_layout* layout, void* out, int device,
+                               recemb_stream_t stream) {
   RECEMB_CHECK_ARG(num_bags >= 0, "num_bags < 0");
   if (num_bags == 0) return RECEMB_OK;
   RECEMB_CHECK_ARG(table && ids && out, "null pointer");
@@ -658,8 +678,10 @@ extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
   if (rc) return rc;
   RowShape shape;
   RECEMB_UNSUPPORTED(pick_shape(a.row_vecs, &shape), "dim %d too large", dim);
-  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h);
+  rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h, layout);
   if (rc) return rc;
+  RECEMB_UNSUPPORTED(!(layout && layout->ids_per_table > 0) || num_bags * bag_size < 0xffffffffll,
+                     "too many slots for table-batched mode");
   a.table = (const uint4*)table;
   a.ids = ids;
   a.lengths = lengths;
@@ -669,6 +691,15 @@ extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
   a.bag_size = bag_size;
   a.last_n = last_n;
   a.bags_per_tile = kPoolTileIds / bag_size;
+  {
+    // small problems: shrink the tile until there are >= 4 tiles per resident CTA, otherwise a
+    // handful of CTAs get a second tile and the launch takes twice as long (tail effect)
+    const int64_t want_tiles = (int64_t)sm_count(device) * 4 * 4;
+    int64_t bpt = (num_bags + want_tiles - 1) / want_tiles;
+    if (bpt < 8) bpt = 8;
+    if ((bpt * bag_size) % 2) ++bpt;  // even id count per tile keeps every tile 16-byte aligned
+    if (bpt < a.bags_per_tile) a.bags_per_tile = (int32_t)bpt;
+  }
   a.pool_mode = pool_mode;
   a.zero_pad = zero_pad;
   a.pad_id = pad_id;
@@ -677,7 +708,6 @@ extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   const int64_t tiles = (num_bags + a.bags_per_tile - 1) / a.bags_per_tile;
-  const int grid = grid_for(device, tiles, 4);
-  if (dtype == RECEMB_F32) return launch_pool<float>(a, shape, grid, (cudaStream_t)stream);
-  return launch_pool<__nv_bfloat16>(a, shape, grid, (cudaStream_t)stream);
+  if (dtype == RECEMB_F32) return launch_pool<float>(a, shape, tiles, device, (cudaStream_t)stream);
+  return launch_pool<__nv_bfloat16>(a, shape, tiles, device, (cudaStream_t)stream);
 }

@@ -31,14 +31,43 @@ int sm_count(int device) {
   return cached[device];
 }
 
+int64_t layout_local_rows(int64_t num_rows, const recemb_layout* layout) {
+  if (!layout || layout->shard_world <= 1) return num_rows;
+  return (num_rows - layout->shard_rank + layout->shard_world - 1) / layout->shard_world;
+}
+int64_t layout_tables(const recemb_layout* layout, int64_t n_ids) {
+  if (!layout || layout->ids_per_table <= 0) return 1;
+  if (layout->num_tables > 0) return layout->num_tables;
+  const int64_t t = (n_ids + layout->ids_per_table - 1) / layout->ids_per_table;
+  return t > 0 ? t : 1;
+}
+
 int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,
-                   int64_t ids_per_table) {
+                   const recemb_layout* layout) {
   HashSpec h;
   h.mode = hash_mode;
   h.shift = 0;
-  RECEMB_CHECK_ARG(ids_per_table >= 0 && ids_per_table < 0xffffffffll, "ids_per_table out of range");
-  h.ids_per_table = (uint32_t)ids_per_table;
+  h.ids_per_table = 0;
+  h.num_tables = 0;
   h.rows_per_table = num_rows;
+  h.shard_world = 1;
+  h.shard_rank = 0;
+  h.mod_world = make_modn(1);
+  if (layout) {
+    RECEMB_CHECK_ARG(layout->ids_per_table >= 0 && layout->ids_per_table < 0xffffffffll,
+                     "ids_per_table out of range");
+    RECEMB_CHECK_ARG(layout->num_tables >= 0, "num_tables < 0");
+    h.ids_per_table = (uint32_t)layout->ids_per_table;
+    h.num_tables = (uint32_t)layout->num_tables;
+    if (layout->shard_world > 1) {
+      RECEMB_CHECK_ARG(layout->shard_rank >= 0 && layout->shard_rank < layout->shard_world,
+                       "shard_rank %d outside [0, %d)", layout->shard_rank, layout->shard_world);
+      h.shard_world = (uint32_t)layout->shard_world;
+      h.shard_rank = (uint32_t)layout->shard_rank;
+      h.mod_world = make_modn((uint64_t)layout->shard_world);
+    }
+    h.rows_per_table = layout_local_rows(num_rows, layout);
+  }
   h.mod_rows = make_modn(1);
   h.mod_sq = make_modn(1);
   switch (hash_mode) {
@@ -74,6 +103,9 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
 
 using namespace recemb;
 
+extern "C" int64_t recemb_layout_total_rows(int64_t num_rows, const recemb_layout* layout, int64_t n_ids) {
+  return layout_local_rows(num_rows, layout) * layout_tables(layout, n_ids);
+}
 extern "C" int recemb_abi_version(void) { return RECEMB_ABI_VERSION; }
 extern "C" const char* recemb_last_error(void) { return t_error; }
 extern "C" uint64_t recemb_launch_count(void) { return g_launch_count.load(); }
@@ -97,15 +129,15 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   // another stream) is still computing; the kernels below must not.
   if (wait_event_after_copy)
     RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
+  recemb_layout layout = {ids_per_table, 0, 1, 0, 0};
   int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
-                             ids_per_table, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
+                             &layout, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
                              stream);
   if (rc) return rc;
-  rc = recemb_bwd_plan(ids_dev_scratch, n, ids_per_table, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
+  rc = recemb_bwd_plan(ids_dev_scratch, n, &layout, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
                        0, -1, 0, nullptr, 0, plan, plan_bytes, device, stream);
   if (rc) return rc;
-  const int64_t total_rows =
-      num_rows * (ids_per_table > 0 ? (n + ids_per_table - 1) / ids_per_table : 1);
+  const int64_t total_rows = recemb_layout_total_rows(num_rows, &layout, n);
   rc = recemb_bwd_apply(plan, plan_bytes, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
                         dtype, total_rows, state1, state2, hp_host, workspace, workspace_bytes, device,
                         stream);

@@ -51,6 +51,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
     rows_per_table = table.shape[0]
+    layout = N.make_layout(ids_per_table=ids_per_table)
     if ids_per_table:
         n_tables = -(-n // ids_per_table)
         if table.shape[0] % n_tables:
@@ -58,7 +59,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
         rows_per_table = table.shape[0] // n_tables
     N.check(N.load().recemb_gather_fwd(
         N.ptr(table), rows_per_table, N.ptr(table2), 0 if table2 is None else table2.shape[0], dim,
-        N.dtype_code(table.dtype), N.ptr(flat), n, ids_per_table, hash_mode, hash_mode2, hash_arg, epilogue,
+        N.dtype_code(table.dtype), N.ptr(flat), n, layout, hash_mode, hash_mode2, hash_arg, epilogue,
         int(zero_pad), pad_id, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_gather_fwd")
     return out.view(*ids.shape, dim), inv
 
@@ -81,7 +82,13 @@ def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue
 def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.Tensor] = None,
              last_n: int = 0, per_slot_weight: Optional[torch.Tensor] = None,
              hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0, pool_mode: int = N.POOL_SUM,
-             zero_pad: bool = False, pad_id: int = 0) -> torch.Tensor:
+             zero_pad: bool = False, pad_id: int = 0, num_rows: Optional[int] = None,
+             shard_world: int = 1, shard_rank: int = 0, bags_per_table: int = 0,
+             num_tables: int = 0) -> torch.Tensor:
+    """`num_rows` = GLOBAL rows of one table (default: table.shape[0]).  Sharded (shard_world > 1):
+    `table` is this rank's row-wise shard and the result is this owner's partial pool.
+    Table-batched (bags_per_table > 0): bag g uses table (g // bags_per_table) [% num_tables] of
+    the stacked (local) table."""
     if ids.dim() != 2:
         raise N.NativeError("pooled bags take ids of shape [num_bags, bag_size]")
     ids = ids.contiguous()
@@ -96,9 +103,11 @@ def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.
     dim = table.shape[1]
     out = torch.empty((m, dim), dtype=table.dtype, device=table.device)
     N.check(N.load().recemb_pool_fwd(
-        N.ptr(table), table.shape[0], dim, N.dtype_code(table.dtype), N.ptr(ids), m, p,
-        N.ptr(lengths), last_n, N.ptr(per_slot_weight), hash_mode, hash_arg, pool_mode,
-        int(zero_pad), pad_id, N.ptr(out), dev, N.stream_ptr(dev)), "recemb_pool_fwd")
+        N.ptr(table), table.shape[0] if num_rows is None else num_rows, dim,
+        N.dtype_code(table.dtype), N.ptr(ids), m, p, N.ptr(lengths), last_n, N.ptr(per_slot_weight),
+        hash_mode, hash_arg, pool_mode, int(zero_pad), pad_id,
+        N.make_layout(bags_per_table * p, num_tables, shard_world, shard_rank), N.ptr(out), dev,
+        N.stream_ptr(dev)), "recemb_pool_fwd")
     return out
 
 
@@ -115,8 +124,8 @@ class BackwardPlan:
     def build(ids: torch.Tensor, *, num_rows: int, hash_mode: int = N.HASH_FLOORMOD,
               hash_arg: int = 0, slots_per_id: int = 1, zero_pad: bool = False, pad_id: int = 0,
               pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
-              last_n: int = 0, buf: Optional[torch.Tensor] = None,
-              ids_per_table: int = 0) -> "BackwardPlan":
+              last_n: int = 0, buf: Optional[torch.Tensor] = None, ids_per_table: int = 0,
+              num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0) -> "BackwardPlan":
         """num_rows is rows PER TABLE; with ids_per_table > 0 the plan covers the stacked table
         of ceil(n_ids / ids_per_table) tables and `self.num_rows` is the stacked total."""
         flat = _flat_ids(ids)
@@ -125,13 +134,14 @@ class BackwardPlan:
         dev = N.require_cuda(flat, lengths)
         n_slots = flat.numel() * slots_per_id
         lib = N.load()
-        total_rows = num_rows * (-(-flat.numel() // ids_per_table) if ids_per_table else 1)
+        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank)
+        total_rows = int(lib.recemb_layout_total_rows(num_rows, layout, flat.numel()))
         need = int(lib.recemb_bwd_plan_bytes(n_slots, total_rows))
         if need == 0:
             N.check(-2, "recemb_bwd_plan_bytes")
         if buf is None or buf.numel() < need:
             buf = torch.empty((need,), dtype=torch.uint8, device=flat.device)
-        N.check(lib.recemb_bwd_plan(N.ptr(flat), flat.numel(), ids_per_table, slots_per_id, hash_mode, num_rows,
+        N.check(lib.recemb_bwd_plan(N.ptr(flat), flat.numel(), layout, slots_per_id, hash_mode, num_rows,
                                     hash_arg, int(zero_pad), pad_id, pad_row, bag_size,
                                     N.ptr(lengths), last_n, N.ptr(buf), buf.numel(), dev,
                                     N.stream_ptr(dev)), "recemb_bwd_plan")
@@ -205,6 +215,18 @@ def epilogue_bwd(grad_out: torch.Tensor, out: Optional[torch.Tensor],
                                          g.shape[0], dim, epilogue, num_shifts, N.ptr(dx), dev,
                                          N.stream_ptr(dev)), "recemb_epilogue_bwd")
     return dx
+
+
+def sum_partials(parts: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[world, rows, dim] per-owner partial pools -> [rows, dim], fixed owner order, fp32 accumulate."""
+    parts = parts.contiguous()
+    dev = N.require_cuda(parts, row_scale)
+    w, rows, dim = parts.shape
+    out = torch.empty((rows, dim), dtype=parts.dtype, device=parts.device)
+    N.check(N.load().recemb_sum_partials(N.ptr(parts), w, rows, dim, N.dtype_code(parts.dtype),
+                                         N.ptr(row_scale), N.ptr(out), dev, N.stream_ptr(dev)),
+            "recemb_sum_partials")
+    return out
 
 
 # --------------------------------------------------------- dot interaction ----

@@ -1,0 +1,202 @@
+"""Row-wise sharded pooled embedding bag over the GPUs of one box (north_star item 4, cfg 5).
+
+Global row r of the table lives on rank `r % W` at local row `r // W` (hashed ids make this
+uniformly balanced and it also spreads the k-shift collapse rows round-robin).  One process per
+GPU; torch.distributed (NCCL over NVLink / NVSwitch) is the plumbing.  The reference itself has no
+model-parallel embeddings (tables replicated): sharded == unsharded is the parity
+statement, checked on one GPU (W emulated), on CPU/gloo (host logic) and on N GPUs.
+
+Data path, fixed-size collectives only (no counts exchange, no host sync):
+
+  forward   ids [b, P]  --all_gather-->  [W, b, P]
+            owner: partial pool of EVERY rank's bags over the rows it owns
+                   (recemb_pool_fwd with shard_world / shard_rank: non-owned slots are skipped)
+            partial [W, b, D]  --all_to_all-->  recv [W, b, D] (owner s's partial of MY bags)
+            out = sum over owners in order 0..W-1 (recemb_sum_partials, fp32 accumulate)
+  backward  grad_out [b, D]  --all_gather-->  [W, b, D]
+            owner: sort-based plan over the gathered ids (non-owned slots dropped, keys = local
+                   rows) + segmented reduction + fused update of ITS rows (no gradient all-reduce)
+
+NVLink bytes per GPU per step (W = 8, b = 8192, P = 20, T tables, R = row bytes): ids in
+(W-1) b T P 8, partials in/out (W-1) b T R each way, grads in (W-1) b T R.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _native as N
+from . import ops
+from .layers import pooled_counts
+from .table import EmbeddingTable, FusedOptimizerConfig
+
+
+def local_rows_of(num_embeddings: int, world: int, rank: int) -> int:
+    return (num_embeddings - rank + world - 1) // world
+
+
+# ------------------------------------------------------------ collectives ----
+class Collectives:
+    """all_gather / all_to_all over a process group.  NCCL uses the native collectives; other
+    backends (gloo, for the CPU tests of the host logic) emulate all_to_all with all_gather."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.native_a2a = dist.get_backend(group) == "nccl"
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        flat = t.contiguous().view(-1)
+        out = torch.empty((self.world * flat.numel(),), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
+
+    def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
+        """t [W, ...]: slice s goes to rank s; returns [W, ...] with slice s received from rank s."""
+        t = t.contiguous()
+        if self.native_a2a:
+            out = torch.empty_like(t)
+            dist.all_to_all_single(out, t, group=self.group)
+            return out
+        everyone = self.all_gather(t)          # [W(src), W(dst), ...]
+        return everyone[:, self.rank].contiguous()
+
+
+class SingleProcess(Collectives):
+    """W == 1: identity collectives (no process group needed)."""
+
+    def __init__(self):
+        self.group, self.world, self.rank, self.native_a2a = None, 1, 0, False
+
+    def all_gather(self, t):
+        return t.unsqueeze(0)
+
+    def all_to_all(self, t):
+        return t
+
+
+# ---------------------------------------------------------------- autograd ----
+class _ShardedPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, module):
+        # ids [B, P] with B = T * b bags of this rank (table-major when T > 1)
+        comm: Collectives = module.comm
+        w, b, p = comm.world, ids.shape[0], ids.shape[1]
+        ids_all = comm.all_gather(ids).view(w * b, p)
+        len_all = None if lengths is None else comm.all_gather(lengths.to(torch.int32)).view(w * b)
+        partial = module.local_pool(module.emb.weight.detach(), ids_all, len_all)      # [W*B, D]
+        recv = comm.all_to_all(partial.view(w, b, -1))                                 # [W, B, D]
+        scale = None
+        if module.mode == "mean":
+            scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad,
+                                        module.pad_id).clamp_(min=1).float()
+        ctx.module = module
+        ctx.save_for_backward(ids_all, len_all, scale)
+        return module.reduce_partials(recv, scale)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids_all, len_all, scale = ctx.saved_tensors
+        module = ctx.module
+        g = grad_out.contiguous()
+        if scale is not None:
+            g = g * scale.unsqueeze(1).to(g.dtype)
+        g_all = module.comm.all_gather(g).view(ids_all.shape[0], -1)                   # [W*b, D]
+        return module.local_backward(ids_all, len_all, g_all), None, None, None
+
+
+class RowWiseShardedEmbeddingBag(nn.Module):
+    """Pooled multi-hot lookup into a row-wise sharded table.
+
+    forward(ids [b, P] int64 of THIS rank's batch, lengths [b] optional) -> [b, D]; with
+    num_tables = T > 1 (T equal-shaped tables, one launch / one collective for all of them):
+    ids [T, b, P], lengths [T, b] -> [T, b, D].
+    `emb.weight` holds this rank's shard [T * ceil((N - rank) / W), D] (state_dict key
+    `emb.weight`; `gather_full_weight()` reassembles the global table(s) for a reference-shaped
+    checkpoint)."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, mode: str = "sum", *, last_n: int = 0,
+                 num_tables: int = 1, skip_pad: bool = False, pad_id: int = 0, group=None,
+                 comm: Optional[Collectives] = None,
+                 dtype: torch.dtype = torch.float32, device=None,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None,
+                 local_pool: Optional[Callable] = None, local_backward: Optional[Callable] = None,
+                 reduce_partials: Optional[Callable] = None):
+        super().__init__()
+        if mode not in ("sum", "mean"):
+            raise ValueError("mode must be 'sum' or 'mean'")
+        if comm is None:
+            comm = Collectives(group) if dist.is_available() and dist.is_initialized() else SingleProcess()
+        self.comm = comm
+        self.num_embeddings, self.emb_dim = int(num_embeddings), int(emb_dim)
+        self.mode, self.last_n, self.skip_pad, self.pad_id = mode, int(last_n), skip_pad, pad_id
+        self.num_tables = int(num_tables)
+        self.local_rows = local_rows_of(num_embeddings, comm.world, comm.rank)
+        self.emb = EmbeddingTable(self.num_tables * self.local_rows, emb_dim, dtype=dtype, device=device)
+        if fused_optimizer is not None:
+            self.emb.enable_fused_optimizer(fused_optimizer)
+        # the three compute hooks default to the CUDA kernels; tests of the host logic on
+        # CPU/gloo inject oracle implementations (never done in product code)
+        self.local_pool = local_pool or self._cuda_local_pool
+        self.local_backward = local_backward or self._cuda_local_backward
+        self.reduce_partials = reduce_partials or ops.sum_partials
+
+    # ----------------------------------------------------------- CUDA hooks ----
+    def _cuda_local_pool(self, shard, ids_all, len_all):
+        return ops.pool_fwd(shard, ids_all, lengths=len_all, last_n=self.last_n, pool_mode=N.POOL_SUM,
+                            zero_pad=self.skip_pad, pad_id=self.pad_id, num_rows=self.num_embeddings,
+                            shard_world=self.comm.world, shard_rank=self.comm.rank, **self._batching(ids_all))
+
+    def _cuda_local_backward(self, ids_all, len_all, g_all):
+        plan = ops.BackwardPlan.build(
+            ids_all, num_rows=self.num_embeddings, zero_pad=self.skip_pad, pad_id=self.pad_id,
+            bag_size=ids_all.shape[1], lengths=len_all, last_n=self.last_n,
+            shard_world=self.comm.world, shard_rank=self.comm.rank,
+            ids_per_table=self._batching(ids_all)["bags_per_table"] * ids_all.shape[1],
+            num_tables=self._batching(ids_all)["num_tables"])
+        return self.emb.consume(plan, g_all, slots_per_grad_row=ids_all.shape[1])
+
+    def _batching(self, ids_all):
+        """gathered bags are [W, T, b]: bag g belongs to table (g // b) % T."""
+        if self.num_tables == 1:
+            return dict(bags_per_table=0, num_tables=0)
+        b = ids_all.shape[0] // (self.comm.world * self.num_tables)
+        return dict(bags_per_table=b, num_tables=self.num_tables)
+
+    # -------------------------------------------------------------- forward ----
+    def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if ids.dtype != torch.int64 or ids.dim() != (2 if self.num_tables == 1 else 3):
+            raise N.NativeError("ids must be int64 [batch, bag_size] ([num_tables, batch, bag_size] when batched)")
+        if self.num_tables == 1:
+            return _ShardedPoolFn.apply(self.emb.grad_anchor(), ids.contiguous(), lengths, self)
+        t, b, p = ids.shape
+        if t != self.num_tables:
+            raise N.NativeError(f"expected ids for {self.num_tables} tables, got {t}")
+        out = _ShardedPoolFn.apply(self.emb.grad_anchor(), ids.contiguous().view(t * b, p),
+                                   None if lengths is None else lengths.contiguous().view(t * b), self)
+        return out.view(t, b, -1)
+
+    @torch.no_grad()
+    def load_full_weight(self, full: torch.Tensor) -> None:
+        """Take this rank's rows (r % W == rank) out of a global [N, D] (or [T, N, D]) table."""
+        full = full.view(self.num_tables, self.num_embeddings, self.emb_dim)
+        shard = full[:, self.comm.rank::self.comm.world].reshape(-1, self.emb_dim)
+        self.emb.weight.copy_(shard.to(self.emb.weight.device, self.emb.weight.dtype))
+
+    @torch.no_grad()
+    def gather_full_weight(self) -> torch.Tensor:
+        """Global [N, D] ([T, N, D]) table under the unsharded module's key (checkpoint / export)."""
+        w, t = self.comm.world, self.num_tables
+        rows_max = local_rows_of(self.num_embeddings, w, 0)
+        mine = self.emb.weight.view(t, self.local_rows, self.emb_dim)
+        pad = torch.zeros((t, rows_max, self.emb_dim), dtype=mine.dtype, device=mine.device)
+        pad[:, :self.local_rows] = mine
+        shards = self.comm.all_gather(pad)                                  # [W, T, rows_max, D]
+        full = torch.empty((t, self.num_embeddings, self.emb_dim), dtype=pad.dtype, device=pad.device)
+        for s in range(w):
+            full[:, s::w] = shards[s, :, :local_rows_of(self.num_embeddings, w, s)]
+        return full[0] if t == 1 else full

@@ -53,13 +53,20 @@ class EmbeddingTable(nn.Module):
         self.padding_idx = padding_idx
         self.sparse = bool(sparse)
         if _weight is None:
-            # nn.Embedding.reset_parameters: N(0, 1), padding row zeroed
-            w = torch.empty((self.num_embeddings, self.embedding_dim), dtype=torch.float32)
-            nn.init.normal_(w)
+            # nn.Embedding.reset_parameters: N(0, 1), padding row zeroed.  On the CPU generator
+            # (device None / cpu) the values equal nn.Embedding's under the same seed; a table
+            # created straight on a CUDA device is filled there, in its own dtype, so that
+            # tens-of-GB shards never exist on the host or in fp32.
+            if device is not None and torch.device(device).type == "cuda":
+                w = torch.empty((self.num_embeddings, self.embedding_dim), dtype=dtype, device=device)
+                w.normal_()
+            else:
+                w = torch.empty((self.num_embeddings, self.embedding_dim), dtype=torch.float32)
+                nn.init.normal_(w)
+                w = w.to(dtype=dtype, device=device)
             if padding_idx is not None:
                 with torch.no_grad():
                     w[padding_idx].fill_(0)
-            w = w.to(dtype=dtype, device=device)
         else:
             w = _weight
         self.weight = nn.Parameter(w)

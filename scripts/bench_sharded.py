@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""cfg 5 (BASELINE.json configs[4]): large-vocab row-wise sharded tables, weak scaling.
+
+  torchrun --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 scripts/bench_sharded.py [--check]
+
+Per GPU: T = 8 tables of 25 M x 128 bf16 rows (51.2 GB; W = 8 -> the named 8 x 200 M x 128),
+local batch b = 8192 bags of P = 20 uniform int64 ids per table, pooled sum, fused row-wise
+Adagrad.  --check first verifies sharded == unsharded at a reduced vocabulary with the real
+NCCL collectives and CUDA kernels.  Prints one JSON line (rank 0)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import recommendations_b200 as R  # noqa: E402
+from recommendations_b200 import _native as N  # noqa: E402
+from recommendations_b200.sharded import RowWiseShardedEmbeddingBag  # noqa: E402
+
+T, B_LOCAL, P, DIM = 8, 8192, 20, 128
+NVLINK_GBS = 770.0
+
+
+def ids_for(rank, t_tables, b, p, seed=5000):
+    g = torch.Generator().manual_seed(seed + 8 * rank)
+    return torch.randint(-2 ** 63, 2 ** 63 - 1, (t_tables, b, p), generator=g, dtype=torch.int64)
+
+
+def check(world, rank, dev):
+    """sharded == unsharded at N = 100003 rows x 4 tables, fp32, both directions."""
+    from oracle import embedding_oracle as O
+    n_rows, dim, t, b, p = 100003, 64, 4, 257, 20
+    torch.manual_seed(99)
+    full = torch.randn(t, n_rows, dim)
+    mod = RowWiseShardedEmbeddingBag(n_rows, dim, num_tables=t, device=dev)
+    mod.load_full_weight(full)
+    ids = ids_for(rank, t, b, p, seed=7000)
+    lengths = torch.randint(0, p + 1, (t, b), generator=torch.Generator().manual_seed(rank))
+    go = torch.randn(t, b, dim, generator=torch.Generator().manual_seed(50 + rank))
+    out = mod(ids.to(dev), lengths.to(dev))
+    for ti in range(t):
+        want = O.pooled_bag(full[ti], ids[ti], lengths=lengths[ti])
+        torch.testing.assert_close(out[ti].cpu(), want, rtol=1e-5, atol=1e-5)
+    out.backward(go.to(dev))
+    # unsharded reference gradient over the GLOBAL batch
+    gw = torch.zeros(t, n_rows, dim)
+    for r in range(world):
+        ids_r = ids_for(r, t, b, p, seed=7000)
+        len_r = torch.randint(0, p + 1, (t, b), generator=torch.Generator().manual_seed(r))
+        go_r = torch.randn(t, b, dim, generator=torch.Generator().manual_seed(50 + r))
+        for ti in range(t):
+            rows = O.row_index(ids_r[ti], n_rows, 0)
+            use = torch.arange(p).unsqueeze(0) < len_r[ti].unsqueeze(1)
+            gw[ti].index_add_(0, rows[use], go_r[ti].unsqueeze(1).expand(-1, p, -1)[use])
+    mine = gw[:, rank::world].reshape(-1, dim)
+    torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(mod.gather_full_weight().cpu(), full)
+    if rank == 0:
+        print(f"[check] sharded == unsharded on {world} rank(s): ok", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.check:
+        check(world, rank, dev)
+
+    n_rows = args.rows_per_gpu * world
+    mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev,
+                                     fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
+    ids_host = ids_for(rank, T, B_LOCAL, P).pin_memory()
+    ids = ids_host.to(dev)
+    grad = torch.randn(T, B_LOCAL, DIM, device=dev, dtype=torch.bfloat16)
+
+    def step():
+        out = mod(ids)
+        out.backward(grad)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    lookups = world * T * B_LOCAL * P
+    row_bytes = DIM * 2
+    nv_in = (world - 1) * T * B_LOCAL * (P * 8 + 2 * row_bytes)   # ids + partials (fwd) + grads (bwd), per GPU
+    if rank == 0:
+        t_step = ms / args.steps * 1e-3
+        print(json.dumps({
+            "metric": "embedding_lookups_per_sec_fwd_bwd", "value": lookups / t_step, "unit": "lookups/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 row-wise sharded over {world} GPU(s), "
+                                   f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
+                       "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes},
+            "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
+                       "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
+            "gpu_launches": N.launch_count() - launches0}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,11 +47,11 @@ def test_argument_errors_are_codes_not_crashes():
     assert lib.recemb_row_index(None, 4, N.HASH_FLOORMOD, 10, 0, None, 0, None) == -1
     assert b"null" in lib.recemb_last_error()
     # row bytes not a multiple of 16
-    rc = lib.recemb_gather_fwd(1 << 20, 10, None, 0, 3, N.F32, 1 << 20, 4, 0, N.HASH_FLOORMOD, 0, 0,
+    rc = lib.recemb_gather_fwd(1 << 20, 10, None, 0, 3, N.F32, 1 << 20, 4, None, N.HASH_FLOORMOD, 0, 0,
                                N.EPI_NONE, 0, 0, 1 << 20, None, 0, None)
     assert rc == -3 and b"16 bytes" in lib.recemb_last_error()
     # unknown hash mode
-    rc = lib.recemb_gather_fwd(1 << 20, 10, None, 0, 4, N.F32, 1 << 20, 4, 0, 99, 0, 0, N.EPI_NONE, 0, 0,
+    rc = lib.recemb_gather_fwd(1 << 20, 10, None, 0, 4, N.F32, 1 << 20, 4, None, 99, 0, 0, N.EPI_NONE, 0, 0,
                                1 << 20, None, 0, None)
     assert rc == -1
     # bad k

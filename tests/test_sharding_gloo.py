@@ -1,0 +1,115 @@
+"""Host logic of the row-wise sharded bag on CPU with gloo, world_size 2: collectives, owner
+mapping, partial-sum reduction, gradient routing.  The three compute hooks are replaced by
+oracle implementations HERE ONLY (the product hooks are the CUDA kernels); the test proves
+sharded == unsharded."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import embedding_oracle as O
+
+N_ROWS, DIM, B, P = 1001, 16, 37, 5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _window(ids, lengths, last_n):
+    m, p = ids.shape
+    pos = torch.arange(p).unsqueeze(0)
+    hi = torch.full((m, 1), p) if lengths is None else lengths.long().clamp(0, p).unsqueeze(1)
+    lo = (hi - last_n).clamp(min=0) if last_n > 0 else torch.zeros_like(hi)
+    return (pos >= lo) & (pos < hi)
+
+
+def _make_hooks(world, rank, last_n):
+    def local_pool(shard, ids_all, len_all):
+        rows = O.row_index(ids_all, N_ROWS, 0)
+        use = _window(ids_all, len_all, last_n) & (rows % world == rank)
+        loc = torch.div(rows, world, rounding_mode="floor")
+        out = torch.zeros(ids_all.shape[0], shard.shape[1])
+        for j in range(ids_all.shape[1]):
+            out = torch.where(use[:, j:j + 1], out + shard[loc[:, j].clamp(max=shard.shape[0] - 1)], out)
+        return out
+
+    def local_backward(ids_all, len_all, g_all):
+        rows = O.row_index(ids_all, N_ROWS, 0)
+        use = _window(ids_all, len_all, last_n) & (rows % world == rank)
+        loc = torch.div(rows, world, rounding_mode="floor")
+        n_local = (N_ROWS - rank + world - 1) // world
+        gw = torch.zeros(n_local, g_all.shape[1])
+        g = g_all.unsqueeze(1).expand(-1, ids_all.shape[1], -1)
+        gw.index_add_(0, loc[use], g[use])
+        return gw
+
+    def reduce(recv, scale):
+        out = recv.sum(0)
+        return out if scale is None else out * scale.unsqueeze(1)
+
+    return local_pool, local_backward, reduce
+
+
+def _worker(rank, world, port, mode, last_n, result):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+        torch.manual_seed(0)
+        full = torch.randn(N_ROWS, DIM)
+        g = torch.Generator().manual_seed(100 + rank)
+        ids = torch.randint(-2 ** 63, 2 ** 63 - 1, (B, P), generator=g, dtype=torch.int64)
+        lengths = torch.randint(0, P + 1, (B,), generator=g)
+        go = torch.randn(B, DIM, generator=g)
+        lp, lb, rd = _make_hooks(world, rank, last_n)
+        mod = RowWiseShardedEmbeddingBag(N_ROWS, DIM, mode=mode, last_n=last_n, local_pool=lp,
+                                         local_backward=lb, reduce_partials=rd)
+        assert mod.emb.weight.shape[0] == (N_ROWS - rank + world - 1) // world
+        mod.load_full_weight(full)
+        out = mod(ids, lengths)
+        want = O.pooled_bag(full, ids, lengths=lengths, last_n=last_n, mode=mode)
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+        out.backward(go)
+        # unsharded gradient of the GLOBAL batch (all ranks' bags), then this rank's rows
+        all_ids = [torch.empty_like(ids) for _ in range(world)]
+        all_len = [torch.empty_like(lengths) for _ in range(world)]
+        all_go = [torch.empty_like(go) for _ in range(world)]
+        dist.all_gather(all_ids, ids)
+        dist.all_gather(all_len, lengths)
+        dist.all_gather(all_go, go)
+        wr = full.clone().requires_grad_(True)
+        for i, l, gg in zip(all_ids, all_len, all_go):
+            rows = O.row_index(i, N_ROWS, 0)
+            use = _window(i, l, last_n).float().unsqueeze(-1)
+            pooled = (wr[rows] * use).sum(1)
+            if mode == "mean":
+                pooled = pooled / use.sum(1).clamp(min=1)
+            pooled.backward(gg)
+        torch.testing.assert_close(mod.emb.weight.grad, wr.grad[rank::world], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(mod.gather_full_weight(), full)
+        result[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,last_n", [("sum", 0), ("mean", 0), ("sum", 2)])
+def test_sharded_equals_unsharded_gloo_world2(mode, last_n):
+    world = 2
+    result = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), mode, last_n, result), nprocs=world, join=True)
+    assert dict(result) == {0: 1, 1: 1}
+
+
+def test_local_rows_partition_is_exact():
+    from recommendations_b200.sharded import local_rows_of
+    for n in (1, 7, 8, 9, 1000, 200_000_000):
+        for w in (1, 2, 4, 8):
+            assert sum(local_rows_of(n, w, r) for r in range(w)) == n
