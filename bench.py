@@ -268,6 +268,19 @@ def run_b200(args):
     # ---- end to end: HOST ids -> C-ABI host entry point -> device result read back ----
     e2e = run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier)
 
+    # ---- N > 1: also time the path that really exchanges data over NVLink (cfg 5: row-wise
+    # sharded large-vocab tables, id all-gather + partial-sum all-to-all), same process group
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del table_all, state_all, grads, outs, plan_buf, ws_buf
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, str(ROOT / "scripts"))
+            import bench_sharded
+            sharded = bench_sharded.run_cfg5(world, rank, dev, args.steps, args.warmup)
+        except Exception as exc:  # the headline line must survive a failure of the extra run
+            sharded = {"error": f"{type(exc).__name__}: {exc}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         w_cpu = table_all[:ROWS].cpu()  # NB: already updated by the timed steps -- any weights do
@@ -289,6 +302,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2: 419 MB out + 419 MB grad + 256 MB table per table vs 126 MB",
                        "multi_gpu": "replicas (tables replicated as in the reference), weak scaling"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "sharded_cfg5": sharded,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -375,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"[bench] note: warmup {args.warmup} < 3", file=sys.stderr)

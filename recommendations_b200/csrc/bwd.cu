@@ -152,54 +152,61 @@ __global__ void __launch_bounds__(kBwdThreads) plan_count_kernel(const uint32_t*
 }
 
 // ---------------------------------------------------- segmented reduction ----
-// Rows are handled as "quads" of 4 consecutive elements (16 B of fp32 / 8 B of
-// bf16): G lanes x V quads per lane cover a row.
+// A row is covered by G lanes x V vectors per lane; a lane-vector is E consecutive elements:
+// E = 4 (16 B of fp32, 8 B of bf16) in general, E = 8 when gradients and table are both bf16
+// (one 16-byte load per lane: half the instructions per row of the E = 4 mapping).
 template <typename T>
-__device__ __forceinline__ void load_quad(const T* p, float* f);
-template <>
-__device__ __forceinline__ void load_quad<float>(const float* p, float* f) {
-  const uint4 v = ldg_v4(p);
-  Vec16<float>::unpack(v, f);
-}
-template <>
-__device__ __forceinline__ void load_quad<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p);
+__device__ __forceinline__ void unpack16(const uint4& v, float* f) { Vec16<T>::unpack(v, f); }
+__device__ __forceinline__ void unpack_bf16x4(const uint2& v, float* f) {
   f[0] = __uint_as_float(v.x << 16);
   f[1] = __uint_as_float(v.x & 0xffff0000u);
   f[2] = __uint_as_float(v.y << 16);
   f[3] = __uint_as_float(v.y & 0xffff0000u);
 }
-// gradients / partial sums are streamed exactly once: keep them out of L1
-template <typename T>
-__device__ __forceinline__ void load_quad_stream(const T* p, float* f);
-template <>
-__device__ __forceinline__ void load_quad_stream<float>(const float* p, float* f) {
-  const uint4 v = ldg_nc_v4(p);
-  Vec16<float>::unpack(v, f);
+
+// STREAM: data read exactly once (gradients, partial records) -> ld.global.nc.L1::no_allocate
+template <typename T, int E, bool STREAM>
+__device__ __forceinline__ void load_vec(const T* p, float* f) {
+  constexpr int BYTES = E * (int)sizeof(T);
+  static_assert(BYTES == 8 || BYTES == 16 || BYTES == 32, "lane vector must be 8, 16 or 32 bytes");
+  if constexpr (BYTES == 8) {  // 4 bf16
+    uint2 v;
+    if constexpr (STREAM)
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    else
+      v = *reinterpret_cast<const uint2*>(p);
+    unpack_bf16x4(v, f);
+  } else if constexpr (BYTES == 16) {  // 4 fp32 or 8 bf16
+    const uint4 v = STREAM ? ldg_nc_v4(p) : ldg_v4(p);
+    unpack16<T>(v, f);
+  } else {  // 8 fp32
+    const uint4 v0 = STREAM ? ldg_nc_v4(p) : ldg_v4(p);
+    const uint4 v1 = STREAM ? ldg_nc_v4(p + 4) : ldg_v4(p + 4);
+    unpack16<T>(v0, f);
+    unpack16<T>(v1, f + 4);
+  }
 }
-template <>
-__device__ __forceinline__ void load_quad_stream<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
-  uint2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  f[0] = __uint_as_float(v.x << 16);
-  f[1] = __uint_as_float(v.x & 0xffff0000u);
-  f[2] = __uint_as_float(v.y << 16);
-  f[3] = __uint_as_float(v.y & 0xffff0000u);
+template <typename T, int E>
+__device__ __forceinline__ void store_vec(T* p, const float* f) {
+  constexpr int BYTES = E * (int)sizeof(T);
+  if constexpr (BYTES == 8) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+  } else if constexpr (BYTES == 16) {
+    stg_v4(p, Vec16<T>::pack(f));
+  } else {
+    stg_v4(p, Vec16<T>::pack(f));
+    stg_v4(p + 4, Vec16<T>::pack(f + 4));
+  }
 }
-template <typename T>
-__device__ __forceinline__ void store_quad(T* p, const float* f);
-template <>
-__device__ __forceinline__ void store_quad<float>(float* p, const float* f) {
-  stg_v4(p, Vec16<float>::pack(f));
-}
-template <>
-__device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
-  uint2 v;
-  v.x = *reinterpret_cast<uint32_t*>(&a);
-  v.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = v;
+template <typename T, int E>
+__device__ __forceinline__ void prefetch_vec(const T* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if constexpr (E * (int)sizeof(T) == 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 4));
 }
 
 struct SegArgs {
@@ -208,7 +215,7 @@ struct SegArgs {
   int32_t n;              // entries at this level (< 2^31)
   const void* grad;       // level 0: [grad_rows, dim] GT ; level >= 1: fp32 partials [n, dim]
   uint32_t dim;
-  int32_t quads;          // dim / 4
+  int32_t vecs;           // dim / E lane-vectors per row
   uint32_t spg;           // slots per gradient row (k shifts / bag size), >= 1
   uint32_t spg_magic;     // floor(2^32 / spg): slot / spg without an integer divide
   const float* slot_weight;
@@ -253,51 +260,51 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 // UPD >= 0: the update kind is a compile-time constant (dead variants disappear);
 // UPD < 0: read a.update at run time.  EXACT: the row is exactly G*V quads.
-template <int G, int V, typename WT, int UPD, bool EXACT>
-__device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float (&g)[V][4], int lig,
+template <int G, int V, int E, typename WT, int UPD, bool EXACT>
+__device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float (&g)[V][E], int lig,
                                           uint32_t gmask) {
   const int upd = UPD >= 0 ? UPD : a.update;
-  const size_t off = (size_t)row * a.dim + lig * 4;
+  const size_t off = (size_t)row * a.dim + lig * E;
   WT* wrow = reinterpret_cast<WT*>(a.table) + off;
   const recemb_optim_params& hp = a.hp;
-  auto live = [&](int j) { return EXACT || (j * G + lig) < a.quads; };
+  auto live = [&](int j) { return EXACT || (j * G + lig) < a.vecs; };
   if (upd == RECEMB_UPD_DENSE_GRAD) {
 #pragma unroll
     for (int j = 0; j < V; ++j)
-      if (live(j)) store_quad<WT>(wrow + j * G * 4, g[j]);
+      if (live(j)) store_vec<WT, E>(wrow + j * G * E, g[j]);
     return;
   }
-  float w[V][4];
+  float w[V][E];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) w[j][e] = 0.f;
-    if (live(j)) load_quad<WT>(wrow + j * G * 4, w[j]);
+    for (int e = 0; e < E; ++e) w[j][e] = 0.f;
+    if (live(j)) load_vec<WT, E, false>(wrow + j * G * E, w[j]);
   }
   if (hp.weight_decay != 0.f && upd != RECEMB_UPD_ADAMW) {
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) g[j][e] += hp.weight_decay * w[j][e];
+      for (int e = 0; e < E; ++e) g[j][e] += hp.weight_decay * w[j][e];
   }
   if (upd == RECEMB_UPD_SGD) {
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[j][e] -= hp.lr * g[j][e];
+      for (int e = 0; e < E; ++e) w[j][e] -= hp.lr * g[j][e];
   } else if (upd == RECEMB_UPD_ADAGRAD) {
     float* srow = a.state1 + off;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (live(j)) {
-        float s[4];
-        load_quad<float>(srow + j * G * 4, s);
+        float s[E];
+        load_vec<float, E, false>(srow + j * G * E, s);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < E; ++e) {
           s[e] += g[j][e] * g[j][e];
           w[j][e] += (-hp.lr * g[j][e]) * fast_rcp(fast_sqrt(s[e]) + hp.eps);
         }
-        store_quad<float>(srow + j * G * 4, s);
+        store_vec<float, E>(srow + j * G * E, s);
       }
     }
   } else if (upd == RECEMB_UPD_ROWWISE_ADAGRAD) {
@@ -305,14 +312,14 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ss += g[j][e] * g[j][e];  // lanes past the row hold zeros
+      for (int e = 0; e < E; ++e) ss += g[j][e] * g[j][e];  // lanes past the row hold zeros
     ss = masked_group_sum<G>(ss, gmask) / (float)a.dim;
     const float s_new = a.state1[row] + ss;
     const float inv = -hp.lr * fast_rcp(fast_sqrt(s_new) + hp.eps);
 #pragma unroll
     for (int j = 0; j < V; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[j][e] += g[j][e] * inv;
+      for (int e = 0; e < E; ++e) w[j][e] += g[j][e] * inv;
     __syncwarp(gmask);  // every lane has read state1[row] before lane 0 overwrites it
     if (lig == 0) a.state1[row] = s_new;
   } else {  // ADAM / ADAMW, lazy: only touched rows move
@@ -323,25 +330,25 @@ __device__ __forceinline__ void apply_row(const SegArgs& a, uint32_t row, float 
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (live(j)) {
-        float m[4], v[4];
-        load_quad<float>(mrow + j * G * 4, m);
-        load_quad<float>(vrow + j * G * 4, v);
+        float m[E], v[E];
+        load_vec<float, E, false>(mrow + j * G * E, m);
+        load_vec<float, E, false>(vrow + j * G * E, v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < E; ++e) {
           if (upd == RECEMB_UPD_ADAMW) w[j][e] *= (1.f - hp.lr * hp.weight_decay);
           m[e] = hp.beta1 * m[e] + (1.f - hp.beta1) * g[j][e];
           v[e] = hp.beta2 * v[e] + (1.f - hp.beta2) * g[j][e] * g[j][e];
           const float denom = fast_sqrt(v[e]) * inv_bc2_sqrt + hp.eps;
           w[j][e] -= step_size * m[e] * fast_rcp(denom);
         }
-        store_quad<float>(mrow + j * G * 4, m);
-        store_quad<float>(vrow + j * G * 4, v);
+        store_vec<float, E>(mrow + j * G * E, m);
+        store_vec<float, E>(vrow + j * G * E, v);
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < V; ++j)
-    if (live(j)) store_quad<WT>(wrow + j * G * 4, w[j]);
+    if (live(j)) store_vec<WT, E>(wrow + j * G * E, w[j]);
 }
 
 // Compile-time shape of one instantiation of the walk.
@@ -364,7 +371,7 @@ struct SegCfg {
 // (its last run continues into chunk c+1).  The two halves of a run cut by ONE boundary are
 // therefore the aligned pair (2c, 2c+1): the next level closes them inside one chunk, and
 // only runs longer than a chunk reach the levels above (which exit on an empty-level flag).
-template <int G, int V, typename GT, typename WT, bool L0, int CH, typename Cfg>
+template <int G, int V, int E, typename GT, typename WT, bool L0, int CH, typename Cfg>
 __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegArgs a) {
   if (!L0 && *a.flag_in == 0) return;  // the previous level emitted nothing
   constexpr int B = Cfg::B, PD = Cfg::PD;
@@ -387,12 +394,12 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
   }
 
   const int upd = Cfg::UPD >= 0 ? Cfg::UPD : a.update;
-  const GT* gbase = reinterpret_cast<const GT*>(a.grad) + lig * 4;
-  const WT* tbase = reinterpret_cast<const WT*>(a.table) + lig * 4;
+  const GT* gbase = reinterpret_cast<const GT*>(a.grad) + lig * E;
+  const WT* tbase = reinterpret_cast<const WT*>(a.table) + lig * E;
   const bool pf_w = upd != RECEMB_UPD_DENSE_GRAD;
   const bool pf_s1 = upd == RECEMB_UPD_ADAGRAD || upd >= RECEMB_UPD_ADAM;
   const bool pf_s2 = upd >= RECEMB_UPD_ADAM;
-  auto live = [&](int j) { return EXACT || (j * G + lig) < a.quads; };
+  auto live = [&](int j) { return EXACT || (j * G + lig) < a.vecs; };
 
   auto grad_row_of = [&](int i, uint32_t slot) -> uint32_t {
     if (!L0) return (uint32_t)i;
@@ -421,15 +428,15 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
         const GT* src = gbase + (size_t)grad_row_of(e0 + u, ss[u]) * a.dim;
 #pragma unroll
         for (int j = 0; j < V; ++j)
-          if (live(j)) prefetch_l2(src + j * G * 4);
+          if (live(j)) prefetch_vec<GT, E>(src + j * G * E);
         if (pf_w && kk[u + 1] != kk[u]) {  // this run ends here: its row will be updated
           const size_t off = (size_t)kk[u] * a.dim;
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             if (live(j)) {
-              prefetch_l2(tbase + off + j * G * 4);
-              if (pf_s1) prefetch_l2(a.state1 + off + lig * 4 + j * G * 4);
-              if (pf_s2) prefetch_l2(a.state2 + off + lig * 4 + j * G * 4);
+              prefetch_vec<WT, E>(tbase + off + j * G * E);
+              if (pf_s1) prefetch_vec<float, E>(a.state1 + off + lig * E + j * G * E);
+              if (pf_s2) prefetch_vec<float, E>(a.state2 + off + lig * E + j * G * E);
             }
           }
           if (upd == RECEMB_UPD_ROWWISE_ADAGRAD && lig == 0) prefetch_l2(a.state1 + kk[u]);
@@ -444,32 +451,32 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
   uint32_t cur = a.keys[start];
   const bool left_open = start > 0 && a.keys[start - 1] == cur;
   bool first = true;
-  float acc[V][4];
+  float acc[V][E];
 #pragma unroll
   for (int j = 0; j < V; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    for (int e = 0; e < E; ++e) acc[j][e] = 0.f;
 
   auto flush = [&](uint32_t key, bool leading, bool trailing) {
     if (key >= a.sentinel) return;
     if (!leading && !trailing) {
-      apply_row<G, V, WT, Cfg::UPD, EXACT>(a, key, acc, lig, gmask);
+      apply_row<G, V, E, WT, Cfg::UPD, EXACT>(a, key, acc, lig, gmask);
       return;
     }
     const int rec = leading ? 2 * chunk - 1 : 2 * chunk;
-    float* dst = a.out_partials + (size_t)rec * a.dim + lig * 4;
+    float* dst = a.out_partials + (size_t)rec * a.dim + lig * E;
 #pragma unroll
     for (int j = 0; j < V; ++j)
-      if (live(j)) store_quad<float>(dst + j * G * 4, acc[j]);
+      if (live(j)) store_vec<float, E>(dst + j * G * E, acc[j]);
     if (lig == 0) {
       a.out_keys[rec] = key;
       *a.flag_out = 1u;
     }
     if (leading && trailing) {  // the whole chunk is one run open on both sides
-      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      float z[E] = {};
 #pragma unroll
       for (int j = 0; j < V; ++j)
-        if (live(j)) store_quad<float>(dst + a.dim + j * G * 4, z);
+        if (live(j)) store_vec<float, E>(dst + a.dim + j * G * E, z);
       if (lig == 0) a.out_keys[rec + 1] = key;
     }
   };
@@ -478,7 +485,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
     prefetch_batch(e0 + PD * B);
     uint32_t k[B + 1], sl[B];
     load_meta(e0, k, sl);
-    float g[B][V][4];
+    float g[B][V][E];
     float wt[B];
 #pragma unroll
     for (int u = 0; u < B; ++u) {
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
 #pragma unroll
       for (int j = 0; j < V; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g[u][j][e] = 0.f;
+        for (int e = 0; e < E; ++e) g[u][j][e] = 0.f;
       if (k[u] < a.sentinel) {
         const uint32_t grow = grad_row_of(e0 + u, sl[u]);
         if (L0 && !PLAIN) {
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
         const GT* src = gbase + (size_t)grow * a.dim;
 #pragma unroll
         for (int j = 0; j < V; ++j)
-          if (live(j)) load_quad_stream<GT>(src + j * G * 4, g[u][j]);
+          if (live(j)) load_vec<GT, E, true>(src + j * G * E, g[u][j]);
       }
     }
 #pragma unroll
@@ -509,19 +516,19 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
 #pragma unroll
           for (int j = 0; j < V; ++j)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+            for (int e = 0; e < E; ++e) acc[j][e] = 0.f;
         }
         if (k[u] < a.sentinel) {
           if (L0 && !PLAIN && (a.slot_weight || a.grad_row_scale)) {
 #pragma unroll
             for (int j = 0; j < V; ++j)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[j][e] += wt[u] * g[u][j][e];
+              for (int e = 0; e < E; ++e) acc[j][e] += wt[u] * g[u][j][e];
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[j][e] += g[u][j][e];
+              for (int e = 0; e < E; ++e) acc[j][e] += g[u][j][e];
           }
         }
       }
@@ -552,19 +559,19 @@ static bool pick_quads(int quads, QuadShape* s) {
 constexpr int kChunk0 = RECEMB_CHUNK0;  // sorted entries per group at level 0
 constexpr int kChunkN = 32;             // records per group at levels >= 1
 
-template <int G, int V, typename GT, typename WT, bool L0, typename Cfg>
+template <int G, int V, int E, typename GT, typename WT, bool L0, typename Cfg>
 static void launch_one(const SegArgs& a, cudaStream_t s) {
   constexpr int CH = L0 ? kChunk0 : kChunkN;
   const int chunks = (a.n + CH - 1) / CH;
   const int groups = kBwdThreads / G;
-  seg_kernel<G, V, GT, WT, L0, CH, Cfg><<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
+  seg_kernel<G, V, E, GT, WT, L0, CH, Cfg><<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
 }
 
 // generic instantiations: any shape / update / scale combination
 #define SEG_GV(G_, V_)                                                                          \
   if (shape.G == G_ && shape.V == V_) {                                                         \
     using Cfg = SegCfg<(V_ == 1) ? 2 : 1, 2, (V_ == 1) ? 4 : (V_ == 2 ? 2 : 1), -1, false, false>; \
-    launch_one<G_, V_, GT, WT, L0, Cfg>(a, s);                                                  \
+    launch_one<G_, V_, 4, GT, WT, L0, Cfg>(a, s);                                                  \
     launched = true;                                                                            \
   }
 
@@ -572,18 +579,19 @@ static void launch_one(const SegArgs& a, cudaStream_t s) {
 // D = 64 fp32 -> G = 16, D = 128 bf16 -> G = 32), update kind fixed at compile time
 template <int G, typename GT, typename WT, bool PLAIN, int B, int PD, int MINB>
 static bool launch_fast(const SegArgs& a, cudaStream_t s) {
+  constexpr int E = 16 / (int)sizeof(WT);  // fast path: one 16-byte vector per lane
   switch (a.update) {
     case RECEMB_UPD_ADAGRAD:
-      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ADAGRAD, PLAIN, true>>(a, s);
+      launch_one<G, 1, E, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ADAGRAD, PLAIN, true>>(a, s);
       return true;
     case RECEMB_UPD_ROWWISE_ADAGRAD:
-      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ROWWISE_ADAGRAD, PLAIN, true>>(a, s);
+      launch_one<G, 1, E, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_ROWWISE_ADAGRAD, PLAIN, true>>(a, s);
       return true;
     case RECEMB_UPD_SGD:
-      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_SGD, PLAIN, true>>(a, s);
+      launch_one<G, 1, E, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_SGD, PLAIN, true>>(a, s);
       return true;
     case RECEMB_UPD_DENSE_GRAD:
-      launch_one<G, 1, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_DENSE_GRAD, PLAIN, true>>(a, s);
+      launch_one<G, 1, E, GT, WT, true, SegCfg<B, PD, MINB, RECEMB_UPD_DENSE_GRAD, PLAIN, true>>(a, s);
       return true;
     default:
       return false;
@@ -607,10 +615,15 @@ static void tune_params(int* b, int* pd, int* minb) {
 template <typename GT, typename WT, bool L0>
 static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
   bool launched = false;
-  if (L0 && shape.V == 1 && a.quads == shape.G && (shape.G == 16 || shape.G == 32) &&
-      std::is_same<GT, WT>::value) {
+  // fast path: gradients and table of one dtype, rows of exactly 16 or 32 lane-vectors of 16 bytes
+  const int vecs16 = (int)(a.dim * sizeof(WT) / 16);
+  if constexpr (L0 && std::is_same<GT, WT>::value)
+  if ((a.dim * sizeof(WT)) % 16 == 0 && (vecs16 == 16 || vecs16 == 32)) {
     const bool plain = a.spg == 1 && !a.slot_weight && !a.grad_row_scale;
-    if (shape.G == 16) {
+    SegArgs f = a;
+    f.vecs = vecs16;
+    const SegArgs& a = f;
+    if (vecs16 == 16) {
       int tb, tp, tm;
       tune_params(&tb, &tp, &tm);
       if (plain && tb == 2 && tp == 1 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 1, 4>(a, s);
@@ -626,6 +639,10 @@ static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
       // one group per warp: half the rows in flight per warp -> prefetch further ahead
       if (plain) launched = launch_fast<32, GT, WT, true, 2, 4, 4>(a, s);
       else launched = launch_fast<32, GT, WT, false, 2, 4, 4>(a, s);
+    }
+    if (launched) {
+      RECEMB_LAUNCHED();
+      return RECEMB_OK;
     }
   }
   if (!launched) {
@@ -873,7 +890,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
 
   SegArgs a;
   a.dim = (uint32_t)dim;
-  a.quads = dim / 4;
+  a.vecs = dim / 4;  // generic kernels: E = 4 (the fast path overrides it)
   a.spg = (uint32_t)slots_per_grad_row;
   a.spg_magic = (uint32_t)((1ull << 32) / (uint64_t)slots_per_grad_row);
   a.slot_weight = slot_weight;

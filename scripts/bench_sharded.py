@@ -68,23 +68,13 @@ def check(world, rank, dev):
         print(f"[check] sharded == unsharded on {world} rank(s): ok", flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
-    ap.add_argument("--check", action="store_true")
-    args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if args.check:
-        check(world, rank, dev)
-
+def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000):
+    """Times the cfg 5 step on an already initialised process group; returns the result dict
+    (every rank computes it, rank 0 prints it)."""
+    class A:
+        pass
+    args = A()
+    args.steps, args.warmup, args.rows_per_gpu = steps, warmup, rows_per_gpu
     n_rows = args.rows_per_gpu * world
     mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev,
                                      fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
@@ -120,9 +110,10 @@ def main():
     lookups = world * T * B_LOCAL * P
     row_bytes = DIM * 2
     nv_in = (world - 1) * T * B_LOCAL * (P * 8 + 2 * row_bytes)   # ids + partials (fwd) + grads (bwd), per GPU
-    if rank == 0:
-        t_step = ms / args.steps * 1e-3
-        print(json.dumps({
+    t_step = ms / args.steps * 1e-3
+    del mod, grad, ids
+    torch.cuda.empty_cache()
+    return {
             "metric": "embedding_lookups_per_sec_fwd_bwd", "value": lookups / t_step, "unit": "lookups/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
@@ -131,7 +122,28 @@ def main():
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
-            "gpu_launches": N.launch_count() - launches0}), flush=True)
+            "gpu_launches": N.launch_count() - launches0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.check:
+        check(world, rank, dev)
+    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
