@@ -203,7 +203,8 @@ RECEMB_API int recemb_plan_views(const void* plan, size_t plan_bytes, const uint
                       int64_t* n_slots_host);
 
 /* ---- backward: segmented reduction + update (a8, a9, K5-K7) ---------------- */
-/* For every distinct row r in the plan: g = sum over its slots s (ascending) of
+/* n_slots = number of (row, slot) entries in the plan.
+ * For every distinct row r in the plan: g = sum over its slots s (ascending) of
  *     slot_weight[s] * grad_row_scale[s / slots_per_grad_row] * grad[s / slots_per_grad_row, :]
  * (both scale arrays optional, fp32) accumulated in fp32, then `update` is
  * applied to row r of `table` (and state1/state2).  Deterministic: fixed
@@ -217,7 +218,7 @@ RECEMB_API int recemb_plan_views(const void* plan, size_t plan_bytes, const uint
  * (embedding_module_gen.py:113-114, :152-153). */
 RECEMB_API size_t recemb_bwd_apply_workspace_bytes(int64_t n_slots, int32_t dim);
 
-RECEMB_API int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void* grad, int grad_dtype,
+RECEMB_API int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad, int grad_dtype,
                      int64_t grad_rows, int32_t dim, int32_t slots_per_grad_row,
                      const float* slot_weight, const float* grad_row_scale, int update,
                      void* table, int dtype, int64_t num_rows, void* state1, void* state2,
@@ -241,6 +242,32 @@ RECEMB_API int recemb_epilogue_bwd(const void* grad_out, const void* out, int dt
  * [world, rows, dim] of per-owner partial pools produced by recemb_pool_fwd(shard_world>1). */
 RECEMB_API int recemb_sum_partials(const void* parts, int32_t world, int64_t rows, int32_t dim, int dtype,
                         const float* row_scale, void* out, int device, recemb_stream_t stream);
+
+/* ---- row-wise sharding: routed exchange (a12) -------------------------------- */
+/* Sender side.  Buckets this rank's lookup slots by owning rank (stable counting sort with
+ * shard_world bins): entries_out[n_ids] receives, bucket after bucket, one int64 per kept slot
+ *     (local row in the owner's stacked shard) << 32 | (shard_rank * bags_total + bag)
+ * and counts_out[shard_world] the bucket sizes (device int64).  Slots outside their bag window
+ * (lengths / last_n) or equal to pad_id (zero_pad) are dropped here and never travel.  Inside
+ * a bucket the entries keep slot order (sorted by bag).  layout: shard_world / shard_rank as in
+ * recemb_layout (shard_rank = THIS rank), ids_per_table / num_tables for stacked tables. */
+RECEMB_API size_t recemb_shard_bucket_workspace_bytes(int64_t n_slots, int32_t world);
+RECEMB_API int recemb_shard_bucket(const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
+                        int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id, int32_t bag_size,
+                        const int32_t* lengths, int32_t last_n, int64_t bags_total, int64_t* entries_out,
+                        int64_t* counts_out, void* workspace, size_t workspace_bytes, int device,
+                        recemb_stream_t stream);
+/* Owner side.  entries = the buckets received from all ranks, concatenated in rank order.  Every
+ * run of equal low word (sender, bag) is pooled (fp32 accumulation in entry order) from `table`
+ * (this rank's stacked shard) into out[low word, :]; rows of bags with no entry are not written
+ * (the caller zero-fills out [shard_world * bags_total, dim]). */
+RECEMB_API int recemb_pool_entries(const void* table, int32_t dim, int dtype, const int64_t* entries, int64_t n,
+                        void* out, int device, recemb_stream_t stream);
+/* Owner side.  Builds a backward plan straight from the received entries: key = local row,
+ * slot = low word = row of the all-gathered gradient [shard_world * bags_total, dim]
+ * (use recemb_bwd_apply with slots_per_grad_row = 1).  plan as in recemb_bwd_plan_bytes(n, total_rows). */
+RECEMB_API int recemb_bwd_plan_entries(const int64_t* entries, int64_t n, int64_t total_rows, void* plan,
+                            size_t plan_bytes, int device, recemb_stream_t stream);
 
 /* ---- ranker pairwise dot interaction (a11) --------------------------------- */
 /* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:

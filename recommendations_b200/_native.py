@@ -90,10 +90,15 @@ SIGNATURES = {
     "recemb_plan_views": (_INT, [_P, _SZ, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                                  C.POINTER(_I64)]),
     "recemb_bwd_apply_workspace_bytes": (_SZ, [_I64, _I32]),
-    "recemb_bwd_apply": (_INT, [_P, _SZ, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
+    "recemb_bwd_apply": (_INT, [_P, _SZ, _I64, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
                                 _P, _P, C.POINTER(OptimParams), _P, _SZ, _INT, _P]),
     "recemb_time_next_apply": (_INT, [_P, _P]),
     "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
+    "recemb_shard_bucket_workspace_bytes": (_SZ, [_I64, _I32]),
+    "recemb_shard_bucket": (_INT, [_P, _I64, C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32,
+                                   _I64, _P, _P, _P, _SZ, _INT, _P]),
+    "recemb_pool_entries": (_INT, [_P, _I32, _INT, _P, _I64, _P, _INT, _P]),
+    "recemb_bwd_plan_entries": (_INT, [_P, _I64, _I64, _P, _SZ, _INT, _P]),
     "recemb_sum_partials": (_INT, [_P, _I32, _I64, _I32, _INT, _P, _P, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),

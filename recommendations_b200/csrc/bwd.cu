@@ -837,7 +837,7 @@ extern "C" size_t recemb_bwd_apply_workspace_bytes(int64_t n_slots, int32_t dim)
   return total;
 }
 
-extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void* grad,
+extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad,
                                 int grad_dtype, int64_t grad_rows, int32_t dim,
                                 int32_t slots_per_grad_row, const float* slot_weight,
                                 const float* grad_row_scale, int update, void* table, int dtype,
@@ -862,7 +862,9 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, const void*
     set_error("adam needs state1 and state2");
     return RECEMB_ERR_INVALID;
   }
-  const int64_t n = grad_rows * slots_per_grad_row;
+  RECEMB_CHECK_ARG(n_slots >= 0, "n_slots < 0");
+  const int64_t n = n_slots;  // entries of the plan (== grad_rows * slots_per_grad_row for plans
+                              // built from ids; free for plans built from routed entries)
   RECEMB_UNSUPPORTED(n < 0x7fffffffll, "too many slots");
   if (n == 0) return RECEMB_OK;
   RECEMB_CHECK_ARG(grad != nullptr && workspace != nullptr, "null grad/workspace");

@@ -138,7 +138,7 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
                        0, -1, 0, nullptr, 0, plan, plan_bytes, device, stream);
   if (rc) return rc;
   const int64_t total_rows = recemb_layout_total_rows(num_rows, &layout, n);
-  rc = recemb_bwd_apply(plan, plan_bytes, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
+  rc = recemb_bwd_apply(plan, plan_bytes, n, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
                         dtype, total_rows, state1, state2, hp_host, workspace, workspace_bytes, device,
                         stream);
   if (rc) return rc;

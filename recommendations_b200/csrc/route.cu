@@ -1,0 +1,389 @@
+// Routed exchange for row-wise sharded pooled lookups (north_star item 4, cfg 5).
+//
+// Every rank buckets ITS lookup slots by owner (stable counting sort, W bins), the buckets go to
+// their owners with one variable-split all-to-all, and an owner then only ever touches the
+// lookups it owns: its pooling, its sort and its segmented reduction are proportional to the
+// slots it serves (~ n per rank whatever W is), not to W x n as with an id all-gather.
+//
+//   recemb_shard_bucket      sender:  ids -> entries (local row, global bag) grouped by owner + counts
+//   recemb_pool_entries      owner:   runs of equal bag in the received entries -> partial pools
+//   recemb_bwd_plan_entries  owner:   received entries -> sorted (row, gradient row) plan
+//
+// An entry is one int64: (local row in the owner's stacked shard) << 32 | (sender_rank * bags + bag).
+// Inside a bucket the entries keep slot order, i.e. they are sorted by bag: the owner sees each
+// (sender, bag) as one contiguous run and pools it in slot order (same fp32 order as the
+// unsharded kernel).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace recemb {
+
+constexpr int kRtThreads = 256;
+constexpr int kRtItems = 16;                        // slots per thread
+constexpr int kRtBlock = kRtThreads * kRtItems;     // slots per CTA
+constexpr int kMaxWorld = 32;
+
+struct BucketArgs {
+  const int64_t* ids;
+  int64_t n;
+  HashSpec h;           // mod_world / shard_world set; ids_per_table / num_tables for the table index
+  int64_t num_rows;     // global rows of one table
+  int zero_pad;
+  int64_t pad_id;
+  int32_t bag_size;
+  const int32_t* lengths;
+  int32_t last_n;
+  uint32_t bag_base;    // sender_rank * bags_total
+  uint8_t* owner8;      // [n]  owner of the slot, 0xff = dropped
+  uint32_t* rowbuf;     // [n]  local row (incl. table offset) at the owner
+  uint32_t* block_hist; // [num_ctas, world]
+  int64_t* entries;     // [n]
+  int64_t* counts;      // [world]
+  uint32_t* block_base; // [num_ctas, world]  exclusive offsets, filled by the scan
+};
+
+__global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketArgs a) {
+  __shared__ uint32_t s_hist[kMaxWorld];
+  if (threadIdx.x < kMaxWorld) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t world = a.h.shard_world;
+  const int64_t base = (int64_t)blockIdx.x * kRtBlock;
+  for (int r = 0; r < kRtItems; ++r) {
+    const int64_t s = base + r * kRtThreads + threadIdx.x;
+    if (s >= a.n) break;
+    const int64_t id = a.ids[s];
+    bool ok = !(a.zero_pad && id == a.pad_id);
+    const int64_t bag = s / a.bag_size;
+    if (ok) {
+      const int p = (int)(s - bag * a.bag_size);
+      int hi = a.bag_size;
+      if (a.lengths) hi = min(max(a.lengths[bag], 0), a.bag_size);
+      const int lo = a.last_n > 0 ? max(0, hi - a.last_n) : 0;
+      ok = p >= lo && p < hi;
+    }
+    uint8_t owner = 0xff;
+    uint32_t lrow = 0;
+    if (ok) {
+      const uint64_t row = (uint64_t)row_of(id, a.h);
+      uint64_t q;
+      const uint32_t o = (uint32_t)udivmod(row, a.h.mod_world, &q);
+      // stacked shard of owner o: table t starts at t * local_rows(o)
+      const uint64_t local_rows = ((uint64_t)a.num_rows - o + world - 1) / world;
+      uint32_t t = 0;
+      if (a.h.ids_per_table) {
+        t = (uint32_t)s / a.h.ids_per_table;
+        if (a.h.num_tables) t %= a.h.num_tables;
+      }
+      owner = (uint8_t)o;
+      lrow = (uint32_t)(q + (uint64_t)t * local_rows);
+      atomicAdd(&s_hist[o], 1u);
+    }
+    a.owner8[s] = owner;
+    a.rowbuf[s] = lrow;
+  }
+  __syncthreads();
+  if (threadIdx.x < world) a.block_hist[(int64_t)blockIdx.x * world + threadIdx.x] = s_hist[threadIdx.x];
+}
+
+// one warp per owner: exclusive scan of that owner's per-CTA counts; then owner bases
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, int num_ctas) {
+  __shared__ uint32_t s_total[kMaxWorld];
+  const int world = (int)a.h.shard_world;
+  const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (o < world) {
+    uint32_t carry = 0;
+    for (int c0 = 0; c0 < num_ctas; c0 += 32) {
+      const int c = c0 + lane;
+      const uint32_t v = c < num_ctas ? a.block_hist[(int64_t)c * world + o] : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (c < num_ctas) a.block_base[(int64_t)c * world + o] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_total[o] = carry;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < world; ++i) {
+      a.counts[i] = (int64_t)s_total[i];
+      const uint32_t t = s_total[i];
+      s_total[i] = run;  // base offset of owner i's bucket
+      run += t;
+    }
+  }
+  __syncthreads();
+  // fold the owner bases into the per-CTA offsets
+  for (int i = threadIdx.x; i < num_ctas * world; i += blockDim.x) a.block_base[i] += s_total[i % world];
+}
+
+// stable scatter: position = base[cta][owner] + (valid slots of that owner earlier in the CTA)
+__global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const BucketArgs a) {
+  __shared__ uint32_t s_run[kMaxWorld];                       // running offset per owner
+  __shared__ uint32_t s_wc[kRtThreads / 32][kMaxWorld];       // per-warp counts of this round
+  const uint32_t world = a.h.shard_world;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < world) s_run[threadIdx.x] = a.block_base[(int64_t)blockIdx.x * world + threadIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * kRtBlock;
+  for (int r = 0; r < kRtItems; ++r) {
+    for (int i = threadIdx.x; i < (kRtThreads / 32) * kMaxWorld; i += kRtThreads) (&s_wc[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t s = base + r * kRtThreads + threadIdx.x;
+    const uint32_t owner = s < a.n ? a.owner8[s] : 0xffu;
+    const bool valid = owner != 0xffu;
+    // rank among the lanes of this warp with the same owner
+    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wc[warp][owner] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      uint32_t pos = s_run[owner] + rank;
+      for (int w = 0; w < warp; ++w) pos += s_wc[w][owner];
+      const uint32_t bag = (uint32_t)(s / a.bag_size);
+      a.entries[pos] = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)(a.bag_base + bag));
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+      uint32_t add = 0;
+      for (int w = 0; w < kRtThreads / 32; ++w) add += s_wc[w][threadIdx.x];
+      s_run[threadIdx.x] += add;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------ owner-side pooling ----
+// Group of G lanes per chunk of kPeChunk entries; a run (equal bag key) belongs to the chunk in
+// which it starts: the group skips a leading run that started earlier and walks past its chunk
+// end to finish its last run.  fp32 accumulation in entry (= slot) order; each output row is
+// written exactly once (rows of bags without owned slots stay at the caller's zero fill).
+constexpr int kPeChunk = 32;
+
+struct PoolEntriesArgs {
+  const int64_t* entries;
+  int32_t n;
+  const void* table;
+  uint32_t dim;
+  int32_t vecs;  // 16-byte vectors per row
+  void* out;
+};
+
+template <int G, typename T>
+__global__ void __launch_bounds__(kRtThreads, 4) pool_entries_kernel(const PoolEntriesArgs a) {
+  constexpr int E = Vec16<T>::kElems;
+  constexpr int B = 4;
+  const int lane = threadIdx.x & 31, lig = lane % G;
+  const int chunk = blockIdx.x * (kRtThreads / G) + threadIdx.x / G;
+  const int start = chunk * kPeChunk;
+  if (start >= a.n) return;
+  const int end = min(start + kPeChunk, a.n);
+  const uint4* table = reinterpret_cast<const uint4*>(a.table);
+  uint4* out = reinterpret_cast<uint4*>(a.out);
+  auto key_of = [&](int i) { return (uint32_t)((uint64_t)a.entries[i] & 0xffffffffull); };
+
+  int i = start;
+  if (start > 0) {  // skip the tail of a run that started in an earlier chunk
+    const uint32_t prev = key_of(start - 1);
+    while (i < a.n && i < end && key_of(i) == prev) ++i;
+    if (i == end && i < a.n && key_of(i) == prev) return;  // whole chunk inside an older run
+  }
+  float acc[E];
+  while (i < end) {  // runs starting in [start, end)
+    const uint32_t key = key_of(i);
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    bool more = true;
+    while (more) {
+      uint4 v[B];
+      bool use[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int j = i + u;
+        use[u] = false;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (j < a.n) {
+          const uint64_t ent = (uint64_t)a.entries[j];
+          if ((uint32_t)(ent & 0xffffffffull) == key) {
+            use[u] = true;
+            if (lig < a.vecs) v[u] = ldg_nc_v4(table + (size_t)(ent >> 32) * a.vecs + lig);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        if (use[u] && more) {
+          float f[E];
+          Vec16<T>::unpack(v[u], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] += f[e];
+          ++i;
+        } else {
+          more = false;
+        }
+      }
+    }
+    if (lig < a.vecs) stg_cs_v4(out + (size_t)key * a.vecs + lig, Vec16<T>::pack(acc));
+  }
+}
+
+// ------------------------------------------------------------------ plan from entries ----
+__global__ void __launch_bounds__(kRtThreads) unpack_entries_kernel(const int64_t* __restrict__ entries, int64_t n,
+                                                                   uint32_t* __restrict__ keys,
+                                                                   uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * kRtThreads;
+  for (; i < n; i += stride) {
+    const uint64_t e = (uint64_t)entries[i];
+    keys[i] = (uint32_t)(e >> 32);
+    vals[i] = (uint32_t)(e & 0xffffffffull);
+  }
+}
+
+}  // namespace recemb
+
+using namespace recemb;
+
+extern "C" size_t recemb_shard_bucket_workspace_bytes(int64_t n_slots, int32_t world) {
+  if (n_slots < 0 || world < 1) return 0;
+  const int64_t ctas = (n_slots + kRtBlock - 1) / kRtBlock;
+  return align_up((size_t)n_slots, 256) + align_up((size_t)n_slots * 4, 256) +
+         2 * align_up((size_t)(ctas > 0 ? ctas : 1) * world * 4, 256) + 256;
+}
+
+extern "C" int recemb_shard_bucket(const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
+                                   int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
+                                   int32_t bag_size, const int32_t* lengths, int32_t last_n, int64_t bags_total,
+                                   int64_t* entries_out, int64_t* counts_out, void* workspace,
+                                   size_t workspace_bytes, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(layout && layout->shard_world >= 1 && layout->shard_world <= kMaxWorld,
+                   "shard_world outside [1, %d]", kMaxWorld);
+  RECEMB_CHECK_ARG(bag_size >= 1 && n_ids >= 0 && n_ids % bag_size == 0, "n_ids not a multiple of bag_size");
+  RECEMB_CHECK_ARG(counts_out && workspace, "null pointer");
+  RECEMB_UNSUPPORTED(n_ids < 0x7fffffffll, "too many slots");
+  RECEMB_UNSUPPORTED((int64_t)layout->shard_world * bags_total < 0xffffffffll, "bag keys overflow 32 bits");
+  RECEMB_UNSUPPORTED(recemb_layout_total_rows(num_rows, layout, n_ids) < 0xfffffff0ll, "local rows overflow 32 bits");
+  const size_t need = recemb_shard_bucket_workspace_bytes(n_ids, layout->shard_world);
+  if (workspace_bytes < need) {
+    set_error("workspace %zu < required %zu", workspace_bytes, need);
+    return RECEMB_ERR_WORKSPACE;
+  }
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  BucketArgs a;
+  int rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h, layout);
+  if (rc) return rc;
+  a.h.shard_world = (uint32_t)layout->shard_world;  // also for world == 1 (one bucket)
+  a.h.mod_world = make_modn((uint64_t)layout->shard_world);
+  a.ids = ids;
+  a.n = n_ids;
+  a.num_rows = num_rows;
+  a.zero_pad = zero_pad;
+  a.pad_id = pad_id;
+  a.bag_size = bag_size;
+  a.lengths = lengths;
+  a.last_n = last_n;
+  a.bag_base = (uint32_t)(layout->shard_rank * bags_total);
+  const int64_t ctas = (n_ids + kRtBlock - 1) / kRtBlock;
+  char* w = (char*)workspace;
+  a.owner8 = (uint8_t*)w;
+  w += align_up((size_t)n_ids, 256);
+  a.rowbuf = (uint32_t*)w;
+  w += align_up((size_t)n_ids * 4, 256);
+  a.block_hist = (uint32_t*)w;
+  w += align_up((size_t)(ctas > 0 ? ctas : 1) * layout->shard_world * 4, 256);
+  a.block_base = (uint32_t*)w;
+  a.entries = entries_out;
+  a.counts = counts_out;
+  if (n_ids == 0) {
+    RECEMB_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int64_t) * layout->shard_world, s));
+    return RECEMB_OK;
+  }
+  RECEMB_CHECK_ARG(ids && entries_out, "null ids / entries");
+  bucket_count_kernel<<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
+  RECEMB_LAUNCHED();
+  bucket_scan_kernel<<<1, 32 * layout->shard_world, 0, s>>>(a, (int)ctas);
+  RECEMB_LAUNCHED();
+  bucket_scatter_kernel<<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+extern "C" int recemb_pool_entries(const void* table, int32_t dim, int dtype, const int64_t* entries, int64_t n,
+                                   void* out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0 && dim > 0, "bad shape");
+  RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "bad dtype");
+  RECEMB_UNSUPPORTED(n < 0x7fffffffll, "too many entries");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(table && entries && out, "null pointer");
+  const int64_t row_bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED(row_bytes % 16 == 0 && row_bytes <= 512, "row of %lld bytes unsupported (16-byte multiple, <= 512)",
+                     (long long)row_bytes);
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  PoolEntriesArgs a;
+  a.entries = entries;
+  a.n = (int32_t)n;
+  a.table = table;
+  a.dim = (uint32_t)dim;
+  a.vecs = (int32_t)(row_bytes / 16);
+  a.out = out;
+  int G = 1;
+  while (G < a.vecs) G <<= 1;
+  const int chunks = (a.n + kPeChunk - 1) / kPeChunk;
+  cudaStream_t s = (cudaStream_t)stream;
+#define PE(G_)                                                                                        \
+  if (G == G_) {                                                                                      \
+    const int groups = kRtThreads / G_;                                                               \
+    const unsigned grid = (unsigned)((chunks + groups - 1) / groups);                                 \
+    if (dtype == RECEMB_F32) pool_entries_kernel<G_, float><<<grid, kRtThreads, 0, s>>>(a);            \
+    else pool_entries_kernel<G_, __nv_bfloat16><<<grid, kRtThreads, 0, s>>>(a);                        \
+  }
+  PE(1) PE(2) PE(4) PE(8) PE(16) PE(32)
+#undef PE
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}
+
+// plan layout (see bwd.cu): [256 B counters][keys_in][vals_in][keys_out][vals_out][sort temp]
+extern "C" int recemb_bwd_plan_entries(const int64_t* entries, int64_t n, int64_t total_rows, void* plan,
+                                       size_t plan_bytes, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0 && total_rows >= 1, "bad n / total_rows");
+  RECEMB_CHECK_ARG(plan && (uintptr_t)plan % 256 == 0, "plan buffer missing / misaligned");
+  RECEMB_UNSUPPORTED(n < 0x7fffffffll && total_rows < 0xfffffff0ll, "sizes overflow 32-bit keys");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(entries, "null entries");
+  const size_t need = recemb_bwd_plan_bytes(n, total_rows);
+  if (need == 0) return RECEMB_ERR_CUDA;
+  if (plan_bytes < need) {
+    set_error("plan buffer %zu < required %zu", plan_bytes, need);
+    return RECEMB_ERR_WORKSPACE;
+  }
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t arr = align_up((size_t)n * 4, 256);
+  char* base = (char*)plan;
+  uint32_t* keys_in = (uint32_t*)(base + 256);
+  uint32_t* vals_in = (uint32_t*)(base + 256 + arr);
+  uint32_t* keys_out = (uint32_t*)(base + 256 + 2 * arr);
+  uint32_t* vals_out = (uint32_t*)(base + 256 + 3 * arr);
+  void* temp = base + 256 + 4 * arr;
+  size_t temp_bytes = plan_bytes - (256 + 4 * arr);
+  int64_t grid = (n + kRtThreads - 1) / kRtThreads;
+  const int64_t cap = (int64_t)sm_count(device) * 16;
+  if (grid > cap) grid = cap;
+  unpack_entries_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>(entries, n, keys_in, vals_in);
+  RECEMB_LAUNCHED();
+  int bits = 0;
+  for (uint64_t x = (uint64_t)total_rows; x; x >>= 1) ++bits;
+  RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
+                                              (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return RECEMB_OK;
+}

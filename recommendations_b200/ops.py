@@ -119,6 +119,7 @@ class BackwardPlan:
     n_slots: int
     num_rows: int
     slots_per_id: int
+    slots_cover_grad: bool = True  # False: slots are explicit gradient-row indices (routed entries)
 
     @staticmethod
     def build(ids: torch.Tensor, *, num_rows: int, hash_mode: int = N.HASH_FLOORMOD,
@@ -186,7 +187,7 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
     """Segmented reduction of `grad` rows over the plan + `update` on `table` (in place)."""
     dim = table.shape[1]
     grad2d = grad.contiguous().view(-1, dim)
-    if grad2d.shape[0] * slots_per_grad_row != plan.n_slots:
+    if plan.slots_cover_grad and grad2d.shape[0] * slots_per_grad_row != plan.n_slots:
         raise N.NativeError(
             f"grad has {grad2d.shape[0]} rows x {slots_per_grad_row} slots, plan has {plan.n_slots}")
     dev = N.require_cuda(plan.buf, grad2d, table, state1, state2, slot_weight, grad_row_scale)
@@ -196,7 +197,7 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
         workspace = torch.empty((need,), dtype=torch.uint8, device=table.device)
     hp = hp or make_optim_params()
     N.check(lib.recemb_bwd_apply(
-        N.ptr(plan.buf), plan.buf.numel(), N.ptr(grad2d), N.dtype_code(grad2d.dtype),
+        N.ptr(plan.buf), plan.buf.numel(), plan.n_slots, N.ptr(grad2d), N.dtype_code(grad2d.dtype),
         grad2d.shape[0], dim, slots_per_grad_row, N.ptr(slot_weight), N.ptr(grad_row_scale), update,
         N.ptr(table), N.dtype_code(table.dtype), table.shape[0], N.ptr(state1), N.ptr(state2),
         C.byref(hp), N.ptr(workspace), workspace.numel(), dev, N.stream_ptr(dev)),
@@ -215,6 +216,56 @@ def epilogue_bwd(grad_out: torch.Tensor, out: Optional[torch.Tensor],
                                          g.shape[0], dim, epilogue, num_shifts, N.ptr(dx), dev,
                                          N.stream_ptr(dev)), "recemb_epilogue_bwd")
     return dx
+
+
+def shard_bucket(ids: torch.Tensor, *, num_rows: int, world: int, rank: int, bags_total: int,
+                 lengths: Optional[torch.Tensor] = None, last_n: int = 0, zero_pad: bool = False,
+                 pad_id: int = 0, bags_per_table: int = 0, num_tables: int = 0,
+                 hash_mode: int = N.HASH_FLOORMOD) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sender side of the routed exchange: ids [bags, P] -> (entries int64 [bags * P] grouped by
+    owner, counts int64 [world]); only the first counts.sum() entries are meaningful."""
+    ids = ids.contiguous()
+    if lengths is not None:
+        lengths = lengths.to(torch.int32).contiguous()
+    dev = N.require_cuda(ids, lengths)
+    m, p = ids.shape
+    lib = N.load()
+    layout = N.Layout(ids_per_table=bags_per_table * p, num_tables=num_tables, shard_world=world,
+                      shard_rank=rank, reserved=0)
+    entries = torch.empty((m * p,), dtype=torch.int64, device=ids.device)
+    counts = torch.empty((world,), dtype=torch.int64, device=ids.device)
+    ws = torch.empty((int(lib.recemb_shard_bucket_workspace_bytes(m * p, world)),), dtype=torch.uint8,
+                     device=ids.device)
+    N.check(lib.recemb_shard_bucket(N.ptr(ids), m * p, layout, hash_mode, num_rows, 0, int(zero_pad), pad_id,
+                                    p, N.ptr(lengths), last_n, bags_total, N.ptr(entries), N.ptr(counts),
+                                    N.ptr(ws), ws.numel(), dev, N.stream_ptr(dev)), "recemb_shard_bucket")
+    return entries, counts
+
+
+def pool_entries(table: torch.Tensor, entries: torch.Tensor, out_rows: int) -> torch.Tensor:
+    """Owner side: received entries -> partial pools [out_rows, dim] (zero where no entry)."""
+    entries = entries.contiguous()
+    dev = N.require_cuda(table, entries)
+    out = torch.zeros((out_rows, table.shape[1]), dtype=table.dtype, device=table.device)
+    N.check(N.load().recemb_pool_entries(N.ptr(table), table.shape[1], N.dtype_code(table.dtype),
+                                         N.ptr(entries), entries.numel(), N.ptr(out), dev,
+                                         N.stream_ptr(dev)), "recemb_pool_entries")
+    return out
+
+
+def plan_from_entries(entries: torch.Tensor, total_rows: int) -> "BackwardPlan":
+    """Owner side: received entries -> plan (key = local row, slot = gathered-gradient row)."""
+    entries = entries.contiguous()
+    dev = N.require_cuda(entries)
+    lib = N.load()
+    n = entries.numel()
+    need = int(lib.recemb_bwd_plan_bytes(n, total_rows))
+    if need == 0:
+        N.check(-2, "recemb_bwd_plan_bytes")
+    buf = torch.empty((need,), dtype=torch.uint8, device=entries.device)
+    N.check(lib.recemb_bwd_plan_entries(N.ptr(entries), n, total_rows, N.ptr(buf), buf.numel(), dev,
+                                        N.stream_ptr(dev)), "recemb_bwd_plan_entries")
+    return BackwardPlan(buf=buf, n_slots=n, num_rows=total_rows, slots_per_id=1, slots_cover_grad=False)
 
 
 def sum_partials(parts: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -6,7 +6,18 @@ GPU; torch.distributed (NCCL over NVLink / NVSwitch) is the plumbing.  The refer
 model-parallel embeddings (tables replicated): sharded == unsharded is the parity
 statement, checked on one GPU (W emulated), on CPU/gloo (host logic) and on N GPUs.
 
-Data path, fixed-size collectives only (no counts exchange, no host sync):
+Two exchange strategies (`exchange=`):
+
+"route" (default for W > 1): every rank buckets its slots by owner (stable counting sort), one
+  counts all-to-all + ONE host read of the bucket sizes, then a variable-split all-to-all moves
+  each lookup only to the rank that owns its row.  An owner pools / sorts / updates just the
+  ~n lookups it serves, independent of W.
+      forward   ids --bucket--> entries(owner-major) --all_to_all_v--> owner: run-pool by (sender, bag)
+                partial [W, B, D] --all_to_all--> requester: sum over owners in order 0..W-1
+      backward  grad_out --all_gather--> owner: plan from its received entries + segmented
+                reduction + fused update of ITS rows (no gradient all-reduce)
+
+"gather" (fixed-size collectives only, no host sync; owner-side work grows with W):
 
   forward   ids [b, P]  --all_gather-->  [W, b, P]
             owner: partial pool of EVERY rank's bags over the rows it owns
@@ -55,6 +66,38 @@ class Collectives:
         dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view((self.world,) + tuple(t.shape))
 
+    def exchange_counts(self, counts: torch.Tensor):
+        """counts [W] (device): how many entries I send to each rank -> (send, recv) host lists.
+        The one host synchronisation of the routed exchange."""
+        if self.native_a2a:
+            recv = torch.empty_like(counts)
+            dist.all_to_all_single(recv, counts, group=self.group)
+            both = torch.stack([counts, recv]).cpu()
+            return both[0].tolist(), both[1].tolist()
+        matrix = self.all_gather(counts).cpu()            # [src, dst]
+        return matrix[self.rank].tolist(), matrix[:, self.rank].tolist()
+
+    def all_to_all_v(self, send: torch.Tensor, send_counts, recv_counts) -> torch.Tensor:
+        """send = buckets for rank 0, 1, ... back to back; returns the buckets received from rank
+        0, 1, ... back to back."""
+        n_send, n_recv = int(sum(send_counts)), int(sum(recv_counts))
+        out = torch.empty((n_recv,) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        if self.native_a2a:
+            dist.all_to_all_single(out, send[:n_send].contiguous(), output_split_sizes=list(recv_counts),
+                                   input_split_sizes=list(send_counts), group=self.group)
+            return out
+        # emulation for backends without all_to_all (gloo): all_gather padded sends, slice mine
+        matrix = self.all_gather(torch.tensor(send_counts, dtype=torch.int64, device=send.device)).cpu()
+        cap = int(matrix.sum(dim=1).max())
+        padded = torch.zeros((cap,) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        padded[:n_send] = send[:n_send]
+        everyone = self.all_gather(padded)
+        pieces = []
+        for src in range(self.world):
+            off = int(matrix[src, :self.rank].sum())
+            pieces.append(everyone[src, off:off + int(matrix[src, self.rank])])
+        return torch.cat(pieces) if pieces else out
+
     def all_to_all(self, t: torch.Tensor) -> torch.Tensor:
         """t [W, ...]: slice s goes to rank s; returns [W, ...] with slice s received from rank s."""
         t = t.contiguous()
@@ -77,6 +120,13 @@ class SingleProcess(Collectives):
 
     def all_to_all(self, t):
         return t
+
+    def exchange_counts(self, counts):
+        c = counts.cpu().tolist()
+        return c, c
+
+    def all_to_all_v(self, send, send_counts, recv_counts):
+        return send[:int(sum(send_counts))]
 
 
 # ---------------------------------------------------------------- autograd ----
@@ -109,6 +159,38 @@ class _ShardedPoolFn(torch.autograd.Function):
         return module.local_backward(ids_all, len_all, g_all), None, None, None
 
 
+class _RoutedPoolFn(torch.autograd.Function):
+    """exchange="route": each lookup travels only to the rank that owns its row."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, module):
+        comm: Collectives = module.comm
+        w, b = comm.world, ids.shape[0]
+        entries, counts = module.bucket(ids, lengths)                    # owner-major, device
+        send_c, recv_c = comm.exchange_counts(counts)                    # host sync (bucket sizes)
+        recv = comm.all_to_all_v(entries, send_c, recv_c)                # int64 [n_recv]
+        partial = module.pool_entries(module.emb.weight.detach(), recv, w * b)   # [W*B, D]
+        back = comm.all_to_all(partial.view(w, b, -1))                   # owner s's partial of MY bags
+        scale = None
+        if module.mode == "mean":
+            scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad,
+                                        module.pad_id).clamp_(min=1).float()
+        ctx.module = module
+        ctx.save_for_backward(recv, scale)
+        return module.reduce_partials(back, scale)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        recv, scale = ctx.saved_tensors
+        module = ctx.module
+        g = grad_out.contiguous()
+        if scale is not None:
+            g = g * scale.unsqueeze(1).to(g.dtype)
+        g_all = module.comm.all_gather(g)                                # [W, B, D]
+        g_all = g_all.view(-1, g_all.shape[-1])
+        return module.entries_backward(recv, g_all), None, None, None
+
+
 class RowWiseShardedEmbeddingBag(nn.Module):
     """Pooled multi-hot lookup into a row-wise sharded table.
 
@@ -125,7 +207,9 @@ class RowWiseShardedEmbeddingBag(nn.Module):
                  dtype: torch.dtype = torch.float32, device=None,
                  fused_optimizer: Optional[FusedOptimizerConfig] = None,
                  local_pool: Optional[Callable] = None, local_backward: Optional[Callable] = None,
-                 reduce_partials: Optional[Callable] = None):
+                 reduce_partials: Optional[Callable] = None, exchange: Optional[str] = None,
+                 bucket: Optional[Callable] = None, pool_entries: Optional[Callable] = None,
+                 entries_backward: Optional[Callable] = None):
         super().__init__()
         if mode not in ("sum", "mean"):
             raise ValueError("mode must be 'sum' or 'mean'")
@@ -144,6 +228,12 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         self.local_pool = local_pool or self._cuda_local_pool
         self.local_backward = local_backward or self._cuda_local_backward
         self.reduce_partials = reduce_partials or ops.sum_partials
+        self.exchange = exchange or ("route" if comm.world > 1 else "gather")
+        if self.exchange not in ("route", "gather"):
+            raise ValueError("exchange must be 'route' or 'gather'")
+        self.bucket = bucket or self._cuda_bucket
+        self.pool_entries = pool_entries or ops.pool_entries
+        self.entries_backward = entries_backward or self._cuda_entries_backward
 
     # ----------------------------------------------------------- CUDA hooks ----
     def _cuda_local_pool(self, shard, ids_all, len_all):
@@ -160,6 +250,18 @@ class RowWiseShardedEmbeddingBag(nn.Module):
             num_tables=self._batching(ids_all)["num_tables"])
         return self.emb.consume(plan, g_all, slots_per_grad_row=ids_all.shape[1])
 
+    def _cuda_bucket(self, ids, lengths):
+        b_tot = ids.shape[0]
+        return ops.shard_bucket(ids, num_rows=self.num_embeddings, world=self.comm.world, rank=self.comm.rank,
+                                bags_total=b_tot, lengths=lengths, last_n=self.last_n, zero_pad=self.skip_pad,
+                                pad_id=self.pad_id,
+                                bags_per_table=b_tot // self.num_tables if self.num_tables > 1 else 0,
+                                num_tables=self.num_tables if self.num_tables > 1 else 0)
+
+    def _cuda_entries_backward(self, recv, g_all):
+        plan = ops.plan_from_entries(recv, self.emb.weight.shape[0])
+        return self.emb.consume(plan, g_all, slots_per_grad_row=1)
+
     def _batching(self, ids_all):
         """gathered bags are [W, T, b]: bag g belongs to table (g // b) % T."""
         if self.num_tables == 1:
@@ -171,13 +273,14 @@ class RowWiseShardedEmbeddingBag(nn.Module):
     def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         if ids.dtype != torch.int64 or ids.dim() != (2 if self.num_tables == 1 else 3):
             raise N.NativeError("ids must be int64 [batch, bag_size] ([num_tables, batch, bag_size] when batched)")
+        fn = _RoutedPoolFn if self.exchange == "route" else _ShardedPoolFn
         if self.num_tables == 1:
-            return _ShardedPoolFn.apply(self.emb.grad_anchor(), ids.contiguous(), lengths, self)
+            return fn.apply(self.emb.grad_anchor(), ids.contiguous(), lengths, self)
         t, b, p = ids.shape
         if t != self.num_tables:
             raise N.NativeError(f"expected ids for {self.num_tables} tables, got {t}")
-        out = _ShardedPoolFn.apply(self.emb.grad_anchor(), ids.contiguous().view(t * b, p),
-                                   None if lengths is None else lengths.contiguous().view(t * b), self)
+        out = fn.apply(self.emb.grad_anchor(), ids.contiguous().view(t * b, p),
+                       None if lengths is None else lengths.contiguous().view(t * b), self)
         return out.view(t, b, -1)
 
     @torch.no_grad()

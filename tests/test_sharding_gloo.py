@@ -55,10 +55,35 @@ def _make_hooks(world, rank, last_n):
         out = recv.sum(0)
         return out if scale is None else out * scale.unsqueeze(1)
 
-    return local_pool, local_backward, reduce
+    # routed exchange hooks (oracle restatements of csrc/route.cu)
+    def bucket(ids, lengths):
+        rows = O.row_index(ids, N_ROWS, 0)
+        owner, loc = rows % world, torch.div(rows, world, rounding_mode="floor")
+        use = _window(ids, lengths, last_n)
+        bag = torch.arange(ids.shape[0]).unsqueeze(1).expand_as(ids)
+        ent, cnt = [], []
+        for o in range(world):
+            m = use & (owner == o)  # boolean indexing keeps slot order: stable
+            ent.append((loc[m] << 32) | (rank * ids.shape[0] + bag[m]))
+            cnt.append(int(m.sum()))
+        return torch.cat(ent), torch.tensor(cnt, dtype=torch.int64)
+
+    def pool_entries(shard, recv, out_rows):
+        out = torch.zeros(out_rows, shard.shape[1])
+        out.index_add_(0, recv & 0xFFFFFFFF, shard[recv >> 32])
+        return out
+
+    def entries_backward(recv, g_all):
+        n_local = (N_ROWS - rank + world - 1) // world
+        gw = torch.zeros(n_local, g_all.shape[1])
+        gw.index_add_(0, recv >> 32, g_all[recv & 0xFFFFFFFF])
+        return gw
+
+    return dict(local_pool=local_pool, local_backward=local_backward, reduce_partials=reduce, bucket=bucket,
+                pool_entries=pool_entries, entries_backward=entries_backward)
 
 
-def _worker(rank, world, port, mode, last_n, result):
+def _worker(rank, world, port, mode, last_n, exchange, result):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -69,9 +94,8 @@ def _worker(rank, world, port, mode, last_n, result):
         ids = torch.randint(-2 ** 63, 2 ** 63 - 1, (B, P), generator=g, dtype=torch.int64)
         lengths = torch.randint(0, P + 1, (B,), generator=g)
         go = torch.randn(B, DIM, generator=g)
-        lp, lb, rd = _make_hooks(world, rank, last_n)
-        mod = RowWiseShardedEmbeddingBag(N_ROWS, DIM, mode=mode, last_n=last_n, local_pool=lp,
-                                         local_backward=lb, reduce_partials=rd)
+        mod = RowWiseShardedEmbeddingBag(N_ROWS, DIM, mode=mode, last_n=last_n, exchange=exchange,
+                                         **_make_hooks(world, rank, last_n))
         assert mod.emb.weight.shape[0] == (N_ROWS - rank + world - 1) // world
         mod.load_full_weight(full)
         out = mod(ids, lengths)
@@ -100,11 +124,12 @@ def _worker(rank, world, port, mode, last_n, result):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,last_n", [("sum", 0), ("mean", 0), ("sum", 2)])
-def test_sharded_equals_unsharded_gloo_world2(mode, last_n):
+@pytest.mark.parametrize("mode,last_n,exchange", [("sum", 0, "route"), ("mean", 0, "route"), ("sum", 2, "route"),
+                                                  ("sum", 0, "gather"), ("mean", 2, "gather")])
+def test_sharded_equals_unsharded_gloo_world2(mode, last_n, exchange):
     world = 2
     result = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), mode, last_n, result), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, last_n, exchange, result), nprocs=world, join=True)
     assert dict(result) == {0: 1, 1: 1}
 
 
