@@ -633,6 +633,9 @@ static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
       else if (plain && tb == 1 && tp == 4 && tm == 5) launched = launch_fast<16, GT, WT, true, 1, 4, 5>(a, s);
       else if (plain && tb == 2 && tp == 4 && tm == 5) launched = launch_fast<16, GT, WT, true, 2, 4, 5>(a, s);
       else if (plain && tb == 2 && tp == 2 && tm == 6) launched = launch_fast<16, GT, WT, true, 2, 2, 6>(a, s);
+      else if (plain && tb == 2 && tp == 2 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 2, 4>(a, s);
+      else if (plain && tb == 2 && tp == 4 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 4, 4>(a, s);
+      else if (plain && tb == 2 && tp == 8 && tm == 4) launched = launch_fast<16, GT, WT, true, 2, 8, 4>(a, s);
       else if (plain) launched = launch_fast<16, GT, WT, true, 2, 1, 4>(a, s);
       else launched = launch_fast<16, GT, WT, false, 2, 1, 4>(a, s);
     } else {

@@ -68,7 +68,7 @@ def check(world, rank, dev):
         print(f"[check] sharded == unsharded on {world} rank(s): ok", flush=True)
 
 
-def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000):
+def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=None):
     """Times the cfg 5 step on an already initialised process group; returns the result dict
     (every rank computes it, rank 0 prints it)."""
     class A:
@@ -76,7 +76,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000):
     args = A()
     args.steps, args.warmup, args.rows_per_gpu = steps, warmup, rows_per_gpu
     n_rows = args.rows_per_gpu * world
-    mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev,
+    mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange=exchange,
                                      fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
     ids_host = ids_for(rank, T, B_LOCAL, P).pin_memory()
     ids = ids_host.to(dev)
@@ -111,6 +111,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000):
     row_bytes = DIM * 2
     nv_in = (world - 1) * T * B_LOCAL * (P * 8 + 2 * row_bytes)   # ids + partials (fwd) + grads (bwd), per GPU
     t_step = ms / args.steps * 1e-3
+    mod_exchange = mod.exchange
     del mod, grad, ids
     torch.cuda.empty_cache()
     return {
@@ -119,7 +120,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000):
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 row-wise sharded over {world} GPU(s), "
                                    f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
-                       "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes},
+                       "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
             "gpu_launches": N.launch_count() - launches0}
@@ -131,6 +132,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--exchange", default=None, choices=["route", "gather"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -141,7 +143,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.check:
         check(world, rank, dev)
-    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu)
+    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
