@@ -95,13 +95,18 @@ enum recemb_update {
  *   row-wise sharding: global row r lives on rank r % shard_world at local row r / shard_world;
  *     `table` is this rank's shard, num_rows stays the GLOBAL count used for hashing, lookups
  *     owned by other ranks are skipped (forward) / dropped (plan).  With both, the stacked local
- *     table is [T * local_rows, dim], local_rows = ceil((num_rows - shard_rank) / shard_world). */
+ *     table is [T * local_rows, dim], local_rows = ceil((num_rows - shard_rank) / shard_world).
+ *   flip_len = L > 0 (sequence gather / k-shift): the lookups form sequences of L; output row i is
+ *     written at the mirrored position inside its sequence, (i / L) * L + (L - 1 - i % L), and the
+ *     plan maps every slot to that mirrored gradient row -- Encoder.flip_all
+ *     (models/lthm/sequence/encoder.py:52-54, :60-61: right-padded -> left-padded) folded into the
+ *     gather's addressing instead of a torch.flip copy of [B, L, D]. */
 typedef struct recemb_layout {
   int64_t ids_per_table;
   int32_t num_tables;
   int32_t shard_world;
   int32_t shard_rank;
-  int32_t reserved;
+  int32_t flip_len;
 } recemb_layout;
 
 typedef struct recemb_optim_params {
@@ -149,8 +154,8 @@ RECEMB_API int recemb_gather_fwd(const void* table, int64_t num_rows, const void
  * (commons/layers.py:152-172): 2k-1 launches -> 1.  inv_norm_out (optional,
  * fp32 [n]) receives 1/max(||x||,eps) for the L2NORM backward. */
 RECEMB_API int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
-                      const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue, void* out,
-                      float* inv_norm_out, int device, recemb_stream_t stream);
+                      const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue, int32_t flip_len,
+                      void* out, float* inv_norm_out, int device, recemb_stream_t stream);
 
 /* ---- forward: pooled multi-hot bag (a5, a11) ------------------------------ */
 /* ids [num_bags, bag_size]; out[b, :] = pool_{p in window(b)} w[b,p] * table[transform(ids[b,p]), :]

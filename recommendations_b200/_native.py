@@ -49,16 +49,17 @@ class Layout(C.Structure):
         ("num_tables", C.c_int32),
         ("shard_world", C.c_int32),
         ("shard_rank", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flip_len", C.c_int32),
     ]
 
 
-def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0):
-    """None when nothing is batched / sharded (the C side treats NULL as one plain table)."""
-    if not ids_per_table and shard_world <= 1:
+def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
+                flip_len: int = 0):
+    """None when nothing is batched / sharded / flipped (the C side treats NULL as one plain table)."""
+    if not ids_per_table and shard_world <= 1 and not flip_len:
         return None
     return Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=shard_world,
-                  shard_rank=shard_rank, reserved=0)
+                  shard_rank=shard_rank, flip_len=flip_len)
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -80,7 +81,7 @@ SIGNATURES = {
     "recemb_layout_total_rows": (_I64, [_I64, C.POINTER(Layout), _I64]),
     "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, C.POINTER(Layout), _INT, _INT, _I64,
                                  _INT, _INT, _I64, _P, _P, _INT, _P]),
-    "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _P, _P, _INT, _P]),
+    "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _I32, _P, _P, _INT, _P]),
     "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,
                                _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
     "recemb_bwd_plan_bytes": (_SZ, [_I64, _I64]),

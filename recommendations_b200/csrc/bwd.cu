@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
       }
     }
     a.keys[s] = key;
-    a.vals[s] = (uint32_t)s;
+    // the slot's gradient row: mirrored inside its sequence when the forward wrote flipped outputs
+    a.vals[s] = a.h.flip_len ? (uint32_t)(flip_index(id_idx, a.h.flip_len) * a.slots_per_id + c) : (uint32_t)s;
   }
 }
 

@@ -119,7 +119,15 @@ struct HashSpec {
   uint32_t shard_world;
   uint32_t shard_rank;
   ModN mod_world;
+  uint32_t flip_len;  // > 0: outputs / gradient rows mirrored inside sequences of flip_len lookups
 };
+
+// position i mirrored inside its sequence of L lookups (L == 0: unchanged)
+__device__ __forceinline__ int64_t flip_index(int64_t i, uint32_t L) {
+  if (!L) return i;
+  const int64_t b = i / L;
+  return b * L + (L - 1 - (i - b * L));
+}
 
 int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,
                    const recemb_layout* layout = nullptr);

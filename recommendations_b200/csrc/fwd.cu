@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 #pragma unroll
               for (int e = 0; e < E; ++e) f[j][e] = f[j][e] / denom;
             if (a.inv_norm && l[u] < cnt && lig == 0)
-              a.inv_norm[tile * kTileIds + l[u]] = 1.f / denom;
+              a.inv_norm[flip_index(tile * kTileIds + l[u], a.h1.flip_len)] = 1.f / denom;
           }
 #pragma unroll
           for (int j = 0; j < V; ++j) v[u][j] = Vec16<T>::pack(f[j]);
@@ -181,7 +181,12 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const int vec = j * G + lig;
-            if (vec < a.row_vecs) stg_cs_v4(out_tile + (int64_t)l[u] * a.row_vecs + vec, v[u][j]);
+            if (vec < a.row_vecs) {
+              uint4* dst = a.h1.flip_len
+                               ? a.out + flip_index(tile * kTileIds + l[u], a.h1.flip_len) * a.row_vecs
+                               : out_tile + (int64_t)l[u] * a.row_vecs;
+              stg_cs_v4(dst + vec, v[u][j]);
+            }
           }
         }
       }
@@ -203,6 +208,7 @@ struct KShiftArgs {
   int epilogue;
   float sqrt_k;
   int bulk_ok;
+  uint32_t flip_len;
 };
 
 template <int G, int V, typename T>
@@ -291,7 +297,8 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
         for (int j = 0; j < V; ++j)
 #pragma unroll
           for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / denom;
-        if (a.inv_norm && live && lig == 0) a.inv_norm[tile * kTileIds + l] = 1.f / denom;
+        if (a.inv_norm && live && lig == 0)
+          a.inv_norm[flip_index(tile * kTileIds + l, a.flip_len)] = 1.f / denom;
       } else if (a.epilogue == RECEMB_EPI_RSQRT_K) {
 #pragma unroll
         for (int j = 0; j < V; ++j)
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
           for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / a.sqrt_k;
       }
       if (live) {
-        uint4* dst = a.out + (tile * kTileIds + l) * (int64_t)a.row_vecs;
+        uint4* dst = a.out + flip_index(tile * kTileIds + l, a.flip_len) * (int64_t)a.row_vecs;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const int vec = j * G + lig;
@@ -604,6 +611,8 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   RECEMB_UNSUPPORTED(!batched || n < 0xffffffffll, "too many lookups for table-batched mode");
   RECEMB_UNSUPPORTED(!layout || layout->shard_world <= 1, "sharded sequence gather is not implemented");
   rc = make_hash_spec(hash_mode, num_rows, hash_arg, &a.h1, layout);
+  RECEMB_CHECK_ARG(!layout || layout->flip_len == 0 || n % layout->flip_len == 0,
+                   "n is not a multiple of flip_len");
   if (rc) return rc;
   a.h2 = a.h1;
   if (table2) {
@@ -630,7 +639,7 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
 
 extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
                                  const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue,
-                                 void* out, float* inv_norm_out, int device,
+                                 int32_t flip_len, void* out, float* inv_norm_out, int device,
                                  recemb_stream_t stream) {
   RECEMB_CHECK_ARG(n >= 0, "n < 0");
   if (n == 0) return RECEMB_OK;
@@ -652,6 +661,8 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
   a.mod_rows = make_modn((uint64_t)num_rows);
   a.epilogue = epilogue;
   a.sqrt_k = (float)sqrt((double)num_shifts);
+  RECEMB_CHECK_ARG(flip_len >= 0 && (flip_len == 0 || n % flip_len == 0), "n is not a multiple of flip_len");
+  a.flip_len = (uint32_t)flip_len;
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);

@@ -53,7 +53,10 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
   h.shard_world = 1;
   h.shard_rank = 0;
   h.mod_world = make_modn(1);
+  h.flip_len = 0;
   if (layout) {
+    RECEMB_CHECK_ARG(layout->flip_len >= 0, "flip_len < 0");
+    h.flip_len = (uint32_t)layout->flip_len;
     RECEMB_CHECK_ARG(layout->ids_per_table >= 0 && layout->ids_per_table < 0xffffffffll,
                      "ids_per_table out of range");
     RECEMB_CHECK_ARG(layout->num_tables >= 0, "num_tables < 0");
@@ -129,7 +132,7 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   // another stream) is still computing; the kernels below must not.
   if (wait_event_after_copy)
     RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
-  recemb_layout layout = {ids_per_table, 0, 1, 0, 0};
+  recemb_layout layout = {ids_per_table, 0, 1, 0, 0};  // no sharding, no flip
   int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
                              &layout, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
                              stream);

@@ -28,13 +28,15 @@ class _GatherFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, anchor2, ids, holder, holder2, hash_mode, hash_mode2, hash_arg,
-                epilogue, zero_pad, pad_id):
+                epilogue, zero_pad, pad_id, flip_len=0):
         need_grad = anchor.requires_grad or (anchor2 is not None and anchor2.requires_grad)
         out, inv = ops.gather_fwd(
             holder.weight.detach(), ids, hash_mode=hash_mode, hash_arg=hash_arg,
             table2=None if holder2 is None else holder2.weight.detach(), hash_mode2=hash_mode2,
-            epilogue=epilogue, zero_pad=zero_pad, pad_id=pad_id, want_inv_norm=need_grad)
+            epilogue=epilogue, zero_pad=zero_pad, pad_id=pad_id, want_inv_norm=need_grad,
+            flip_len=flip_len)
         ctx.holder, ctx.holder2 = holder, holder2
+        ctx.flip_len = flip_len
         ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         return out
@@ -55,14 +57,16 @@ class _GatherFn(torch.autograd.Function):
             if holder.sparse and holder.fused is None:
                 rows = ops.row_index(ids.view(-1), mode, holder.num_embeddings, hash_arg)
                 vals = g.to(holder.weight.dtype)
+                if ctx.flip_len:  # gradient rows are in mirrored order
+                    vals = vals.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
                 grads[i] = _coo(rows, vals, holder)
                 continue
             plan = ops.BackwardPlan.build(
                 ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
                 zero_pad=zero_pad, pad_id=pad_id,
-                pad_row=-1 if holder.padding_idx is None else holder.padding_idx)
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
             grads[i] = holder.consume(plan, g)
-        return (grads[0], grads[1]) + (None,) * 9
+        return (grads[0], grads[1]) + (None,) * 10
 
 
 def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable) -> torch.Tensor:
@@ -75,10 +79,10 @@ def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable) -> torc
 
 class _KShiftFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, ids, holder, num_shifts, epilogue):
+    def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0):
         out, inv = ops.kshift_fwd(holder.weight.detach(), ids, num_shifts, epilogue,
-                                  want_inv_norm=anchor.requires_grad)
-        ctx.holder, ctx.k, ctx.epilogue = holder, num_shifts, epilogue
+                                  want_inv_norm=anchor.requires_grad, flip_len=flip_len)
+        ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         return out
 
@@ -92,12 +96,14 @@ class _KShiftFn(torch.autograd.Function):
             flat = ids.contiguous().view(-1)
             rows = torch.cat([ops.row_index(flat, N.HASH_ROTL_FLOORMOD, holder.num_embeddings, c)
                               for c in range(k)])
+            if ctx.flip_len:
+                dx = dx.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
             vals = dx.to(holder.weight.dtype).repeat(k, 1)
-            return (_coo(rows, vals, holder), None, None, None, None)
+            return (_coo(rows, vals, holder), None, None, None, None, None)
         plan = ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
-            pad_row=-1 if holder.padding_idx is None else holder.padding_idx)
-        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None)
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
+        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None)
 
 
 class _PoolFn(torch.autograd.Function):
@@ -144,6 +150,17 @@ def pooled_counts(ids, lengths, last_n, zero_pad, pad_id) -> torch.Tensor:
     return ok.sum(dim=1)
 
 
+def _flip_len(ids: torch.Tensor, flip: bool) -> int:
+    """flip_sequences: write the [.., L, D] output mirrored along L (Encoder.flip_all,
+    models/lthm/sequence/encoder.py:52-54: right-padded histories -> left-padded) inside the
+    gather instead of a torch.flip copy afterwards."""
+    if not flip:
+        return 0
+    if ids.dim() < 2:
+        raise N.NativeError("flip_sequences needs ids of shape [..., L]")
+    return int(ids.shape[-1])
+
+
 # ------------------------------------------------------------------ modules ----
 class FlatEmbedding(nn.Module):
     """commons/layers.py:44-61: row = floor_mod(id, N); out = table[row]; optional L2 norm.
@@ -156,8 +173,9 @@ class FlatEmbedding(nn.Module):
                  zero_init: bool = False, normalize_output: bool = False, *,
                  dtype: torch.dtype = torch.float32, device=None, sparse: bool = False,
                  fused_optimizer: Optional[FusedOptimizerConfig] = None,
-                 fused_pad_mask: bool = False):
+                 fused_pad_mask: bool = False, flip_sequences: bool = False):
         super().__init__()
+        self._flip_sequences = flip_sequences
         self._num_embeddings = num_embeddings
         self._emb_dim = emb_dim
         self.padding_idx = padding_idx
@@ -174,7 +192,7 @@ class FlatEmbedding(nn.Module):
         t = self._emb_table
         return _GatherFn.apply(t.grad_anchor(), None, x, t, None, N.HASH_FLOORMOD, 0, 0,
                                N.EPI_L2NORM if self._normalize_output else N.EPI_NONE,
-                               self._fused_pad_mask, 0)
+                               self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences))
 
 
 class KShiftEmbedding(nn.Module):
@@ -185,8 +203,9 @@ class KShiftEmbedding(nn.Module):
     def __init__(self, num_embeddings: int, emb_dim: int, num_shifts: int = 8,
                  normalize_output: bool = False, sparse: bool = False, *,
                  dtype: torch.dtype = torch.float32, device=None,
-                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None, flip_sequences: bool = False):
         super().__init__()
+        self._flip_sequences = flip_sequences
         self.emb = EmbeddingTable(num_embeddings, emb_dim, sparse=sparse, dtype=dtype, device=device)
         self._num_embeddings = num_embeddings
         self._num_shifts = num_shifts
@@ -197,7 +216,8 @@ class KShiftEmbedding(nn.Module):
 
     def forward(self, id_: torch.Tensor) -> torch.Tensor:
         return _KShiftFn.apply(self.emb.grad_anchor(), id_, self.emb, self._num_shifts,
-                               N.EPI_L2NORM if self._normalize_output else N.EPI_RSQRT_K)
+                               N.EPI_L2NORM if self._normalize_output else N.EPI_RSQRT_K,
+                               _flip_len(id_, self._flip_sequences))
 
     def get_row_idx(self, x: torch.Tensor, col_idx: int) -> torch.Tensor:
         """Bit-exact commons/layers.py:174-185 (wrapping <<, arithmetic >>, floor-mod)."""

@@ -39,7 +39,8 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
                hash_arg: int = 0, table2: Optional[torch.Tensor] = None,
                hash_mode2: int = N.HASH_FLOORMOD, epilogue: int = N.EPI_NONE,
                zero_pad: bool = False, pad_id: int = 0, want_inv_norm: bool = False,
-               out: Optional[torch.Tensor] = None, ids_per_table: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               out: Optional[torch.Tensor] = None, ids_per_table: int = 0,
+               flip_len: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     flat = _flat_ids(ids)
     dev = N.require_cuda(table, table2, flat, out)
     n, dim = flat.numel(), table.shape[1]
@@ -51,7 +52,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
     rows_per_table = table.shape[0]
-    layout = N.make_layout(ids_per_table=ids_per_table)
+    layout = N.make_layout(ids_per_table=ids_per_table, flip_len=flip_len)
     if ids_per_table:
         n_tables = -(-n // ids_per_table)
         if table.shape[0] % n_tables:
@@ -65,7 +66,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
 
 
 def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue: int,
-               want_inv_norm: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               want_inv_norm: bool = False, flip_len: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     flat = _flat_ids(ids)
     dev = N.require_cuda(table, flat)
     n, dim = flat.numel(), table.shape[1]
@@ -75,7 +76,7 @@ def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
     N.check(N.load().recemb_kshift_fwd(
         N.ptr(table), table.shape[0], dim, N.dtype_code(table.dtype), N.ptr(flat), n, num_shifts,
-        epilogue, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_kshift_fwd")
+        epilogue, flip_len, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_kshift_fwd")
     return out.view(*ids.shape, dim), inv
 
 
@@ -126,7 +127,8 @@ class BackwardPlan:
               hash_arg: int = 0, slots_per_id: int = 1, zero_pad: bool = False, pad_id: int = 0,
               pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
               last_n: int = 0, buf: Optional[torch.Tensor] = None, ids_per_table: int = 0,
-              num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0) -> "BackwardPlan":
+              num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
+              flip_len: int = 0) -> "BackwardPlan":
         """num_rows is rows PER TABLE; with ids_per_table > 0 the plan covers the stacked table
         of ceil(n_ids / ids_per_table) tables and `self.num_rows` is the stacked total."""
         flat = _flat_ids(ids)
@@ -135,7 +137,7 @@ class BackwardPlan:
         dev = N.require_cuda(flat, lengths)
         n_slots = flat.numel() * slots_per_id
         lib = N.load()
-        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank)
+        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank, flip_len)
         total_rows = int(lib.recemb_layout_total_rows(num_rows, layout, flat.numel()))
         need = int(lib.recemb_bwd_plan_bytes(n_slots, total_rows))
         if need == 0:
@@ -231,7 +233,7 @@ def shard_bucket(ids: torch.Tensor, *, num_rows: int, world: int, rank: int, bag
     m, p = ids.shape
     lib = N.load()
     layout = N.Layout(ids_per_table=bags_per_table * p, num_tables=num_tables, shard_world=world,
-                      shard_rank=rank, reserved=0)
+                      shard_rank=rank, flip_len=0)
     entries = torch.empty((m * p,), dtype=torch.int64, device=ids.device)
     counts = torch.empty((world,), dtype=torch.int64, device=ids.device)
     ws = torch.empty((int(lib.recemb_shard_bucket_workspace_bytes(m * p, world)),), dtype=torch.uint8,

@@ -55,7 +55,7 @@ def test_argument_errors_are_codes_not_crashes():
                                1 << 20, None, 0, None)
     assert rc == -1
     # bad k
-    rc = lib.recemb_kshift_fwd(1 << 20, 10, 4, N.F32, 1 << 20, 4, 64, N.EPI_RSQRT_K, 1 << 20, None, 0, None)
+    rc = lib.recemb_kshift_fwd(1 << 20, 10, 4, N.F32, 1 << 20, 4, 64, N.EPI_RSQRT_K, 0, 1 << 20, None, 0, None)
     assert rc == -1 and b"num_shifts" in lib.recemb_last_error()
     # workspace sizing is pure host arithmetic
     assert lib.recemb_bwd_apply_workspace_bytes(1_638_400, 64) > 2 * (1_638_400 // 64) * 64 * 4

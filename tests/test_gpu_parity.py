@@ -478,6 +478,39 @@ def test_padding_idx_row_never_updated():
     assert g[0].abs().sum() == 0 and g[9].sum() == 4 and g[3].sum() == 4
 
 
+# ----------------------------------------------- fused flip (right-pad -> left-pad) ----
+@pytest.mark.parametrize("kind", ["flat", "flat_norm", "kshift", "kshift_sparse"])
+def test_flip_sequences_equals_torch_flip(kind):
+    b, l, n_rows, dim = 37, 50, 4001, 32
+    torch.manual_seed(13)
+    w = torch.randn(n_rows, dim)
+    ids = seeded_ids(b * l, 90, (b, l))
+    ids[:, 35:] = 0
+    go = torch.randn(b, l, dim, generator=torch.Generator().manual_seed(14))
+    wr = w.clone().requires_grad_(True)
+    if kind.startswith("flat"):
+        norm = kind == "flat_norm"
+        m = R.FlatEmbedding(n_rows, dim, normalize_output=norm, flip_sequences=True, device=DEV)
+        m.load_state_dict({"_emb_table.weight": w})
+        ref = O.flat_embedding(wr, ids, normalize=norm).flip(1)
+        param = m._emb_table.weight
+    else:
+        m = R.KShiftEmbedding(n_rows, dim, num_shifts=8, normalize_output=True, flip_sequences=True,
+                              sparse=kind.endswith("sparse"), device=DEV)
+        m.load_state_dict({"emb.weight": w})
+        ref = O.kshift_embedding(wr, ids, 8, normalize=True).flip(1)
+        param = m.emb.weight
+    out = m(ids.to(DEV))
+    if kind == "flat":
+        assert torch.equal(out.cpu(), ref.detach())  # rows bit-exact, only re-addressed
+    else:
+        close(out, ref.detach())
+    out.backward(go.to(DEV))
+    ref.backward(go)
+    g = param.grad.to_dense() if param.grad.is_sparse else param.grad
+    torch.testing.assert_close(g.cpu(), wr.grad, rtol=1e-4, atol=1e-5)
+
+
 # ------------------------------------------------------------ table-batched mode ----
 def test_table_batched_gather_plan_update_equal_per_table_calls():
     t_tables, n, n_rows, dim = 3, 5000, 1009, 64
