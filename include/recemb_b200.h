@@ -286,6 +286,20 @@ RECEMB_API int recemb_dot_interaction_bwd(const void* feats, const void* grad_ou
                                int32_t num_feats, int32_t dim, void* grad_feats, int device,
                                recemb_stream_t stream);
 
+/* ---- id production (feeder of the path) ------------------------ */
+/* ids_out[i] = XXH64(bytes[offsets[i] : offsets[i+1]], seed) - 2^63 as signed int64: bit-exact
+ * hash_string_to_long (commons/feature_utils.py:40-46; xxhash==3.5.0).  to_lower lower-cases ASCII
+ * A-Z on the fly (value_to_lower; non-ASCII text must be lower-cased by the caller).  seed is
+ * hash_feature_name_to_int(feature) (:36-37, an xxh32 of the feature name, computed on the host). */
+RECEMB_API int recemb_xxh64_ids(const uint8_t* bytes, const int64_t* offsets, int64_t n, uint64_t seed,
+                     int to_lower, int64_t* ids_out, int device, recemb_stream_t stream);
+/* out[r, :] = the first history_length elements of values[offsets[r] : offsets[r+1]] that differ
+ * from remove_ids[r] (remove_ids optional), right-padded with pad_token: pad_array (:21-25) +
+ * handle_categorical_history_feature (:149-179, remove_history_id_from_history). */
+RECEMB_API int recemb_pad_histories(const int64_t* values, const int64_t* offsets, const int64_t* remove_ids,
+                         int64_t rows, int32_t history_length, int64_t pad_token, int64_t* out, int device,
+                         recemb_stream_t stream);
+
 /* ---- host-buffer entry points (end-to-end path) ---------------------------- */
 /* One fused training step of a FlatEmbedding-style table with HOST ids:
  * H2D copy of ids_host (pinned or pageable) into ids_dev_scratch, forward gather

@@ -103,6 +103,8 @@ SIGNATURES = {
     "recemb_sum_partials": (_INT, [_P, _I32, _I64, _I32, _INT, _P, _P, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
+    "recemb_xxh64_ids": (_INT, [_P, _P, _I64, C.c_uint64, _INT, _P, _INT, _P]),
+    "recemb_pad_histories": (_INT, [_P, _P, _P, _I64, _I32, _I64, _P, _INT, _P]),
     "recemb_flat_step_host": (_INT, [_P, _I64, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
                                      C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _P, _INT, _P]),
 }

@@ -557,3 +557,60 @@ def test_full_size_gather_and_update_properties():
     counts = torch.bincount(rows.view(-1), minlength=n_rows).float()
     assert torch.equal(w[:, 0], -counts) and torch.equal(w[:, 37], -counts)
     assert float(w[:, 0].double().sum()) == -float(n)  # checksum of checksums
+
+
+# -------------------- cfg 1 shapes: the LTHM product front-end the embedding path feeds ----
+def test_cfg1_lthm_product_front_end():
+    """BASELINE cfg 1 (B 256, L 50, KShiftEmbedding(10 000, 32, k = 8), right-padded histories):
+    Encoder.forward -> ProductTower front-end restated with the oracle (encoder.py:44-54,
+    product_tower.py:47-59): detached k-shift embeddings, pad mask ids == 0, six
+    CosineVectorEmbedding bags summed, masked_fill, flip to left-padding; then the
+    embedding_module_gen-style table update (fwd + bwd + Adagrad) on the same batch."""
+    b, l, n_rows, d_in, d_out, k = 256, 50, 10_000, 32, 64, 8
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(-2 ** 63, 2 ** 63 - 1, (b, l), generator=g, dtype=torch.int64)
+    valid = torch.randint(1, l + 1, (b,), generator=g)
+    ids[torch.arange(l).unsqueeze(0) >= valid.unsqueeze(1)] = 0  # right padding with token 0
+    torch.manual_seed(1234)
+    w = torch.randn(n_rows, d_in)
+    ks = R.KShiftEmbedding(n_rows, d_in, num_shifts=k, normalize_output=True, flip_sequences=True, device=DEV)
+    ks.load_state_dict({"emb.weight": w})
+    bins = [2, 4, 8, 12, 16, 20]
+    cvs = [R.CosineVectorEmbedding(d_in, d_out, n_proj=32, num_bins=nb, device=DEV) for nb in bins]
+
+    # --- B200 path: flipped gather, bags on the flipped embeddings, mask applied in flipped order
+    x = ks(ids.to(DEV)).detach()                                   # [B, L, d_in], already left-padded
+    mask = (ids == 0).flip(1).to(DEV)
+    emb = sum(cv(x) for cv in cvs).masked_fill(mask.unsqueeze(-1), 0.0)
+
+    # --- oracle restatement of the reference flow (flip last, as Encoder.flip_all does)
+    x_ref = O.kshift_embedding(w, ids, k, normalize=True)
+    emb_ref = torch.zeros(b, l, d_out)
+    agree = 1.0
+    for cv in cvs:
+        idxs = O.cosine_bucket_indices(x_ref, cv.projection_mat.cpu(), cv.grid.cpu(), cv.pos_offset.cpu())
+        got_idx = cv.bucket_indices(x.flip(1)).cpu()
+        agree = min(agree, (got_idx == idxs).float().mean().item())
+        emb_ref = emb_ref + O.embedding_bag_sum(cv.emb.weight.detach().cpu(), idxs).view(b, l, d_out)
+    emb_ref = emb_ref.masked_fill((ids == 0).unsqueeze(-1), 0.0).flip(1)
+    close(x, x_ref.flip(1))
+    assert agree >= 0.999  # bucket edges: float compare of a GPU vs CPU matmul
+    bad = (emb.cpu() - emb_ref).abs().amax(-1) > 1e-4          # positions whose bucket flipped at an edge
+    assert bad.float().mean().item() <= 0.01
+
+    # --- table update on the same batch (reconstruction loop body, embedding_module_gen.py:148-153)
+    ks2 = R.KShiftEmbedding(n_rows, d_in, num_shifts=k, normalize_output=True, device=DEV,
+                            fused_optimizer=R.FusedOptimizerConfig(kind="adagrad", lr=0.5))
+    ks2.load_state_dict({"emb.weight": w})
+    target = torch.nn.functional.normalize(torch.randn(b, l, d_in, generator=g), dim=-1)
+    loss = torch.nn.functional.mse_loss(ks2(ids.to(DEV)), target.to(DEV))
+    loss.backward()
+    wr = w.clone().requires_grad_(True)
+    loss_ref = torch.nn.functional.mse_loss(O.kshift_embedding(wr, ids, k, normalize=True), target)
+    loss_ref.backward()
+    w_ref, s_ref = w.clone(), torch.zeros_like(w)
+    O.adagrad_step(w_ref, wr.grad, s_ref, lr=0.5)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item()) + 1e-9
+    got = ks2.emb.weight.cpu()
+    err = (got - w_ref).abs()
+    assert (err <= 1e-5 + 1e-5 * w_ref.abs()).float().mean().item() >= 0.999 and err.max().item() <= 1.01
