@@ -9,6 +9,8 @@
 // shared memory by the TMA engine's 1-D bulk copy (cp.async.bulk -> UBLKCP)
 // double-buffered against the gather, table rows are read with
 // ld.global.nc.L1::no_allocate and write-once outputs leave with st.global.cs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace recemb {
@@ -83,6 +85,7 @@ struct GatherArgs {
   int zero_pad;
   int64_t pad_id;
   int bulk_ok;
+  int prefetch_iters;  // L2 prefetch distance in warp iterations (0 = off)
 };
 
 template <int G, int V, typename T, int EPI, bool TWO>
@@ -124,6 +127,24 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 
     uint4* out_tile = a.out + tile * kTileIds * (int64_t)a.row_vecs;
     for (int base = warp * RPW; base < cnt; base += kWarps * RPW * UNROLL) {
+      // pull the rows of a later iteration of this warp into L2 (row indices of the whole tile
+      // are already in shared memory): the loads below then mostly hit L2
+      if (a.prefetch_iters > 0) {
+        const int pbase = base + a.prefetch_iters * kWarps * RPW * UNROLL;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int pl = pbase + u * kWarps * RPW + gi;
+          if (pl < cnt) {
+            const int64_t r = rows[pl];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const int vec = j * G + lig;
+              if (r >= 0 && vec < a.row_vecs)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.table + r * a.row_vecs + vec));
+            }
+          }
+        }
+      }
       uint4 v[UNROLL][V];
       uint4 w[TWO ? UNROLL : 1][TWO ? V : 1];
       int l[UNROLL];
@@ -235,8 +256,6 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
     if (next < num_tiles) st.issue(b ^ 1, a.ids + next * kTileIds, tile_count(next));
     const int cnt = tile_count(tile);
     st.acquire(b, a.ids + tile * kTileIds, cnt);
-    if (!a.bulk_ok) {
-    }  // acquire() already synchronised
     const int64_t* ids = s_ids[b];
 
     for (int base = warp * RPW; base < cnt; base += kWarps * RPW) {
@@ -628,6 +647,14 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   a.zero_pad = zero_pad;
   a.pad_id = pad_id;
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
+  {
+    static int pf = -1;  // RECEMB_GATHER_PREFETCH=<iters> (tuning aid); default below
+    if (pf < 0) {
+      const char* e = getenv("RECEMB_GATHER_PREFETCH");
+      pf = e ? atoi(e) : 0;
+    }
+    a.prefetch_iters = pf;
+  }
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   const int64_t tiles = (n + kTileIds - 1) / kTileIds;

@@ -66,6 +66,14 @@ class Collectives:
         dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view((self.world,) + tuple(t.shape))
 
+    def all_gather_start(self, t: torch.Tensor):
+        """Asynchronous all_gather: returns (output view, wait()).  The collective runs on the
+        backend's own stream; kernels enqueued before wait() overlap with it."""
+        flat = t.contiguous().view(-1)
+        out = torch.empty((self.world * flat.numel(),), dtype=t.dtype, device=t.device)
+        work = dist.all_gather_into_tensor(out, flat, group=self.group, async_op=True)
+        return out.view((self.world,) + tuple(t.shape)), work.wait
+
     def exchange_counts(self, counts: torch.Tensor):
         """counts [W] (device): how many entries I send to each rank -> (send, recv) host lists.
         The one host synchronisation of the routed exchange."""
@@ -118,6 +126,9 @@ class SingleProcess(Collectives):
     def all_gather(self, t):
         return t.unsqueeze(0)
 
+    def all_gather_start(self, t):
+        return t.unsqueeze(0), (lambda: None)
+
     def all_to_all(self, t):
         return t
 
@@ -159,6 +170,15 @@ class _ShardedPoolFn(torch.autograd.Function):
         return module.local_backward(ids_all, len_all, g_all), None, None, None
 
 
+def _mark(module, name):
+    """Optional phase timing (module.phase_events = []): CUDA events at phase boundaries."""
+    ev = getattr(module, "phase_events", None)
+    if ev is not None and torch.cuda.is_available():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev.append((name, e))
+
+
 class _RoutedPoolFn(torch.autograd.Function):
     """exchange="route": each lookup travels only to the rank that owns its row."""
 
@@ -166,18 +186,26 @@ class _RoutedPoolFn(torch.autograd.Function):
     def forward(ctx, anchor, ids, lengths, module):
         comm: Collectives = module.comm
         w, b = comm.world, ids.shape[0]
+        _mark(module, "start")
         entries, counts = module.bucket(ids, lengths)                    # owner-major, device
+        _mark(module, "bucket")
         send_c, recv_c = comm.exchange_counts(counts)                    # host sync (bucket sizes)
+        _mark(module, "counts+sync")
         recv = comm.all_to_all_v(entries, send_c, recv_c)                # int64 [n_recv]
+        _mark(module, "a2a_entries")
         partial = module.pool_entries(module.emb.weight.detach(), recv, w * b)   # [W*B, D]
+        _mark(module, "pool_entries")
         back = comm.all_to_all(partial.view(w, b, -1))                   # owner s's partial of MY bags
+        _mark(module, "a2a_partials")
         scale = None
         if module.mode == "mean":
             scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad,
                                         module.pad_id).clamp_(min=1).float()
         ctx.module = module
         ctx.save_for_backward(recv, scale)
-        return module.reduce_partials(back, scale)
+        out = module.reduce_partials(back, scale)
+        _mark(module, "reduce")
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -186,9 +214,14 @@ class _RoutedPoolFn(torch.autograd.Function):
         g = grad_out.contiguous()
         if scale is not None:
             g = g * scale.unsqueeze(1).to(g.dtype)
-        g_all = module.comm.all_gather(g)                                # [W, B, D]
+        _mark(module, "bwd_start")
+        # the sort of the received entries does not need the gradients: it runs while the
+        # all-gather of the pooled gradients is in flight on the NCCL stream
+        g_all, wait = module.comm.all_gather_start(g)                    # [W, B, D]
         g_all = g_all.view(-1, g_all.shape[-1])
-        return module.entries_backward(recv, g_all), None, None, None
+        res = module.entries_backward(recv, g_all, wait)
+        _mark(module, "ag_grads||plan+apply")
+        return res, None, None, None
 
 
 class RowWiseShardedEmbeddingBag(nn.Module):
@@ -258,8 +291,9 @@ class RowWiseShardedEmbeddingBag(nn.Module):
                                 bags_per_table=b_tot // self.num_tables if self.num_tables > 1 else 0,
                                 num_tables=self.num_tables if self.num_tables > 1 else 0)
 
-    def _cuda_entries_backward(self, recv, g_all):
-        plan = ops.plan_from_entries(recv, self.emb.weight.shape[0])
+    def _cuda_entries_backward(self, recv, g_all, wait=lambda: None):
+        plan = ops.plan_from_entries(recv, self.emb.weight.shape[0])   # overlaps the gradient all-gather
+        wait()
         return self.emb.consume(plan, g_all, slots_per_grad_row=1)
 
     def _batching(self, ids_all):

@@ -112,6 +112,20 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     nv_in = (world - 1) * T * B_LOCAL * (P * 8 + 2 * row_bytes)   # ids + partials (fwd) + grads (bwd), per GPU
     t_step = ms / args.steps * 1e-3
     mod_exchange = mod.exchange
+    phases = None
+    if os.environ.get("RECEMB_PHASES"):
+        mod.phase_events = []
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        ev = mod.phase_events
+        acc = {}
+        for (n0, e0_), (n1, e1_) in zip(ev[:-1], ev[1:]):
+            if n1 in ("start",):
+                continue
+            acc.setdefault(n1, []).append(e0_.elapsed_time(e1_))
+        phases = {k: round(sum(v) / len(v), 4) for k, v in acc.items()}
+        mod.phase_events = None
     del mod, grad, ids
     torch.cuda.empty_cache()
     return {
@@ -123,7 +137,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
-            "gpu_launches": N.launch_count() - launches0}
+            "gpu_launches": N.launch_count() - launches0, "phases_ms": phases}
 
 
 def main():

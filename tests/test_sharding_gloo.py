@@ -73,7 +73,8 @@ def _make_hooks(world, rank, last_n):
         out.index_add_(0, recv & 0xFFFFFFFF, shard[recv >> 32])
         return out
 
-    def entries_backward(recv, g_all):
+    def entries_backward(recv, g_all, wait=lambda: None):
+        wait()
         n_local = (N_ROWS - rank + world - 1) // world
         gw = torch.zeros(n_local, g_all.shape[1])
         gw.index_add_(0, recv >> 32, g_all[recv & 0xFFFFFFFF])
