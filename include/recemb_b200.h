@@ -274,6 +274,93 @@ RECEMB_API int recemb_pool_entries(const void* table, int32_t dim, int dtype, co
 RECEMB_API int recemb_bwd_plan_entries(const int64_t* entries, int64_t n, int64_t total_rows, void* plan,
                             size_t plan_bytes, int device, recemb_stream_t stream);
 
+/* ---- row-wise sharding over peer memory (a12; NVLink 5 / NVSwitch P2P) -------- */
+/* The "peer" exchange replaces the NCCL collectives of the routed exchange by loads and stores
+ * on peer-mapped device memory inside the lookup kernels themselves (no host synchronisation,
+ * fixed shapes, CUDA-graph capturable):
+ *   forward   ONE kernel: every lookup reads its row straight from the owning rank's shard over
+ *             NVLink (ld.global on the mapped peer pointer) and is pooled on the requester in
+ *             slot order -- bit-identical to the unsharded pooled bag.
+ *   backward  bucket-by-owner (as recemb_shard_bucket) whose scatter stores each entry directly
+ *             into the owner's inbox, a push all-gather of the pooled gradients, one device-side
+ *             barrier over flags in peer memory, then the owner's sort + segmented reduction +
+ *             fused update of ITS rows; a second barrier closes the step (peers must not read
+ *             rows that are still being updated).
+ * Memory is shared with CUDA IPC: a rank exports the allocation behind a device pointer
+ * (recemb_peer_export), the handles travel over the caller's host channel (torch.distributed),
+ * every other rank maps them (recemb_peer_open).  The library keeps no global state: the mapped
+ * pointers live in a caller-owned recemb_peer_group. */
+#define RECEMB_PEER_HANDLE_BYTES 64
+#define RECEMB_MAX_PEERS 16
+
+typedef struct recemb_peer_group {
+  int32_t world;
+  int32_t rank;
+  void* arena[RECEMB_MAX_PEERS];       /* exchange arena of every rank as mapped HERE (arena[rank] is local) */
+  const void* table[RECEMB_MAX_PEERS]; /* stacked table shard of every rank as mapped HERE */
+} recemb_peer_group;
+
+/* Byte offsets inside one rank's exchange arena (identical on every rank). */
+typedef struct recemb_peer_arena {
+  int64_t bytes;       /* total size; the caller allocates it zero-filled, 256-byte aligned */
+  int64_t off_flags;   /* uint64 [world]   barrier flags, slot s is written by rank s */
+  int64_t off_epoch;   /* uint64           this rank's barrier count */
+  int64_t off_status;  /* uint32           sticky bits: 1 = inbox overflow (entries dropped), 2 = barrier timeout */
+  int64_t off_counts;  /* int64 [world]    entries rank s pushed into my inbox this step */
+  int64_t off_inbox;   /* int64 [world][cap] entries, region s written by rank s */
+  int64_t off_grads;   /* [world][bags_total][dim] pooled gradients, slice s written by rank s */
+  int64_t cap;         /* inbox capacity per sender (entries) */
+  int64_t bags_total;
+} recemb_peer_arena;
+
+/* handle_out identifies the whole allocation that contains ptr; *offset_out = ptr - its base. */
+RECEMB_API int recemb_peer_export(const void* ptr, uint8_t handle_out[RECEMB_PEER_HANDLE_BYTES],
+                       int64_t* offset_out, int64_t* alloc_bytes_out, int device);
+/* Maps an exported allocation into this process (peer access is enabled on demand); *base_out is
+ * the mapped base, add the exporter's offset.  A handle must be opened once per process. */
+RECEMB_API int recemb_peer_open(const uint8_t handle[RECEMB_PEER_HANDLE_BYTES], void** base_out, int device);
+RECEMB_API int recemb_peer_close(void* base, int device);
+
+RECEMB_API int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags_total, int32_t dim, int dtype,
+                             recemb_peer_arena* out);
+
+/* Device-side barrier over all ranks of the group (one tiny kernel on `stream`): everything the
+ * ranks enqueued before it -- including their stores into peer memory -- is visible to
+ * everything enqueued after it on any rank.  Every rank must call it the same number of times.
+ * A rank that waits longer than ~2 s sets status bit 2 and continues (no GPU hang). */
+RECEMB_API int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int device,
+                        recemb_stream_t stream);
+
+/* Forward.  As recemb_pool_fwd on the unsharded table of num_rows (GLOBAL) rows per table, except
+ * that global row r is read from group->table[r % world] at local row r / world (+ the table
+ * offset t * local_rows(owner) for stacked tables: layout->ids_per_table / num_tables).  `out` is
+ * the complete pool of this rank's bags. */
+RECEMB_API int recemb_peer_pool_fwd(const recemb_peer_group* group, int64_t num_rows, int32_t dim, int dtype,
+                         const int64_t* ids, int64_t num_bags, int32_t bag_size, const int32_t* lengths,
+                         int32_t last_n, const float* per_slot_weight, int hash_mode, int64_t hash_arg,
+                         int pool_mode, int zero_pad, int64_t pad_id, const recemb_layout* layout,
+                         void* out, int device, recemb_stream_t stream);
+
+/* Backward, sender side.  recemb_shard_bucket whose entries land in the owners' inboxes: entry
+ * k of my bucket for owner o is stored at inbox(o)[rank][k], the bucket size at counts(o)[rank].
+ * Entries beyond arena->cap are dropped and status bit 1 is set on this rank.  workspace as
+ * recemb_shard_bucket_workspace_bytes. */
+RECEMB_API int recemb_peer_bucket_push(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                            const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
+                            int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id, int32_t bag_size,
+                            const int32_t* lengths, int32_t last_n, void* workspace, size_t workspace_bytes,
+                            int device, recemb_stream_t stream);
+/* Backward, sender side.  Push all-gather: src (bytes, 16-byte multiple) is stored at
+ * arena(p) + dst_offset + rank * bytes of EVERY rank p (its own included). */
+RECEMB_API int recemb_peer_allgather_push(const recemb_peer_group* group, const void* src, int64_t bytes,
+                               int64_t dst_offset, int device, recemb_stream_t stream);
+/* Backward, owner side (after the barrier).  Plan over my inbox: world * cap (row, gradient row)
+ * pairs, unused inbox positions carry the sentinel key total_rows and sort last.  Use with
+ * recemb_bwd_apply(n_slots = world * cap, grad = my arena + off_grads, slots_per_grad_row = 1);
+ * plan as in recemb_bwd_plan_bytes(world * cap, total_rows). */
+RECEMB_API int recemb_peer_plan(const recemb_peer_group* group, const recemb_peer_arena* arena, int64_t total_rows,
+                     void* plan, size_t plan_bytes, int device, recemb_stream_t stream);
+
 /* ---- ranker pairwise dot interaction (a11) --------------------------------- */
 /* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:
  * the strictly-lower triangle of feats[b] @ feats[b]^T, fp32 accumulation on the

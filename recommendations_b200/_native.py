@@ -53,6 +53,27 @@ class Layout(C.Structure):
     ]
 
 
+PEER_HANDLE_BYTES = 64
+MAX_PEERS = 16
+
+
+class PeerGroupStruct(C.Structure):
+    """recemb_peer_group: every rank's arena / table shard as mapped in this process."""
+    _fields_ = [
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("arena", C.c_void_p * MAX_PEERS),
+        ("table", C.c_void_p * MAX_PEERS),
+    ]
+
+
+class PeerArena(C.Structure):
+    """recemb_peer_arena: byte offsets inside one rank's exchange arena."""
+    _fields_ = [(name, C.c_int64) for name in
+                ("bytes", "off_flags", "off_epoch", "off_status", "off_counts", "off_inbox", "off_grads",
+                 "cap", "bags_total")]
+
+
 def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
                 flip_len: int = 0):
     """None when nothing is batched / sharded / flipped (the C side treats NULL as one plain table)."""
@@ -101,6 +122,18 @@ SIGNATURES = {
     "recemb_pool_entries": (_INT, [_P, _I32, _INT, _P, _I64, _P, _INT, _P]),
     "recemb_bwd_plan_entries": (_INT, [_P, _I64, _I64, _P, _SZ, _INT, _P]),
     "recemb_sum_partials": (_INT, [_P, _I32, _I64, _I32, _INT, _P, _P, _INT, _P]),
+    "recemb_peer_export": (_INT, [_P, _P, C.POINTER(_I64), C.POINTER(_I64), _INT]),
+    "recemb_peer_open": (_INT, [_P, C.POINTER(_P), _INT]),
+    "recemb_peer_close": (_INT, [_P, _INT]),
+    "recemb_peer_arena_layout": (_INT, [_I32, _I64, _I64, _I32, _INT, C.POINTER(PeerArena)]),
+    "recemb_peer_barrier": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _P]),
+    "recemb_peer_pool_fwd": (_INT, [C.POINTER(PeerGroupStruct), _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P,
+                                    _INT, _I64, _INT, _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
+    "recemb_peer_bucket_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
+                                       C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32, _P, _SZ,
+                                       _INT, _P]),
+    "recemb_peer_allgather_push": (_INT, [C.POINTER(PeerGroupStruct), _P, _I64, _I64, _INT, _P]),
+    "recemb_peer_plan": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I64, _P, _SZ, _INT, _P]),
     "recemb_dot_interaction_fwd": (_INT, [_P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_xxh64_ids": (_INT, [_P, _P, _I64, C.c_uint64, _INT, _P, _INT, _P]),

@@ -354,17 +354,26 @@ struct PoolArgs {
   int zero_pad;
   int64_t pad_id;
   int bulk_ok;
+  // PEER: global row r of a table lives on rank r % world (h.mod_world) at local row r / world of
+  // peer_table[r % world] (every rank's stacked shard, peer-mapped over NVLink); table == nullptr
+  const uint4* peer_table[RECEMB_MAX_PEERS];
+  int64_t rows_div;  // num_rows / world: local rows of owner o = rows_div + (o < rows_rem)
+  uint32_t rows_rem;
 };
 
 constexpr int kPoolTileIds = 2048;
 
-template <int G, int V, typename T>
+template <int G, int V, typename T, bool PEER>
 __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const PoolArgs a) {
   constexpr int RPW = 32 / G;
   constexpr int E = Vec16<T>::kElems;
   constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);
   __shared__ alignas(16) int64_t s_ids[2][kPoolTileIds];
   __shared__ alignas(8) uint64_t s_bar[2];
+  __shared__ const uint4* s_peer[PEER ? RECEMB_MAX_PEERS : 1];
+  if constexpr (PEER) {
+    if (threadIdx.x < RECEMB_MAX_PEERS) s_peer[threadIdx.x] = a.peer_table[threadIdx.x];
+  }  // published by the __syncthreads() of IdStager::init
 
   const int64_t num_tiles = (a.num_bags + a.bags_per_tile - 1) / a.bags_per_tile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -415,9 +424,25 @@ __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const 
         const bool my_ok = live && my_p < hi;
         const int64_t my_id = my_ok ? ids[lb * P + my_p] : 0;
         const bool my_use = my_ok && !(a.zero_pad && my_id == a.pad_id);
-        int64_t my_row = my_use ? row_of(my_id, a.h) : -1;
-        if (my_row >= 0) my_row = shard_local_row(my_row, a.h);  // -1: another rank owns it
-        if (my_row >= 0) my_row += table_offset(bag * P + my_p, a.h);
+        // address of the slot's row (0 = nothing to pool), shuffled to the lanes that load it
+        uint64_t my_src = 0;
+        if constexpr (PEER) {
+          if (my_use) {
+            uint64_t q;
+            const uint32_t o = (uint32_t)udivmod((uint64_t)row_of(my_id, a.h), a.h.mod_world, &q);
+            if (a.h.ids_per_table) {
+              uint32_t t = (uint32_t)(bag * P + my_p) / a.h.ids_per_table;
+              if (a.h.num_tables) t %= a.h.num_tables;
+              q += (uint64_t)t * (uint64_t)(a.rows_div + (o < a.rows_rem ? 1 : 0));
+            }
+            my_src = (uint64_t)(s_peer[o] + q * (uint64_t)a.row_vecs);
+          }
+        } else {
+          int64_t my_row = my_use ? row_of(my_id, a.h) : -1;
+          if (my_row >= 0) my_row = shard_local_row(my_row, a.h);  // -1: another rank owns it
+          if (my_row >= 0) my_row += table_offset(bag * P + my_p, a.h);
+          if (my_row >= 0) my_src = (uint64_t)(a.table + my_row * a.row_vecs);
+        }
         float my_w = 1.f;
         if (my_use && a.slot_weight) my_w = a.slot_weight[bag * P + my_p];
         const int sub = min(G, span - p0);
@@ -429,14 +454,14 @@ __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const 
           for (int u = 0; u < BATCH; ++u) {
             const int cc = cb + u;
             const int src = gi * G + (cc < G ? cc : 0);
-            const int64_t r = __shfl_sync(0xffffffffu, my_row, src);
+            const uint4* r = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, my_src, src));
             wt[u] = __shfl_sync(0xffffffffu, my_w, src);
-            use[u] = (cc < sub) && r >= 0;
+            use[u] = (cc < sub) && r != nullptr;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
               const int vec = j * G + lig;
               v[u][j] = make_uint4(0, 0, 0, 0);
-              if (use[u] && vec < a.row_vecs) v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+              if (use[u] && vec < a.row_vecs) v[u][j] = ldg_nc_v4(r + vec);
             }
           }
 #pragma unroll
@@ -565,9 +590,13 @@ static int launch_kshift(const KShiftArgs& a, RowShape shape, int64_t tiles, int
 }
 
 template <typename T>
-static int launch_pool(const PoolArgs& a, RowShape shape, int64_t tiles, int device, cudaStream_t s) {
+static int launch_pool(const PoolArgs& a, RowShape shape, int64_t tiles, int device, cudaStream_t s, bool peer) {
   bool launched = false;
-  DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T>>(a, tiles, device, s)))
+  if (peer) {
+    DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T, true>>(a, tiles, device, s)))
+  } else {
+    DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T, false>>(a, tiles, device, s)))
+  }
   if (!launched) {
     set_error("pool: no kernel for G=%d V=%d", shape.G, shape.V);
     return RECEMB_ERR_UNSUPPORTED;
@@ -698,15 +727,17 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
   return launch_kshift<__nv_bfloat16>(a, shape, tiles, device, (cudaStream_t)stream);
 }
 
-extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
-                               const int64_t* ids, int64_t num_bags, int32_t bag_size,
-                               const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
-                               int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad,
-                               int64_t pad_id, const recemb_layout* layout, void* out, int device,
-                               recemb_stream_t stream) {
+// shared by recemb_pool_fwd (one local table / shard) and recemb_peer_pool_fwd (group != nullptr:
+// rows are read from the owning rank's shard over peer-mapped memory)
+static int pool_fwd_common(const void* table, const recemb_peer_group* group, int64_t num_rows, int32_t dim,
+                           int dtype, const int64_t* ids, int64_t num_bags, int32_t bag_size,
+                           const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
+                           int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad,
+                           int64_t pad_id, const recemb_layout* layout, void* out, int device,
+                           recemb_stream_t stream) {
   RECEMB_CHECK_ARG(num_bags >= 0, "num_bags < 0");
   if (num_bags == 0) return RECEMB_OK;
-  RECEMB_CHECK_ARG(table && ids && out, "null pointer");
+  RECEMB_CHECK_ARG((table || group) && ids && out, "null pointer");
   RECEMB_CHECK_ARG(bag_size >= 1, "bag_size < 1");
   RECEMB_UNSUPPORTED(bag_size <= kPoolTileIds, "bag_size %d > %d", bag_size, kPoolTileIds);
   RECEMB_CHECK_ARG(pool_mode == RECEMB_POOL_SUM || pool_mode == RECEMB_POOL_MEAN, "bad pool_mode");
@@ -721,6 +752,22 @@ extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
   RECEMB_UNSUPPORTED(!(layout && layout->ids_per_table > 0) || num_bags * bag_size < 0xffffffffll,
                      "too many slots for table-batched mode");
   a.table = (const uint4*)table;
+  a.rows_div = num_rows;
+  a.rows_rem = 0;
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.peer_table[i] = nullptr;
+  if (group) {
+    RECEMB_CHECK_ARG(group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
+                         group->rank < group->world,
+                     "peer group world %d / rank %d out of range", group->world, group->rank);
+    RECEMB_CHECK_ARG(!layout || layout->shard_world <= 1, "peer pooling takes an unsharded layout");
+    for (int i = 0; i < group->world; ++i) {
+      RECEMB_CHECK_ARG(group->table[i] && (uintptr_t)group->table[i] % 16 == 0, "peer table %d null / misaligned", i);
+      a.peer_table[i] = (const uint4*)group->table[i];
+    }
+    a.h.mod_world = make_modn((uint64_t)group->world);
+    a.rows_div = num_rows / group->world;
+    a.rows_rem = (uint32_t)(num_rows % group->world);
+  }
   a.ids = ids;
   a.lengths = lengths;
   a.slot_weight = per_slot_weight;
@@ -746,6 +793,29 @@ extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim,
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   const int64_t tiles = (num_bags + a.bags_per_tile - 1) / a.bags_per_tile;
-  if (dtype == RECEMB_F32) return launch_pool<float>(a, shape, tiles, device, (cudaStream_t)stream);
-  return launch_pool<__nv_bfloat16>(a, shape, tiles, device, (cudaStream_t)stream);
+  if (dtype == RECEMB_F32) return launch_pool<float>(a, shape, tiles, device, (cudaStream_t)stream, group != nullptr);
+  return launch_pool<__nv_bfloat16>(a, shape, tiles, device, (cudaStream_t)stream, group != nullptr);
+}
+
+extern "C" int recemb_pool_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                               const int64_t* ids, int64_t num_bags, int32_t bag_size,
+                               const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
+                               int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad,
+                               int64_t pad_id, const recemb_layout* layout, void* out, int device,
+                               recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(table || num_bags == 0, "null table");
+  return pool_fwd_common(table, nullptr, num_rows, dim, dtype, ids, num_bags, bag_size, lengths, last_n,
+                         per_slot_weight, hash_mode, hash_arg, pool_mode, zero_pad, pad_id, layout, out, device,
+                         stream);
+}
+
+extern "C" int recemb_peer_pool_fwd(const recemb_peer_group* group, int64_t num_rows, int32_t dim, int dtype,
+                                    const int64_t* ids, int64_t num_bags, int32_t bag_size,
+                                    const int32_t* lengths, int32_t last_n, const float* per_slot_weight,
+                                    int hash_mode, int64_t hash_arg, int pool_mode, int zero_pad, int64_t pad_id,
+                                    const recemb_layout* layout, void* out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group, "null peer group");
+  return pool_fwd_common(nullptr, group, num_rows, dim, dtype, ids, num_bags, bag_size, lengths, last_n,
+                         per_slot_weight, hash_mode, hash_arg, pool_mode, zero_pad, pad_id, layout, out, device,
+                         stream);
 }

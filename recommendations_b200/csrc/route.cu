@@ -41,6 +41,11 @@ struct BucketArgs {
   int64_t* entries;     // [n]
   int64_t* counts;      // [world]
   uint32_t* block_base; // [num_ctas, world]  exclusive offsets, filled by the scan
+  // peer exchange (PEER kernels): entries go straight into the owners' inboxes over NVLink
+  int64_t* peer_inbox[RECEMB_MAX_PEERS];  // owner o's inbox region reserved for THIS rank, [cap]
+  int64_t* peer_count[RECEMB_MAX_PEERS];  // owner o's count slot for THIS rank
+  uint32_t cap;                           // inbox capacity per sender
+  uint32_t* status;                       // this rank's sticky status word (bit 0: inbox overflow)
 };
 
 __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketArgs a) {
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketAr
 }
 
 // one warp per owner: exclusive scan of that owner's per-CTA counts; then owner bases
+template <bool PEER>
 __global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, int num_ctas) {
   __shared__ uint32_t s_total[kMaxWorld];
   const int world = (int)a.h.shard_world;
@@ -108,6 +114,19 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, i
     if (lane == 0) s_total[o] = carry;
   }
   __syncthreads();
+  if constexpr (PEER) {
+    // every bucket starts at 0 of its own inbox region; the owner learns the size from its count slot
+    if (threadIdx.x < world) {
+      uint32_t t = s_total[threadIdx.x];
+      if (t > a.cap) {
+        t = a.cap;
+        atomicOr(a.status, 1u);
+      }
+      *a.peer_count[threadIdx.x] = (int64_t)t;
+      if (a.counts) a.counts[threadIdx.x] = (int64_t)t;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     uint32_t run = 0;
     for (int i = 0; i < world; ++i) {
@@ -123,12 +142,17 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, i
 }
 
 // stable scatter: position = base[cta][owner] + (valid slots of that owner earlier in the CTA)
+template <bool PEER>
 __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const BucketArgs a) {
   __shared__ uint32_t s_run[kMaxWorld];                       // running offset per owner
   __shared__ uint32_t s_wc[kRtThreads / 32][kMaxWorld];       // per-warp counts of this round
+  __shared__ int64_t* s_dst[PEER ? RECEMB_MAX_PEERS : 1];     // PEER: my region of every owner's inbox
   const uint32_t world = a.h.shard_world;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < world) s_run[threadIdx.x] = a.block_base[(int64_t)blockIdx.x * world + threadIdx.x];
+  if constexpr (PEER) {
+    if (threadIdx.x < RECEMB_MAX_PEERS) s_dst[threadIdx.x] = a.peer_inbox[threadIdx.x];
+  }  // both published by the first __syncthreads() of the loop
   const int64_t base = (int64_t)blockIdx.x * kRtBlock;
   for (int r = 0; r < kRtItems; ++r) {
     for (int i = threadIdx.x; i < (kRtThreads / 32) * kMaxWorld; i += kRtThreads) (&s_wc[0][0])[i] = 0;
@@ -145,7 +169,12 @@ __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const Bucket
       uint32_t pos = s_run[owner] + rank;
       for (int w = 0; w < warp; ++w) pos += s_wc[w][owner];
       const uint32_t bag = (uint32_t)(s / a.bag_size);
-      a.entries[pos] = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)(a.bag_base + bag));
+      const int64_t entry = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)(a.bag_base + bag));
+      if constexpr (PEER) {
+        if (pos < a.cap) s_dst[owner][pos] = entry;  // store into the owner's HBM over NVLink
+      } else {
+        a.entries[pos] = entry;
+      }
     }
     __syncthreads();
     if (threadIdx.x < world) {
@@ -244,6 +273,23 @@ __global__ void __launch_bounds__(kRtThreads) unpack_entries_kernel(const int64_
   }
 }
 
+// inbox [world][cap] + counts [world] -> (key, value) pairs; unused positions get the sentinel key
+__global__ void __launch_bounds__(kRtThreads) unpack_inbox_kernel(const int64_t* __restrict__ inbox,
+                                                                 const int64_t* __restrict__ counts, int64_t cap,
+                                                                 int64_t n, uint32_t sentinel,
+                                                                 uint32_t* __restrict__ keys,
+                                                                 uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * kRtThreads;
+  for (; i < n; i += stride) {
+    const int64_t sender = i / cap;
+    const bool valid = (i - sender * cap) < counts[sender];
+    const uint64_t e = valid ? (uint64_t)inbox[i] : 0ull;
+    keys[i] = valid ? (uint32_t)(e >> 32) : sentinel;
+    vals[i] = (uint32_t)(e & 0xffffffffull);
+  }
+}
+
 }  // namespace recemb
 
 using namespace recemb;
@@ -255,15 +301,17 @@ extern "C" size_t recemb_shard_bucket_workspace_bytes(int64_t n_slots, int32_t w
          2 * align_up((size_t)(ctas > 0 ? ctas : 1) * world * 4, 256) + 256;
 }
 
-extern "C" int recemb_shard_bucket(const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
-                                   int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
-                                   int32_t bag_size, const int32_t* lengths, int32_t last_n, int64_t bags_total,
-                                   int64_t* entries_out, int64_t* counts_out, void* workspace,
-                                   size_t workspace_bytes, int device, recemb_stream_t stream) {
+// group == nullptr: buckets into entries_out / counts_out (routed NCCL exchange);
+// group != nullptr: buckets straight into the owners' inboxes (peer exchange)
+static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena* arena, const int64_t* ids,
+                         int64_t n_ids, const recemb_layout* layout, int hash_mode, int64_t num_rows,
+                         int64_t hash_arg, int zero_pad, int64_t pad_id, int32_t bag_size, const int32_t* lengths,
+                         int32_t last_n, int64_t bags_total, int64_t* entries_out, int64_t* counts_out,
+                         void* workspace, size_t workspace_bytes, int device, recemb_stream_t stream) {
   RECEMB_CHECK_ARG(layout && layout->shard_world >= 1 && layout->shard_world <= kMaxWorld,
                    "shard_world outside [1, %d]", kMaxWorld);
   RECEMB_CHECK_ARG(bag_size >= 1 && n_ids >= 0 && n_ids % bag_size == 0, "n_ids not a multiple of bag_size");
-  RECEMB_CHECK_ARG(counts_out && workspace, "null pointer");
+  RECEMB_CHECK_ARG((group || counts_out) && workspace, "null pointer");
   RECEMB_UNSUPPORTED(n_ids < 0x7fffffffll, "too many slots");
   RECEMB_UNSUPPORTED((int64_t)layout->shard_world * bags_total < 0xffffffffll, "bag keys overflow 32 bits");
   RECEMB_UNSUPPORTED(recemb_layout_total_rows(num_rows, layout, n_ids) < 0xfffffff0ll, "local rows overflow 32 bits");
@@ -300,18 +348,73 @@ extern "C" int recemb_shard_bucket(const int64_t* ids, int64_t n_ids, const rece
   a.block_base = (uint32_t*)w;
   a.entries = entries_out;
   a.counts = counts_out;
+  a.cap = 0;
+  a.status = nullptr;
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.peer_inbox[i] = a.peer_count[i] = nullptr;
+  if (group) {
+    RECEMB_CHECK_ARG(arena && group->world == layout->shard_world && group->rank == layout->shard_rank &&
+                         group->world <= RECEMB_MAX_PEERS,
+                     "peer group does not match the layout (world %d rank %d)", group->world, group->rank);
+    RECEMB_CHECK_ARG(arena->cap >= 1 && arena->cap < 0xffffffffll && arena->bags_total == bags_total,
+                     "arena capacity / bags_total mismatch");
+    for (int o = 0; o < group->world; ++o) {
+      RECEMB_CHECK_ARG(group->arena[o], "peer arena %d not mapped", o);
+      char* base = (char*)group->arena[o];
+      a.peer_inbox[o] = (int64_t*)(base + arena->off_inbox) + (int64_t)group->rank * arena->cap;
+      a.peer_count[o] = (int64_t*)(base + arena->off_counts) + group->rank;
+    }
+    a.cap = (uint32_t)arena->cap;
+    a.status = (uint32_t*)((char*)group->arena[group->rank] + arena->off_status);
+  }
   if (n_ids == 0) {
-    RECEMB_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int64_t) * layout->shard_world, s));
+    if (group) {
+      bucket_scan_kernel<true><<<1, 32 * layout->shard_world, 0, s>>>(a, 0);  // zero counts at the owners
+      RECEMB_LAUNCHED();
+    } else {
+      RECEMB_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int64_t) * layout->shard_world, s));
+    }
     return RECEMB_OK;
   }
-  RECEMB_CHECK_ARG(ids && entries_out, "null ids / entries");
+  RECEMB_CHECK_ARG(ids && (group || entries_out), "null ids / entries");
   bucket_count_kernel<<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
   RECEMB_LAUNCHED();
-  bucket_scan_kernel<<<1, 32 * layout->shard_world, 0, s>>>(a, (int)ctas);
-  RECEMB_LAUNCHED();
-  bucket_scatter_kernel<<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
-  RECEMB_LAUNCHED();
+  if (group) {
+    bucket_scan_kernel<true><<<1, 32 * layout->shard_world, 0, s>>>(a, (int)ctas);
+    RECEMB_LAUNCHED();
+    bucket_scatter_kernel<true><<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
+    RECEMB_LAUNCHED();
+  } else {
+    bucket_scan_kernel<false><<<1, 32 * layout->shard_world, 0, s>>>(a, (int)ctas);
+    RECEMB_LAUNCHED();
+    bucket_scatter_kernel<false><<<(unsigned)ctas, kRtThreads, 0, s>>>(a);
+    RECEMB_LAUNCHED();
+  }
   return RECEMB_OK;
+}
+
+extern "C" int recemb_shard_bucket(const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
+                                   int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
+                                   int32_t bag_size, const int32_t* lengths, int32_t last_n, int64_t bags_total,
+                                   int64_t* entries_out, int64_t* counts_out, void* workspace,
+                                   size_t workspace_bytes, int device, recemb_stream_t stream) {
+  return bucket_common(nullptr, nullptr, ids, n_ids, layout, hash_mode, num_rows, hash_arg, zero_pad, pad_id,
+                       bag_size, lengths, last_n, bags_total, entries_out, counts_out, workspace, workspace_bytes,
+                       device, stream);
+}
+
+extern "C" int recemb_peer_bucket_push(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                       const int64_t* ids, int64_t n_ids, const recemb_layout* layout,
+                                       int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad,
+                                       int64_t pad_id, int32_t bag_size, const int32_t* lengths, int32_t last_n,
+                                       void* workspace, size_t workspace_bytes, int device,
+                                       recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena, "null peer group / arena");
+  RECEMB_CHECK_ARG(bag_size >= 1 && n_ids == arena->bags_total * bag_size,
+                   "n_ids %lld != arena bags_total %lld x bag_size %d", (long long)n_ids,
+                   (long long)arena->bags_total, bag_size);
+  return bucket_common(group, arena, ids, n_ids, layout, hash_mode, num_rows, hash_arg, zero_pad, pad_id, bag_size,
+                       lengths, last_n, arena->bags_total, nullptr, nullptr, workspace, workspace_bytes, device,
+                       stream);
 }
 
 extern "C" int recemb_pool_entries(const void* table, int32_t dim, int dtype, const int64_t* entries, int64_t n,
@@ -381,6 +484,48 @@ extern "C" int recemb_bwd_plan_entries(const int64_t* entries, int64_t n, int64_
   unpack_entries_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>(entries, n, keys_in, vals_in);
   RECEMB_LAUNCHED();
   int bits = 0;
+  for (uint64_t x = (uint64_t)total_rows; x; x >>= 1) ++bits;
+  RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
+                                              (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return RECEMB_OK;
+}
+
+
+extern "C" int recemb_peer_plan(const recemb_peer_group* group, const recemb_peer_arena* arena, int64_t total_rows,
+                                void* plan, size_t plan_bytes, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena && group->world >= 1 && group->world <= RECEMB_MAX_PEERS, "bad peer group");
+  RECEMB_CHECK_ARG(total_rows >= 1 && arena->cap >= 1, "bad total_rows / capacity");
+  RECEMB_CHECK_ARG(plan && (uintptr_t)plan % 256 == 0, "plan buffer missing / misaligned");
+  const int64_t n = (int64_t)group->world * arena->cap;
+  RECEMB_UNSUPPORTED(n < 0x7fffffffll && total_rows < 0xfffffff0ll, "sizes overflow 32-bit keys");
+  const size_t need = recemb_bwd_plan_bytes(n, total_rows);
+  if (need == 0) return RECEMB_ERR_CUDA;
+  if (plan_bytes < need) {
+    set_error("plan buffer %zu < required %zu", plan_bytes, need);
+    return RECEMB_ERR_WORKSPACE;
+  }
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  const char* mine = (const char*)group->arena[group->rank];
+  RECEMB_CHECK_ARG(mine, "local arena missing");
+  const size_t arr = align_up((size_t)n * 4, 256);
+  char* base = (char*)plan;
+  uint32_t* keys_in = (uint32_t*)(base + 256);
+  uint32_t* vals_in = (uint32_t*)(base + 256 + arr);
+  uint32_t* keys_out = (uint32_t*)(base + 256 + 2 * arr);
+  uint32_t* vals_out = (uint32_t*)(base + 256 + 3 * arr);
+  void* temp = base + 256 + 4 * arr;
+  size_t temp_bytes = plan_bytes - (256 + 4 * arr);
+  int64_t grid = (n + kRtThreads - 1) / kRtThreads;
+  const int64_t cap_grid = (int64_t)sm_count(device) * 16;
+  if (grid > cap_grid) grid = cap_grid;
+  unpack_inbox_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>((const int64_t*)(mine + arena->off_inbox),
+                                                           (const int64_t*)(mine + arena->off_counts), arena->cap,
+                                                           n, (uint32_t)total_rows, keys_in, vals_in);
+  RECEMB_LAUNCHED();
+  int bits = 0;  // the sentinel key == total_rows must sort last
   for (uint64_t x = (uint64_t)total_rows; x; x >>= 1) ++bits;
   RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
                                               (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));

@@ -282,6 +282,79 @@ def sum_partials(parts: torch.Tensor, row_scale: Optional[torch.Tensor] = None) 
     return out
 
 
+# ------------------------------------------------------------ peer exchange ----
+def peer_pool_fwd(group, ids: torch.Tensor, *, num_rows: int, dim: int, dtype: torch.dtype,
+                  lengths: Optional[torch.Tensor] = None, last_n: int = 0,
+                  per_slot_weight: Optional[torch.Tensor] = None, hash_mode: int = N.HASH_FLOORMOD,
+                  hash_arg: int = 0, pool_mode: int = N.POOL_SUM, zero_pad: bool = False, pad_id: int = 0,
+                  bags_per_table: int = 0, num_tables: int = 0) -> torch.Tensor:
+    """Pooled bags over a row-wise sharded table: every row is read from its owner's shard through
+    peer-mapped memory (group: peer.PeerGroup).  Complete pools of THIS rank's bags, slot order."""
+    if ids.dim() != 2 or ids.dtype != torch.int64:
+        raise N.NativeError("pooled bags take int64 ids of shape [num_bags, bag_size]")
+    ids = ids.contiguous()
+    if lengths is not None:
+        lengths = lengths.to(torch.int32).contiguous()
+    if per_slot_weight is not None:
+        per_slot_weight = per_slot_weight.to(torch.float32).contiguous()
+    dev = N.require_cuda(ids, lengths, per_slot_weight)
+    m, p = ids.shape
+    out = torch.empty((m, dim), dtype=dtype, device=ids.device)
+    N.check(N.load().recemb_peer_pool_fwd(
+        C.byref(group.struct), num_rows, dim, N.dtype_code(dtype), N.ptr(ids), m, p, N.ptr(lengths), last_n,
+        N.ptr(per_slot_weight), hash_mode, hash_arg, pool_mode, int(zero_pad), pad_id,
+        N.make_layout(bags_per_table * p, num_tables), N.ptr(out), dev, N.stream_ptr(dev)),
+        "recemb_peer_pool_fwd")
+    return out
+
+
+def peer_bucket_push(group, ids: torch.Tensor, *, num_rows: int, lengths: Optional[torch.Tensor] = None,
+                     last_n: int = 0, zero_pad: bool = False, pad_id: int = 0, bags_per_table: int = 0,
+                     num_tables: int = 0, hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0) -> None:
+    """Sender side of the peer backward: my (local row, gradient row) entries land in the owners'
+    inboxes, my bucket sizes in their count slots."""
+    ids = ids.contiguous()
+    if lengths is not None:
+        lengths = lengths.to(torch.int32).contiguous()
+    dev = N.require_cuda(ids, lengths)
+    m, p = ids.shape
+    lib = N.load()
+    layout = N.Layout(ids_per_table=bags_per_table * p, num_tables=num_tables, shard_world=group.world,
+                      shard_rank=group.rank, flip_len=0)
+    ws = torch.empty((int(lib.recemb_shard_bucket_workspace_bytes(m * p, group.world)),), dtype=torch.uint8,
+                     device=ids.device)
+    N.check(lib.recemb_peer_bucket_push(C.byref(group.struct), C.byref(group.layout), N.ptr(ids), m * p, layout,
+                                        hash_mode, num_rows, hash_arg, int(zero_pad), pad_id, p, N.ptr(lengths),
+                                        last_n, N.ptr(ws), ws.numel(), dev, N.stream_ptr(dev)),
+            "recemb_peer_bucket_push")
+
+
+def peer_allgather_push(group, src: torch.Tensor, dst_offset: int) -> None:
+    """src -> slice `rank` at dst_offset of every rank's arena (push all-gather over NVLink)."""
+    src = src.contiguous()
+    dev = N.require_cuda(src)
+    N.check(N.load().recemb_peer_allgather_push(C.byref(group.struct), N.ptr(src), src.numel() * src.element_size(),
+                                                dst_offset, dev, N.stream_ptr(dev)), "recemb_peer_allgather_push")
+
+
+def peer_barrier(group) -> None:
+    N.check(N.load().recemb_peer_barrier(C.byref(group.struct), C.byref(group.layout), group.device,
+                                         N.stream_ptr(group.device)), "recemb_peer_barrier")
+
+
+def peer_plan(group, total_rows: int) -> "BackwardPlan":
+    """Owner side (after the barrier): plan over my inbox, world * cap pairs, unused ones = sentinel."""
+    lib = N.load()
+    n = group.world * int(group.layout.cap)
+    need = int(lib.recemb_bwd_plan_bytes(n, total_rows))
+    if need == 0:
+        N.check(-2, "recemb_bwd_plan_bytes")
+    buf = torch.empty((need,), dtype=torch.uint8, device=group.arena.device)
+    N.check(lib.recemb_peer_plan(C.byref(group.struct), C.byref(group.layout), total_rows, N.ptr(buf), buf.numel(),
+                                 group.device, N.stream_ptr(group.device)), "recemb_peer_plan")
+    return BackwardPlan(buf=buf, n_slots=n, num_rows=total_rows, slots_per_id=1, slots_cover_grad=False)
+
+
 # --------------------------------------------------------- dot interaction ----
 def dot_interaction_fwd(feats: torch.Tensor) -> torch.Tensor:
     if feats.dim() != 3 or feats.dtype != torch.bfloat16:

@@ -28,6 +28,16 @@ Two exchange strategies (`exchange=`):
             owner: sort-based plan over the gathered ids (non-owned slots dropped, keys = local
                    rows) + segmented reduction + fused update of ITS rows (no gradient all-reduce)
 
+"peer" (CUDA only; NVLink / NVSwitch peer memory, no collective-library call and no host
+  synchronisation on the data path; fixed shapes, CUDA-graph capturable):
+
+  forward   ONE kernel: each lookup loads its row straight from the owner's shard over NVLink and
+            is pooled here in slot order -> bit-identical to the unsharded pooled bag
+  backward  bucket-by-owner whose scatter stores the entries into the owners' inboxes, push
+            all-gather of the pooled gradients, device-side barrier, owner: sort of its inbox +
+            segmented reduction + fused update of ITS rows; one more barrier before the next
+            forward reads the updated rows
+
 NVLink bytes per GPU per step (W = 8, b = 8192, P = 20, T tables, R = row bytes): ids in
 (W-1) b T P 8, partials in/out (W-1) b T R each way, grads in (W-1) b T R.
 """
@@ -42,6 +52,7 @@ import torch.nn as nn
 from . import _native as N
 from . import ops
 from .layers import pooled_counts
+from .peer import PeerGroup, arena_layout
 from .table import EmbeddingTable, FusedOptimizerConfig
 
 
@@ -224,6 +235,60 @@ class _RoutedPoolFn(torch.autograd.Function):
         return res, None, None, None
 
 
+class _PeerPoolFn(torch.autograd.Function):
+    """exchange="peer": rows pulled / entries and gradients pushed through peer-mapped memory."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, module):
+        pg = module.peer_group()
+        pg.raise_on_status()
+        _mark(module, "start")
+        if module._peer_dirty:
+            # rows updated since the last barrier (backward / optimizer.step / a weight load) must
+            # be complete on every rank before anybody reads them
+            ops.peer_barrier(pg)
+            module._peer_dirty = False
+        out = ops.peer_pool_fwd(
+            pg, ids, num_rows=module.num_embeddings, dim=module.emb_dim, dtype=module.emb.weight.dtype,
+            lengths=lengths, last_n=module.last_n,
+            pool_mode=N.POOL_MEAN if module.mode == "mean" else N.POOL_SUM, zero_pad=module.skip_pad,
+            pad_id=module.pad_id, **module._own_batching(ids))
+        _mark(module, "peer_pool")
+        scale = None
+        if module.mode == "mean":
+            scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad,
+                                        module.pad_id).clamp_(min=1).float()
+        ctx.module = module
+        ctx.save_for_backward(ids, lengths, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, lengths, scale = ctx.saved_tensors
+        module = ctx.module
+        pg = module.peer_group()
+        g = grad_out.contiguous()
+        if scale is not None:
+            g = g * scale.unsqueeze(1).to(g.dtype)
+        if g.dtype != module.emb.weight.dtype:
+            g = g.to(module.emb.weight.dtype)
+        _mark(module, "bwd_start")
+        ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths, last_n=module.last_n,
+                             zero_pad=module.skip_pad, pad_id=module.pad_id, **module._own_batching(ids))
+        _mark(module, "bucket_push")
+        ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
+        _mark(module, "grads_push")
+        ops.peer_barrier(pg)
+        _mark(module, "barrier")
+        plan = ops.peer_plan(pg, module.emb.weight.shape[0])
+        _mark(module, "plan")
+        res = module.emb.consume(plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype), slots_per_grad_row=1)
+        _mark(module, "apply")
+        pg.snapshot_status()
+        module._peer_dirty = True
+        return res, None, None, None
+
+
 class RowWiseShardedEmbeddingBag(nn.Module):
     """Pooled multi-hot lookup into a row-wise sharded table.
 
@@ -242,7 +307,7 @@ class RowWiseShardedEmbeddingBag(nn.Module):
                  local_pool: Optional[Callable] = None, local_backward: Optional[Callable] = None,
                  reduce_partials: Optional[Callable] = None, exchange: Optional[str] = None,
                  bucket: Optional[Callable] = None, pool_entries: Optional[Callable] = None,
-                 entries_backward: Optional[Callable] = None):
+                 entries_backward: Optional[Callable] = None, capacity_factor: Optional[float] = None):
         super().__init__()
         if mode not in ("sum", "mean"):
             raise ValueError("mode must be 'sum' or 'mean'")
@@ -262,8 +327,14 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         self.local_backward = local_backward or self._cuda_local_backward
         self.reduce_partials = reduce_partials or ops.sum_partials
         self.exchange = exchange or ("route" if comm.world > 1 else "gather")
-        if self.exchange not in ("route", "gather"):
-            raise ValueError("exchange must be 'route' or 'gather'")
+        if self.exchange not in ("route", "gather", "peer"):
+            raise ValueError("exchange must be 'route', 'gather' or 'peer'")
+        # peer exchange: inbox capacity per sender = capacity_factor * (my slots / W); hashed ids
+        # spread evenly (binomial), skewed in-range ids (identity hashing) need more head-room
+        self.capacity_factor = capacity_factor
+        self._peer: Optional[PeerGroup] = None
+        self._peer_key = None
+        self._peer_dirty = True
         self.bucket = bucket or self._cuda_bucket
         self.pool_entries = pool_entries or ops.pool_entries
         self.entries_backward = entries_backward or self._cuda_entries_backward
@@ -296,6 +367,54 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         wait()
         return self.emb.consume(plan, g_all, slots_per_grad_row=1)
 
+    def _own_batching(self, ids):
+        """this rank's bags are [T, b]: bag g belongs to table g // b."""
+        if self.num_tables == 1:
+            return dict(bags_per_table=0, num_tables=0)
+        return dict(bags_per_table=ids.shape[0] // self.num_tables, num_tables=self.num_tables)
+
+    # ----------------------------------------------------------- peer group ----
+    def peer_capacity(self, n_slots: int) -> int:
+        w = self.comm.world
+        f = self.capacity_factor if self.capacity_factor is not None else (1.0 if w == 1 else 1.5)
+        cap = min(n_slots, int(n_slots / w * f) + 64)
+        return max(2, cap + (cap & 1))
+
+    def peer_group(self) -> PeerGroup:
+        if self._peer is None:
+            raise N.NativeError("peer exchange: call forward first (the group is built for its batch shape)")
+        return self._peer
+
+    def _ensure_peer_group(self, ids: torch.Tensor) -> None:
+        """(Re)builds the peer group when the batch shape or the weight storage changed.
+        Collective over the module's process group: every rank must reach it together."""
+        w = self.emb.weight
+        key = (w.data_ptr(), tuple(ids.shape))
+        if self._peer is not None and self._peer_key == key:
+            return
+        self.close_peer()
+        cap = self.peer_capacity(ids.numel())
+        if self.comm.world == 1:
+            layout = arena_layout(1, cap, ids.shape[0], self.emb_dim, w.dtype)
+            arena = PeerGroup.new_arena(layout, w.device)
+            self._peer = PeerGroup.local(1, 0, [arena], [w.detach()], layout)
+        else:
+            self._peer = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group)
+        self._peer_key = key
+        self._peer_dirty = True
+
+    def close_peer(self) -> None:
+        """Collective: unmap the peers' memory (before this rank's shard / arena may be freed)."""
+        if self._peer is None:
+            return
+        torch.cuda.synchronize(self.emb.weight.device)
+        if self.comm.world > 1:
+            dist.barrier(group=self.comm.group)
+        self._peer.close()
+        if self.comm.world > 1:
+            dist.barrier(group=self.comm.group)
+        self._peer, self._peer_key = None, None
+
     def _batching(self, ids_all):
         """gathered bags are [W, T, b]: bag g belongs to table (g // b) % T."""
         if self.num_tables == 1:
@@ -307,13 +426,18 @@ class RowWiseShardedEmbeddingBag(nn.Module):
     def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         if ids.dtype != torch.int64 or ids.dim() != (2 if self.num_tables == 1 else 3):
             raise N.NativeError("ids must be int64 [batch, bag_size] ([num_tables, batch, bag_size] when batched)")
-        fn = _RoutedPoolFn if self.exchange == "route" else _ShardedPoolFn
+        fn = {"route": _RoutedPoolFn, "gather": _ShardedPoolFn, "peer": _PeerPoolFn}[self.exchange]
         if self.num_tables == 1:
+            if self.exchange == "peer":
+                self._ensure_peer_group(ids)
             return fn.apply(self.emb.grad_anchor(), ids.contiguous(), lengths, self)
         t, b, p = ids.shape
         if t != self.num_tables:
             raise N.NativeError(f"expected ids for {self.num_tables} tables, got {t}")
-        out = fn.apply(self.emb.grad_anchor(), ids.contiguous().view(t * b, p),
+        flat = ids.contiguous().view(t * b, p)
+        if self.exchange == "peer":
+            self._ensure_peer_group(flat)
+        out = fn.apply(self.emb.grad_anchor(), flat,
                        None if lengths is None else lengths.contiguous().view(t * b), self)
         return out.view(t, b, -1)
 
@@ -323,6 +447,7 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         full = full.view(self.num_tables, self.num_embeddings, self.emb_dim)
         shard = full[:, self.comm.rank::self.comm.world].reshape(-1, self.emb_dim)
         self.emb.weight.copy_(shard.to(self.emb.weight.device, self.emb.weight.dtype))
+        self._peer_dirty = True
 
     @torch.no_grad()
     def gather_full_weight(self) -> torch.Tensor:

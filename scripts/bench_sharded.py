@@ -35,13 +35,13 @@ def ids_for(rank, t_tables, b, p, seed=5000):
     return torch.randint(-2 ** 63, 2 ** 63 - 1, (t_tables, b, p), generator=g, dtype=torch.int64)
 
 
-def check(world, rank, dev):
+def check(world, rank, dev, exchange=None):
     """sharded == unsharded at N = 100003 rows x 4 tables, fp32, both directions."""
     from oracle import embedding_oracle as O
     n_rows, dim, t, b, p = 100003, 64, 4, 257, 20
     torch.manual_seed(99)
     full = torch.randn(t, n_rows, dim)
-    mod = RowWiseShardedEmbeddingBag(n_rows, dim, num_tables=t, device=dev)
+    mod = RowWiseShardedEmbeddingBag(n_rows, dim, num_tables=t, device=dev, exchange=exchange)
     mod.load_full_weight(full)
     ids = ids_for(rank, t, b, p, seed=7000)
     lengths = torch.randint(0, p + 1, (t, b), generator=torch.Generator().manual_seed(rank))
@@ -49,6 +49,8 @@ def check(world, rank, dev):
     out = mod(ids.to(dev), lengths.to(dev))
     for ti in range(t):
         want = O.pooled_bag(full[ti], ids[ti], lengths=lengths[ti])
+        if mod.exchange == "peer":   # rows pulled from their owners, pooled here in slot order
+            assert torch.equal(out[ti].cpu(), want), "peer forward is not bit-identical to the unsharded bag"
         torch.testing.assert_close(out[ti].cpu(), want, rtol=1e-5, atol=1e-5)
     out.backward(go.to(dev))
     # unsharded reference gradient over the GLOBAL batch
@@ -64,11 +66,19 @@ def check(world, rank, dev):
     mine = gw[:, rank::world].reshape(-1, dim)
     torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(mod.gather_full_weight().cpu(), full)
+    if mod.exchange == "peer":
+        # second step on the same group (barrier bookkeeping, inbox reuse), then the status word
+        mod.emb.weight.grad = None
+        out2 = mod(ids.to(dev), lengths.to(dev))
+        assert torch.equal(out2, out)
+        out2.backward(go.to(dev))
+        torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
+        mod.peer_group().raise_on_status(synchronize=True)
     if rank == 0:
-        print(f"[check] sharded == unsharded on {world} rank(s): ok", flush=True)
+        print(f"[check] sharded == unsharded on {world} rank(s), exchange={mod.exchange}: ok", flush=True)
 
 
-def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=None):
+def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=None, graph=False):
     """Times the cfg 5 step on an already initialised process group; returns the result dict
     (every rank computes it, rank 0 prints it)."""
     class A:
@@ -95,6 +105,21 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     for _ in range(args.warmup):
         step()
     barrier()
+    launches_per_step = None
+    if graph:
+        # the peer step has fixed shapes and no host synchronisation: capture fwd + bwd + update once
+        if mod.exchange != "peer":
+            raise SystemExit("--graph needs --exchange peer (the NCCL exchanges synchronise with the host)")
+        l0 = N.launch_count()
+        g = torch.cuda.CUDAGraph()
+        # thread_local: the NCCL watchdog thread may query events while this thread captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            step()
+        launches_per_step = N.launch_count() - l0
+        eager_step, step = step, g.replay
+        for _ in range(2):
+            step()
+        barrier()
     launches0 = N.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -110,9 +135,17 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     lookups = world * T * B_LOCAL * P
     row_bytes = DIM * 2
     nv_in = (world - 1) * T * B_LOCAL * (P * 8 + 2 * row_bytes)   # ids + partials (fwd) + grads (bwd), per GPU
+    if mod.exchange == "peer":
+        # rows pulled from remote owners (fwd) + entries pushed into my inbox + gathered gradients (bwd)
+        remote = (world - 1) / world
+        nv_in = int(remote * T * B_LOCAL * P * (row_bytes + 8) + (world - 1) * T * B_LOCAL * row_bytes)
     t_step = ms / args.steps * 1e-3
     mod_exchange = mod.exchange
     phases = None
+    if graph:
+        step = eager_step
+    if mod.exchange == "peer":
+        mod.peer_group().raise_on_status(synchronize=True)
     if os.environ.get("RECEMB_PHASES"):
         mod.phase_events = []
         for _ in range(5):
@@ -126,7 +159,10 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             acc.setdefault(n1, []).append(e0_.elapsed_time(e1_))
         phases = {k: round(sum(v) / len(v), 4) for k, v in acc.items()}
         mod.phase_events = None
+    mod.close_peer()
     del mod, grad, ids
+    if graph:
+        del g, step, eager_step
     torch.cuda.empty_cache()
     return {
             "metric": "embedding_lookups_per_sec_fwd_bwd", "value": lookups / t_step, "unit": "lookups/s",
@@ -137,7 +173,8 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
-            "gpu_launches": N.launch_count() - launches0, "phases_ms": phases}
+            "gpu_launches": (launches_per_step * args.steps if graph else N.launch_count() - launches0),
+            "cuda_graph": bool(graph), "phases_ms": phases}
 
 
 def main():
@@ -146,7 +183,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--exchange", default=None, choices=["route", "gather"])
+    ap.add_argument("--exchange", default=None, choices=["route", "gather", "peer"])
+    ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (peer exchange only)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -156,8 +194,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.check:
-        check(world, rank, dev)
-    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange)
+        check(world, rank, dev, args.exchange)
+    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange, args.graph)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:

@@ -1,0 +1,216 @@
+"""Peer exchange of the row-wise sharded pooled lookup, W ranks emulated on ONE GPU: every "peer"
+pointer is another allocation on the same device (the kernels cannot tell; only the cross-rank
+barrier is left out because the virtual ranks run one after the other).  Forward must be
+bit-identical to the unsharded pooled bag, the inboxes bit-identical to the routed buckets, the
+owner-side update equal to the unsharded update."""
+import pytest
+import torch
+
+from recommendations_b200 import _native as N
+from recommendations_b200 import ops
+from recommendations_b200.peer import PeerGroup, arena_layout
+from oracle import embedding_oracle as O
+from conftest import seeded_ids
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_groups(world, full, cap, bags_total, dtype):
+    """full [T, N, D] -> per-rank stacked shards, arenas and PeerGroups on one device."""
+    t, n_rows, dim = full.shape
+    shards = [full[:, r::world].reshape(-1, dim).contiguous().to(dtype).to(DEV) for r in range(world)]
+    layout = arena_layout(world, cap, bags_total, dim, dtype)
+    arenas = [PeerGroup.new_arena(layout, DEV) for _ in range(world)]
+    return shards, arenas, [PeerGroup.local(world, r, arenas, shards, layout) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,tables", [(1, 1), (2, 1), (3, 2), (8, 1), (8, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_peer_pool_is_bit_identical_to_unsharded(world, tables, dtype):
+    n_rows, dim, b, p = 100003, 128, 1001, 20
+    m = tables * b
+    torch.manual_seed(world)
+    full = torch.randn(tables, n_rows, dim).to(dtype)
+    shards, _, groups = make_groups(world, full.float(), 64, m, dtype)
+    stacked = full.reshape(-1, dim).contiguous().to(DEV)
+    batching = dict(bags_per_table=b if tables > 1 else 0, num_tables=tables if tables > 1 else 0)
+    for r in range(world):
+        ids = seeded_ids(m * p, 90 + r, (m, p)).to(DEV)
+        lengths = torch.randint(0, p + 1, (m,), generator=torch.Generator().manual_seed(r)).to(DEV)
+        for mode in (N.POOL_SUM, N.POOL_MEAN):
+            got = ops.peer_pool_fwd(groups[r], ids, num_rows=n_rows, dim=dim, dtype=dtype, lengths=lengths,
+                                    pool_mode=mode, **batching)
+            want = ops.pool_fwd(stacked, ids, lengths=lengths, num_rows=n_rows, pool_mode=mode, **batching)
+            assert torch.equal(got, want)
+        # last-N window + pad skipping follow the same code path
+        got = ops.peer_pool_fwd(groups[r], ids, num_rows=n_rows, dim=dim, dtype=dtype, lengths=lengths, last_n=5,
+                                zero_pad=True, pad_id=int(ids[0, 0]), **batching)
+        want = ops.pool_fwd(stacked, ids, lengths=lengths, num_rows=n_rows, last_n=5, zero_pad=True,
+                            pad_id=int(ids[0, 0]), **batching)
+        assert torch.equal(got, want)
+    # against the CPU oracle too (one rank, table 0)
+    ids = seeded_ids(b * p, 90, (b, p))
+    if tables == 1:
+        lengths = torch.randint(0, p + 1, (b,), generator=torch.Generator().manual_seed(0))
+        got = ops.peer_pool_fwd(groups[0], ids.to(DEV), num_rows=n_rows, dim=dim, dtype=dtype,
+                                lengths=lengths.to(DEV))
+        want = O.pooled_bag(full[0], ids, lengths=lengths)
+        if dtype == torch.float32:
+            assert torch.equal(got.cpu(), want)
+        else:
+            torch.testing.assert_close(got.float().cpu(), want.float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("world,tables", [(1, 1), (2, 1), (8, 1), (4, 3)])
+def test_peer_backward_exchange(world, tables):
+    """bucket_push / allgather_push of every virtual sender, then every owner's plan + update."""
+    n_rows, dim, b, p = 30011, 64, 301, 20
+    m = tables * b
+    torch.manual_seed(world + 10)
+    full = torch.randn(tables, n_rows, dim)
+    cap = m * p  # worst case: no overflow
+    shards, arenas, groups = make_groups(world, full, cap, m, torch.float32)
+    batching = dict(bags_per_table=b if tables > 1 else 0, num_tables=tables if tables > 1 else 0)
+    senders = []
+    for r in range(world):
+        ids = seeded_ids(m * p, 80 + r, (m, p))
+        lengths = torch.randint(0, p + 1, (m,), generator=torch.Generator().manual_seed(r))
+        go = torch.randn(m, dim, generator=torch.Generator().manual_seed(100 + r))
+        ops.peer_bucket_push(groups[r], ids.to(DEV), num_rows=n_rows, lengths=lengths.to(DEV), **batching)
+        ops.peer_allgather_push(groups[r], go.to(DEV), int(groups[r].layout.off_grads))
+        # the routed bucketing is the (already oracle-checked) reference for the inbox contents
+        ent, cnt = ops.shard_bucket(ids.to(DEV), num_rows=n_rows, world=world, rank=r, bags_total=m,
+                                    lengths=lengths.to(DEV), **batching)
+        senders.append((ids, lengths, go, ent.cpu(), cnt.cpu()))
+    torch.cuda.synchronize()
+    hp = ops.make_optim_params(lr=0.5, eps=1e-10)
+    # unsharded reference: dense gradient of the global batch per table
+    gw = torch.zeros(tables, n_rows, dim)
+    for (ids, lengths, go, _, _) in senders:
+        rows = O.row_index(ids, n_rows, 0)
+        use = torch.arange(p).unsqueeze(0) < lengths.unsqueeze(1)
+        tt = (torch.arange(m) // b).unsqueeze(1).expand(m, p)
+        flat = (tt * n_rows + rows)[use]
+        gw.view(-1, dim).index_add_(0, flat, go.unsqueeze(1).expand(-1, p, -1)[use])
+    for o in range(world):
+        g = groups[o]
+        counts = g.counts_view().cpu()
+        inbox = g.inbox_view().cpu()
+        for r, (_, _, _, ent, cnt) in enumerate(senders):
+            assert int(counts[r]) == int(cnt[o])
+            lo = int(cnt[:o].sum())
+            assert torch.equal(inbox[r, :int(cnt[o])], ent[lo:lo + int(cnt[o])])  # bit-exact, stable
+        # gathered gradients: slice r = sender r's rows
+        gv = g.grads_view(dim, torch.float32).cpu()
+        for r, (_, _, go, _, _) in enumerate(senders):
+            assert torch.equal(gv[r * m:(r + 1) * m], go)
+        assert int(g.status_word().cpu()[0]) == 0
+        # plan: valid pairs sorted by row (stable), sentinel keys last
+        total_rows = shards[o].shape[0]
+        plan = ops.peer_plan(g, total_rows)
+        recv = torch.cat([inbox[r, :int(counts[r])] for r in range(world)])
+        keys = recv >> 32
+        order = torch.argsort(keys, stable=True)
+        n_valid = recv.numel()
+        assert torch.equal(plan.sorted_rows.cpu()[:n_valid], keys[order])
+        assert torch.equal(plan.sorted_slots.cpu()[:n_valid], (recv & 0xFFFFFFFF)[order])
+        assert bool((plan.sorted_rows.cpu()[n_valid:] == total_rows).all())
+        # dense gradient of this owner's rows == the unsharded gradient restricted to them
+        dense = torch.zeros_like(shards[o])
+        ops.bwd_apply(plan, g.grads_view(dim, torch.float32), table=dense, update=N.UPD_DENSE_GRAD,
+                      slots_per_grad_row=1)
+        want = gw[:, o::world].reshape(-1, dim)
+        torch.testing.assert_close(dense.cpu(), want, rtol=1e-5, atol=1e-5)
+        # fused row-wise Adagrad on the shard == on the unsharded table
+        st = torch.zeros(total_rows, device=DEV)
+        w_o = shards[o].clone()
+        ops.bwd_apply(plan, g.grads_view(dim, torch.float32), table=w_o, update=N.UPD_ROWWISE_ADAGRAD, state1=st,
+                      slots_per_grad_row=1, hp=hp)
+        gsq = (want * want).mean(dim=1)
+        touched = gsq > 0
+        w_want = shards[o].cpu().clone()
+        w_want[touched] -= 0.5 * want[touched] / (gsq[touched].sqrt().unsqueeze(1) + 1e-10)
+        torch.testing.assert_close(w_o.cpu(), w_want, rtol=1e-4, atol=1e-5)
+
+
+def test_peer_inbox_overflow_sets_status():
+    world, n_rows, dim, m, p = 4, 1009, 32, 64, 20
+    full = torch.randn(1, n_rows, dim)
+    shards, arenas, groups = make_groups(world, full, 16, m, torch.float32)   # far too small
+    ids = seeded_ids(m * p, 5, (m, p)).to(DEV)
+    ops.peer_bucket_push(groups[1], ids, num_rows=n_rows)
+    torch.cuda.synchronize()
+    assert int(groups[1].status_word().cpu()[0]) & 1
+    for o in range(world):
+        assert int(groups[o].counts_view().cpu()[1]) == 16   # clamped to the capacity
+    groups[1].snapshot_status()
+    torch.cuda.synchronize()
+    with pytest.raises(N.NativeError, match="overflow"):
+        groups[1].raise_on_status()
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+@pytest.mark.parametrize("tables", [1, 3])
+def test_peer_module_single_rank_matches_other_exchanges(mode, tables):
+    """exchange="peer" with W = 1 (own memory as the only peer) through the nn.Module + autograd."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    n_rows, dim, b, p = 9973, 64, 257, 20
+    shape = (b, p) if tables == 1 else (tables, b, p)
+    ids = seeded_ids(tables * b * p, 73, shape).to(DEV)
+    lengths = torch.randint(0, p + 1, shape[:-1], generator=torch.Generator().manual_seed(5)).to(DEV)
+    a = RowWiseShardedEmbeddingBag(n_rows, dim, mode=mode, exchange="peer", num_tables=tables, device=DEV)
+    c = RowWiseShardedEmbeddingBag(n_rows, dim, mode=mode, exchange="gather", num_tables=tables, device=DEV)
+    c.load_state_dict(a.state_dict())
+    go = torch.randn(*shape[:-1], dim, device=DEV)
+    oa, oc = a(ids, lengths), c(ids, lengths)
+    torch.testing.assert_close(oa, oc, rtol=1e-6, atol=1e-6)
+    oa.backward(go)
+    oc.backward(go)
+    torch.testing.assert_close(a.emb.weight.grad, c.emb.weight.grad, rtol=1e-5, atol=1e-6)
+    # second step reuses the group (same shapes) and the barrier bookkeeping
+    a.emb.weight.grad = None
+    oa2 = a(ids, lengths)
+    assert torch.equal(oa2, oa)
+    oa2.backward(go)
+    torch.testing.assert_close(a.emb.weight.grad, c.emb.weight.grad, rtol=1e-5, atol=1e-6)
+    a.peer_group().raise_on_status(synchronize=True)
+
+
+def test_peer_module_fused_step_in_cuda_graph():
+    """The peer step has fixed shapes and no host synchronisation: forward + backward + fused
+    row-wise Adagrad replay from one CUDA graph and match the eager steps."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    import recommendations_b200 as R
+    n_rows, dim, b, p, tables = 50021, 128, 512, 20, 2
+    ids = seeded_ids(tables * b * p, 11, (tables, b, p)).to(DEV)
+    go = torch.randn(tables, b, dim, device=DEV, dtype=torch.bfloat16)
+    cfg = dict(kind="rowwise_adagrad", lr=0.05)
+    eager = RowWiseShardedEmbeddingBag(n_rows, dim, exchange="peer", num_tables=tables, dtype=torch.bfloat16,
+                                       device=DEV, fused_optimizer=R.FusedOptimizerConfig(**cfg))
+    graphed = RowWiseShardedEmbeddingBag(n_rows, dim, exchange="peer", num_tables=tables, dtype=torch.bfloat16,
+                                         device=DEV, fused_optimizer=R.FusedOptimizerConfig(**cfg))
+    graphed.load_state_dict(eager.state_dict())
+
+    def step(mod):
+        out = mod(ids)
+        out.backward(go)
+        return out
+
+    # warm-up on a side stream (allocations, peer group), then capture one step
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(graphed)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_static = step(graphed)   # captured, not executed
+    for _ in range(3):
+        graph.replay()               # graphed: warm-up + 3 replays = 4 steps
+    for _ in range(4):
+        out_eager = step(eager)      # out_* = the forward of step 4
+    torch.cuda.synchronize()
+    assert torch.equal(out_static, out_eager)
+    assert torch.equal(graphed.emb.weight, eager.emb.weight)
+    graphed.peer_group().raise_on_status(synchronize=True)
