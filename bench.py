@@ -269,7 +269,7 @@ def run_b200(args):
     e2e = run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier)
 
     # ---- N > 1: also time the path that really exchanges data over NVLink (cfg 5: row-wise
-    # sharded large-vocab tables, id all-gather + partial-sum all-to-all), same process group
+    # sharded large-vocab tables), same process group
     sharded = None
     if world > 1 and not args.no_sharded:
         del table_all, state_all, grads, outs, plan_buf, ws_buf
@@ -277,7 +277,10 @@ def run_b200(args):
         try:
             sys.path.insert(0, str(ROOT / "scripts"))
             import bench_sharded
-            sharded = bench_sharded.run_cfg5(world, rank, dev, args.steps, args.warmup)
+            # peer exchange: rows pulled / entries and gradients pushed through NVLink peer memory
+            # inside the lookup kernels, whole step replayed from one CUDA graph
+            sharded = bench_sharded.run_cfg5(world, rank, dev, args.steps, args.warmup, exchange="peer",
+                                             graph=True)
         except Exception as exc:  # the headline line must survive a failure of the extra run
             sharded = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -303,8 +303,8 @@ typedef struct recemb_peer_group {
 /* Byte offsets inside one rank's exchange arena (identical on every rank). */
 typedef struct recemb_peer_arena {
   int64_t bytes;       /* total size; the caller allocates it zero-filled, 256-byte aligned */
-  int64_t off_flags;   /* uint64 [world]   barrier flags, slot s is written by rank s */
-  int64_t off_epoch;   /* uint64           this rank's barrier count */
+  int64_t off_flags;   /* uint64 [channels][RECEMB_MAX_PEERS]  barrier flags, slot s is written by rank s */
+  int64_t off_epoch;   /* uint64 [channels] this rank's barrier counts */
   int64_t off_status;  /* uint32           sticky bits: 1 = inbox overflow (entries dropped), 2 = barrier timeout */
   int64_t off_counts;  /* int64 [world]    entries rank s pushed into my inbox this step */
   int64_t off_inbox;   /* int64 [world][cap] entries, region s written by rank s */
@@ -325,11 +325,14 @@ RECEMB_API int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
                              recemb_peer_arena* out);
 
 /* Device-side barrier over all ranks of the group (one tiny kernel on `stream`): everything the
- * ranks enqueued before it -- including their stores into peer memory -- is visible to
- * everything enqueued after it on any rank.  Every rank must call it the same number of times.
+ * ranks enqueued before it on that stream -- including their stores into peer memory -- is
+ * visible to everything enqueued after it on any rank.  `channel` (0 .. RECEMB_PEER_CHANNELS-1)
+ * selects an independent set of flags, so that two streams of a rank can each run their own
+ * barrier sequence concurrently; every rank must call a channel the same number of times.
  * A rank that waits longer than ~2 s sets status bit 2 and continues (no GPU hang). */
-RECEMB_API int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int device,
-                        recemb_stream_t stream);
+#define RECEMB_PEER_CHANNELS 2
+RECEMB_API int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                        int device, recemb_stream_t stream);
 
 /* Forward.  As recemb_pool_fwd on the unsharded table of num_rows (GLOBAL) rows per table, except
  * that global row r is read from group->table[r % world] at local row r / world (+ the table

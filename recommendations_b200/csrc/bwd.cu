@@ -231,6 +231,8 @@ struct SegArgs {
   float* out_partials;    // [2 * chunks, dim]
   const uint32_t* flag_in;  // level >= 1: non-zero iff the previous level emitted a record
   uint32_t* flag_out;
+  int32_t chunk;          // consecutive entries per group (level 0: wave-fitted, >= kChunk0)
+  int32_t pf_bulk;        // level 0 fast path: rows prefetched with one bulk L2 prefetch per row
 };
 
 template <int G>
@@ -257,6 +259,12 @@ __device__ __forceinline__ float fast_rcp(float x) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// whole row (16-byte aligned, multiple of 16 bytes) into L2 through the TMA engine: one
+// instruction per row instead of one per lane, and it translates like a real access (a
+// per-lane prefetch.global.L2 that misses the TLB may be dropped: tables of tens of GB)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // UPD >= 0: the update kind is a compile-time constant (dead variants disappear);
@@ -383,10 +391,11 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
   const int gi_warp = lane / G;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi_warp * G));
   const int chunk = blockIdx.x * GROUPS + threadIdx.x / G;
-  const int num_chunks = (a.n + CH - 1) / CH;
+  const int CHR = L0 ? a.chunk : CH;  // level 0: run-time chunk (wave-fitted by the host)
+  const int num_chunks = (a.n + CHR - 1) / CHR;
   if (chunk >= num_chunks) return;
-  const int start = chunk * CH;
-  const int end = min(start + CH, a.n);
+  const int start = chunk * CHR;
+  const int end = min(start + CHR, a.n);
 
   if (lig == 0) {
     if (chunk > 0) a.out_keys[2 * chunk - 1] = kNoKey;
@@ -423,6 +432,26 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
     if (e0 >= end) return;
     uint32_t kk[B + 1], ss[B];
     load_meta(e0, kk, ss);
+    if constexpr (L0 && EXACT) {
+      if (a.pf_bulk) {
+        if (lig == 0) {
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            if (kk[u] < a.sentinel) {
+              prefetch_l2_bulk(gbase + (size_t)grad_row_of(e0 + u, ss[u]) * a.dim, a.dim * (uint32_t)sizeof(GT));
+              if (pf_w && kk[u + 1] != kk[u]) {
+                const size_t off = (size_t)kk[u] * a.dim;
+                prefetch_l2_bulk(tbase + off, a.dim * (uint32_t)sizeof(WT));
+                if (pf_s1) prefetch_l2_bulk(a.state1 + off, a.dim * 4u);
+                if (pf_s2) prefetch_l2_bulk(a.state2 + off, a.dim * 4u);
+                if (upd == RECEMB_UPD_ROWWISE_ADAGRAD) prefetch_l2(a.state1 + kk[u]);
+              }
+            }
+          }
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       if (kk[u] < a.sentinel) {
@@ -560,12 +589,45 @@ static bool pick_quads(int quads, QuadShape* s) {
 constexpr int kChunk0 = RECEMB_CHUNK0;  // sorted entries per group at level 0
 constexpr int kChunkN = 32;             // records per group at levels >= 1
 
+// chunk size the last level-0 launch of this thread used (the host sizes level 1 from it)
+static thread_local int t_chunk_used = 0;
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int G, int V, int E, typename GT, typename WT, bool L0, typename Cfg>
-static void launch_one(const SegArgs& a, cudaStream_t s) {
+static void launch_one(const SegArgs& a_in, cudaStream_t s) {
   constexpr int CH = L0 ? kChunk0 : kChunkN;
-  const int chunks = (a.n + CH - 1) / CH;
-  const int groups = kBwdThreads / G;
-  seg_kernel<G, V, E, GT, WT, L0, CH, Cfg><<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
+  constexpr int groups = kBwdThreads / G;
+  auto kernel = seg_kernel<G, V, E, GT, WT, L0, CH, Cfg>;
+  SegArgs a = a_in;
+  a.chunk = CH;
+  if constexpr (L0) {
+    // Wave fit: every group does the same amount of work, so a grid of 2.2 waves takes as long
+    // as 3.  Stretch the chunk (never below kChunk0: the workspace is sized for that) until the
+    // chunks fill a whole number of waves of resident groups.
+    static int occ = 0;  // per instantiation
+    static const int fit = env_flag("RECEMB_SEG_FIT", 1);
+    if (occ == 0) {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBwdThreads, 0) != cudaSuccess || v < 1) v = 1;
+      occ = v;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t resident = (int64_t)occ * sm_count(dev) * groups;
+    const int64_t chunks64 = ((int64_t)a.n + CH - 1) / CH;
+    if (fit && chunks64 > resident) {
+      const int64_t waves = chunks64 / resident;
+      int64_t c = ((int64_t)a.n + waves * resident - 1) / (waves * resident);
+      c += c & 1;
+      if (c > CH && c <= 2 * CH) a.chunk = (int32_t)c;
+    }
+    t_chunk_used = a.chunk;
+  }
+  const int chunks = (a.n + a.chunk - 1) / a.chunk;
+  kernel<<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
 }
 
 // generic instantiations: any shape / update / scale combination
@@ -888,7 +950,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
   cudaStream_t s = (cudaStream_t)stream;
 
   int64_t sizes[kMaxLevels];
-  const int L = level_sizes(n, sizes, kMaxLevels);
+  int L = level_sizes(n, sizes, kMaxLevels);
   RECEMB_CUDA(cudaMemsetAsync(workspace, 0, 256, s));  // per-level "records emitted" flags
   const char* pbase = (const char*)plan;
   char* w = (char*)workspace;
@@ -908,6 +970,11 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
   a.state2 = (float*)state2;
   if (hp_host) a.hp = *hp_host;
   else a.hp = recemb_optim_params{};
+  a.chunk = kChunk0;
+  {
+    static const int pf = env_flag("RECEMB_SEG_PF_BULK", 0);
+    a.pf_bulk = pf;
+  }
 
   const uint32_t* in_keys = (const uint32_t*)(pbase + kCounterBytes + 2 * arr);
   const uint32_t* in_slots = (const uint32_t*)(pbase + kCounterBytes + 3 * arr);
@@ -942,6 +1009,18 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
     if (l == 0 && t_ev_stop) cudaEventRecord(t_ev_stop, s);
     if (l == 0) t_ev_start = t_ev_stop = nullptr;
     if (rc) return rc;
+    if (l == 0 && t_chunk_used > kChunk0) {
+      // level 0 used longer chunks: fewer records than the (upper-bound) layout reserves;
+      // the levels above shrink accordingly (offsets stay inside the reserved areas)
+      sizes[1] = 2 * ((n + t_chunk_used - 1) / t_chunk_used);
+      int64_t m = sizes[1];
+      int LL = 2;
+      while (m > kChunkN && LL < kMaxLevels) {
+        m = 2 * ((m + kChunkN - 1) / kChunkN);
+        sizes[LL++] = m;
+      }
+      if (L > 1) L = LL;
+    }
     in_keys = out_keys;
     in_slots = nullptr;
     in_grad = out_part;

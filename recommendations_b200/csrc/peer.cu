@@ -168,7 +168,7 @@ extern "C" int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
   RECEMB_UNSUPPORTED((int64_t)world * cap < 0x7fffffffll, "inbox too large for 32-bit slots");
   int64_t off = 0;
   out->off_flags = off;
-  off += 256;  // RECEMB_MAX_PEERS x 8 bytes, padded
+  off += align_up((size_t)RECEMB_PEER_CHANNELS * RECEMB_MAX_PEERS * 8, 256);
   out->off_epoch = off;
   off += 128;
   out->off_status = off;
@@ -185,16 +185,18 @@ extern "C" int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
   return RECEMB_OK;
 }
 
-extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int device,
-                                   recemb_stream_t stream) {
+extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                                   int device, recemb_stream_t stream) {
   RECEMB_CHECK_ARG(arena, "null arena");
+  RECEMB_CHECK_ARG(channel >= 0 && channel < RECEMB_PEER_CHANNELS, "barrier channel %d out of range", channel);
   PeerPtrs p;
   int rc = make_ptrs(group, &p);
   if (rc) return rc;
   if (p.world == 1) return RECEMB_OK;
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, arena->off_flags, arena->off_epoch, arena->off_status);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, arena->off_flags + (int64_t)channel * RECEMB_MAX_PEERS * 8,
+                                                         arena->off_epoch + (int64_t)channel * 8, arena->off_status);
   RECEMB_LAUNCHED();
   return RECEMB_OK;
 }

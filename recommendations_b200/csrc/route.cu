@@ -20,7 +20,7 @@
 namespace recemb {
 
 constexpr int kRtThreads = 256;
-constexpr int kRtItems = 16;                        // slots per thread
+constexpr int kRtItems = 4;                         // slots per thread
 constexpr int kRtBlock = kRtThreads * kRtItems;     // slots per CTA
 constexpr int kMaxWorld = 32;
 

@@ -337,8 +337,9 @@ def peer_allgather_push(group, src: torch.Tensor, dst_offset: int) -> None:
                                                 dst_offset, dev, N.stream_ptr(dev)), "recemb_peer_allgather_push")
 
 
-def peer_barrier(group) -> None:
-    N.check(N.load().recemb_peer_barrier(C.byref(group.struct), C.byref(group.layout), group.device,
+def peer_barrier(group, channel: int = 0) -> None:
+    """Device-side barrier on the current stream; `channel` = independent flag set (one per stream)."""
+    N.check(N.load().recemb_peer_barrier(C.byref(group.struct), C.byref(group.layout), channel, group.device,
                                          N.stream_ptr(group.device)), "recemb_peer_barrier")
 
 

@@ -273,15 +273,23 @@ class _PeerPoolFn(torch.autograd.Function):
         if g.dtype != module.emb.weight.dtype:
             g = g.to(module.emb.weight.dtype)
         _mark(module, "bwd_start")
+        # the gradients travel on a side stream with their own barrier channel, under the
+        # bucketing / entry push / sort of the main stream: NVLink and the SMs work in parallel
+        main = torch.cuda.current_stream(g.device)
+        side = module._side_stream(g.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
+            ops.peer_barrier(pg, channel=1)
+        g.record_stream(side)
         ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths, last_n=module.last_n,
                              zero_pad=module.skip_pad, pad_id=module.pad_id, **module._own_batching(ids))
         _mark(module, "bucket_push")
-        ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
-        _mark(module, "grads_push")
-        ops.peer_barrier(pg)
+        ops.peer_barrier(pg, channel=0)
         _mark(module, "barrier")
         plan = ops.peer_plan(pg, module.emb.weight.shape[0])
         _mark(module, "plan")
+        main.wait_stream(side)
         res = module.emb.consume(plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype), slots_per_grad_row=1)
         _mark(module, "apply")
         pg.snapshot_status()
@@ -402,6 +410,11 @@ class RowWiseShardedEmbeddingBag(nn.Module):
             self._peer = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group)
         self._peer_key = key
         self._peer_dirty = True
+
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
 
     def close_peer(self) -> None:
         """Collective: unmap the peers' memory (before this rank's shard / arena may be freed)."""

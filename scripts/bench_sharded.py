@@ -177,6 +177,56 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             "cuda_graph": bool(graph), "phases_ms": phases}
 
 
+def phase_bench(world, rank, dev, rows_per_gpu=25_000_000, reps=10):
+    """Peer exchange, one phase at a time (all ranks run the same phase together, `reps` launches
+    back to back between two events): where the step time goes at this W."""
+    from recommendations_b200 import ops
+    n_rows = rows_per_gpu * world
+    mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange="peer",
+                                     fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
+    ids = ids_for(rank, T, B_LOCAL, P).to(dev)
+    grad = torch.randn(T, B_LOCAL, DIM, device=dev, dtype=torch.bfloat16)
+    out = mod(ids)
+    out.backward(grad)          # builds the group, fills inbox / gradient buffer once
+    pg = mod.peer_group()
+    flat = ids.view(T * B_LOCAL, P)
+    batching = dict(bags_per_table=B_LOCAL, num_tables=T)
+    total_rows = mod.emb.weight.shape[0]
+    res = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = round(float(t.item()), 4)
+
+    timed("pull_pool_fwd", lambda: ops.peer_pool_fwd(pg, flat, num_rows=n_rows, dim=DIM, dtype=torch.bfloat16,
+                                                     **batching))
+    timed("bucket_push", lambda: ops.peer_bucket_push(pg, flat, num_rows=n_rows, **batching))
+    timed("grads_push", lambda: ops.peer_allgather_push(pg, grad, int(pg.layout.off_grads)))
+    timed("barrier", lambda: ops.peer_barrier(pg, 0))
+    plan = ops.peer_plan(pg, total_rows)
+    timed("plan(unpack+sort)", lambda: ops.peer_plan(pg, total_rows))
+    gv = pg.grads_view(DIM, torch.bfloat16)
+    timed("apply(seg+adagrad)", lambda: mod.emb.consume(plan, gv, slots_per_grad_row=1))
+    pg.raise_on_status(synchronize=True)
+    mod.close_peer()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
@@ -184,6 +234,7 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=25_000_000)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default=None, choices=["route", "gather", "peer"])
+    ap.add_argument("--phase-bench", action="store_true", help="time the phases of the peer exchange one by one")
     ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (peer exchange only)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,7 +246,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.check:
         check(world, rank, dev, args.exchange)
-    res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange, args.graph)
+    if args.phase_bench:
+        res = {"phase_ms": phase_bench(world, rank, dev, args.rows_per_gpu), "n_gpus": world}
+    else:
+        res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange, args.graph)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
