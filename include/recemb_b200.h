@@ -117,7 +117,10 @@ typedef struct recemb_optim_params {
   float beta2;
   float bias_correction1; /* 1 - beta1^step (host-computed) */
   float bias_correction2; /* 1 - beta2^step */
-  float reserved;
+  float grad_div;         /* > 0: every gradient element is divided by it (IEEE division) before the
+                             reduction -- the backward of KShiftEmbedding's x / sqrt(num_shifts)
+                             (commons/layers.py:170) folded into the segmented reduction instead of
+                             a separate pass that materialises dx; 0 = off */
 } recemb_optim_params;
 
 /* ---- library info -------------------------------------------------------- */
@@ -211,7 +214,8 @@ RECEMB_API int recemb_plan_views(const void* plan, size_t plan_bytes, const uint
 /* n_slots = number of (row, slot) entries in the plan.
  * For every distinct row r in the plan: g = sum over its slots s (ascending) of
  *     slot_weight[s] * grad_row_scale[s / slots_per_grad_row] * grad[s / slots_per_grad_row, :]
- * (both scale arrays optional, fp32) accumulated in fp32, then `update` is
+ * (both scale arrays optional, fp32; without them and with hp_host->grad_div > 0 the term is
+ * grad[...] / grad_div) accumulated in fp32, then `update` is
  * applied to row r of `table` (and state1/state2).  Deterministic: fixed
  * chunking, no atomics.  Workspace: recemb_bwd_apply_workspace_bytes().
  *   DENSE_GRAD        table = grad_weight (dtype `dtype`), states unused

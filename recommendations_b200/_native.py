@@ -39,7 +39,7 @@ class OptimParams(C.Structure):
         ("beta2", C.c_float),
         ("bias_correction1", C.c_float),
         ("bias_correction2", C.c_float),
-        ("reserved", C.c_float),
+        ("grad_div", C.c_float),
     ]
 
 

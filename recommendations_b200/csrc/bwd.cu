@@ -554,6 +554,11 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
             for (int j = 0; j < V; ++j)
 #pragma unroll
               for (int e = 0; e < E; ++e) acc[j][e] += wt[u] * g[u][j][e];
+          } else if (L0 && !PLAIN && a.hp.grad_div > 0.f) {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+#pragma unroll
+              for (int e = 0; e < E; ++e) acc[j][e] += __fdiv_rn(g[u][j][e], a.hp.grad_div);
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
@@ -566,6 +571,177 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
   }
   const bool right_open = end < a.n && a.keys[end] == cur;
   flush(cur, first && left_open, right_open);
+}
+
+// ---- level 0, mostly-unique rows: table rows loaded together with the gradients --------------
+// seg_kernel closes a run when the NEXT key arrives and only then loads the row it updates: with
+// few duplicates (pooled bags over large vocabularies: every entry its own run) a group has one
+// dependent row access in flight at a time and the walk is bound by memory latency, not
+// bandwidth.  Here a run is closed at its LAST entry (k[u+1] != k[u], one look-ahead key), so
+// the table rows (and row-wise Adagrad states) of every run that ends inside a batch are
+// requested at the top of the batch next to its gradient rows: 2B row accesses in flight per
+// group instead of ~1.  Rows of 16 lanes x 16 bytes (or 32 x 16), update kind fixed at compile
+// time: row-wise Adagrad or SGD (the update kinds whose only per-row state is a scalar).
+template <int G, int E, typename T, typename Cfg>
+__global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const SegArgs a) {
+  constexpr int B = Cfg::B, PD = Cfg::PD, UPD = Cfg::UPD;
+  constexpr bool PLAIN = Cfg::PLAIN;
+  constexpr int GROUPS = kBwdThreads / G;
+  static_assert(E * sizeof(T) == 16, "one 16-byte vector per lane");
+  static_assert(UPD == RECEMB_UPD_ROWWISE_ADAGRAD || UPD == RECEMB_UPD_SGD, "scalar-state updates only");
+  const int lane = threadIdx.x & 31;
+  const int lig = lane % G;
+  const int gi_warp = lane / G;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi_warp * G));
+  const int chunk = blockIdx.x * GROUPS + threadIdx.x / G;
+  const int num_chunks = (a.n + a.chunk - 1) / a.chunk;
+  if (chunk >= num_chunks) return;
+  const int start = chunk * a.chunk;
+  const int end = min(start + a.chunk, a.n);
+  if (lig == 0) {
+    if (chunk > 0) a.out_keys[2 * chunk - 1] = kNoKey;
+    a.out_keys[2 * chunk] = kNoKey;
+    if (chunk == num_chunks - 1) a.out_keys[2 * chunk + 1] = kNoKey;
+  }
+  const T* gbase = reinterpret_cast<const T*>(a.grad) + lig * E;
+  T* tbase = reinterpret_cast<T*>(a.table) + lig * E;
+  const recemb_optim_params& hp = a.hp;
+
+  auto grad_row_of = [&](uint32_t slot) -> uint32_t {
+    if (PLAIN || a.spg == 1) return slot;
+    uint32_t q = __umulhi(slot, a.spg_magic);
+    if (slot - q * a.spg >= a.spg) ++q;
+    return q;
+  };
+  // true keys of [e0, e0+B] (kNoKey past the list) and slots of [e0, e0+B)
+  auto load_meta = [&](int e0, uint32_t(&kk)[B + 1], uint32_t(&ss)[B]) {
+#pragma unroll
+    for (int u = 0; u <= B; ++u) {
+      const int i = e0 + u;
+      kk[u] = i < a.n ? a.keys[i] : kNoKey;
+      if (u < B) ss[u] = i < a.n ? a.slots[i] : 0u;
+    }
+  };
+  auto prefetch_batch = [&](int e0) {
+    if (e0 >= end) return;
+    uint32_t kk[B + 1], ss[B];
+    load_meta(e0, kk, ss);
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      if (e0 + u < end && kk[u] < a.sentinel) {
+        prefetch_vec<T, E>(gbase + (size_t)grad_row_of(ss[u]) * a.dim);
+        if (kk[u + 1] != kk[u]) {
+          prefetch_vec<T, E>(tbase + (size_t)kk[u] * a.dim);
+          if (UPD == RECEMB_UPD_ROWWISE_ADAGRAD && lig == 0) prefetch_l2(a.state1 + kk[u]);
+        }
+      }
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
+
+  const bool left_open = start > 0 && a.keys[start - 1] == a.keys[start];
+  bool first = true;
+  float acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+
+  for (int e0 = start; e0 < end; e0 += B) {
+    if (PD > 0) prefetch_batch(e0 + PD * B);
+    uint32_t k[B + 1], sl[B];
+    load_meta(e0, k, sl);
+    uint4 gv[B], wv[B];
+    float sv[B], wt[B];
+    bool closes[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const bool live = e0 + u < end && k[u] < a.sentinel;
+      gv[u] = make_uint4(0, 0, 0, 0);
+      wv[u] = make_uint4(0, 0, 0, 0);
+      sv[u] = 0.f;
+      wt[u] = 1.f;
+      closes[u] = live && k[u + 1] != k[u];
+      if (live) {
+        const uint32_t grow = grad_row_of(sl[u]);
+        gv[u] = ldg_nc_v4(gbase + (size_t)grow * a.dim);
+        if (!PLAIN) {
+          if (a.slot_weight) wt[u] = a.slot_weight[sl[u]];
+          if (a.grad_row_scale) wt[u] *= a.grad_row_scale[grow];
+        }
+      }
+      if (closes[u]) {
+        wv[u] = ldg_v4(tbase + (size_t)k[u] * a.dim);
+        if (UPD == RECEMB_UPD_ROWWISE_ADAGRAD) sv[u] = a.state1[k[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int i = e0 + u;
+      if (i < end) {
+        const bool live = k[u] < a.sentinel;
+        if (live) {
+          float f[E];
+          unpack16<T>(gv[u], f);
+          if (!PLAIN && (a.slot_weight || a.grad_row_scale)) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] += wt[u] * f[e];
+          } else if (!PLAIN && hp.grad_div > 0.f) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] += __fdiv_rn(f[e], hp.grad_div);
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] += f[e];
+          }
+        }
+        const bool chunk_last = i == end - 1;
+        if (live && (closes[u] || chunk_last)) {
+          const bool leading = first && left_open;
+          const bool trailing = !closes[u];  // the run goes on in the next chunk
+          if (!leading && !trailing) {
+            float w[E];
+            unpack16<T>(wv[u], w);
+            if (hp.weight_decay != 0.f) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) acc[e] += hp.weight_decay * w[e];
+            }
+            if (UPD == RECEMB_UPD_SGD) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) w[e] -= hp.lr * acc[e];
+            } else {
+              float ss = 0.f;
+#pragma unroll
+              for (int e = 0; e < E; ++e) ss += acc[e] * acc[e];
+              ss = masked_group_sum<G>(ss, gmask) / (float)a.dim;
+              const float s_new = sv[u] + ss;
+              const float inv = -hp.lr * fast_rcp(fast_sqrt(s_new) + hp.eps);
+#pragma unroll
+              for (int e = 0; e < E; ++e) w[e] += acc[e] * inv;
+              if (lig == 0) a.state1[k[u]] = s_new;
+            }
+            stg_v4(tbase + (size_t)k[u] * a.dim, Vec16<T>::pack(w));
+          } else {
+            const int rec = leading ? 2 * chunk - 1 : 2 * chunk;
+            float* dst = a.out_partials + (size_t)rec * a.dim + lig * E;
+            store_vec<float, E>(dst, acc);
+            if (lig == 0) {
+              a.out_keys[rec] = k[u];
+              *a.flag_out = 1u;
+            }
+            if (leading && trailing) {  // the whole chunk is one run open on both sides
+              float z[E] = {};
+              store_vec<float, E>(dst + a.dim, z);
+              if (lig == 0) a.out_keys[rec + 1] = k[u];
+            }
+          }
+        }
+        if (closes[u] || chunk_last || !live) {
+          if (live || closes[u]) first = false;
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] = 0.f;
+        }
+      }
+    }
+  }
 }
 
 struct QuadShape {
@@ -596,11 +772,10 @@ static int env_flag(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int G, int V, int E, typename GT, typename WT, bool L0, typename Cfg>
-static void launch_one(const SegArgs& a_in, cudaStream_t s) {
+template <auto kernel, int G, bool L0>
+static void launch_kernel(const SegArgs& a_in, cudaStream_t s) {
   constexpr int CH = L0 ? kChunk0 : kChunkN;
   constexpr int groups = kBwdThreads / G;
-  auto kernel = seg_kernel<G, V, E, GT, WT, L0, CH, Cfg>;
   SegArgs a = a_in;
   a.chunk = CH;
   if constexpr (L0) {
@@ -628,6 +803,11 @@ static void launch_one(const SegArgs& a_in, cudaStream_t s) {
   }
   const int chunks = (a.n + a.chunk - 1) / a.chunk;
   kernel<<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
+}
+
+template <int G, int V, int E, typename GT, typename WT, bool L0, typename Cfg>
+static void launch_one(const SegArgs& a, cudaStream_t s) {
+  launch_kernel<seg_kernel<G, V, E, GT, WT, L0, (L0 ? kChunk0 : kChunkN), Cfg>, G, L0>(a, s);
 }
 
 // generic instantiations: any shape / update / scale combination
@@ -661,6 +841,22 @@ static bool launch_fast(const SegArgs& a, cudaStream_t s) {
   }
 }
 
+// mostly-unique fast path (seg_pre_kernel): row-wise Adagrad / SGD on rows of 16 or 32 lane-vectors
+template <int G, typename T, bool PLAIN, int B, int PD, int MINB>
+static bool launch_pre(const SegArgs& a, cudaStream_t s) {
+  constexpr int E = 16 / (int)sizeof(T);
+  switch (a.update) {
+    case RECEMB_UPD_ROWWISE_ADAGRAD:
+      launch_kernel<seg_pre_kernel<G, E, T, SegCfg<B, PD, MINB, RECEMB_UPD_ROWWISE_ADAGRAD, PLAIN, true>>, G, true>(a, s);
+      return true;
+    case RECEMB_UPD_SGD:
+      launch_kernel<seg_pre_kernel<G, E, T, SegCfg<B, PD, MINB, RECEMB_UPD_SGD, PLAIN, true>>, G, true>(a, s);
+      return true;
+    default:
+      return false;
+  }
+}
+
 // RECEMB_SEG_TUNE="B,PD,MINB": tuning aid for the fp32 G = 16 fast path (one GPU session can
 // compare instantiations).  Unset = default.
 static void tune_params(int* b, int* pd, int* minb) {
@@ -682,10 +878,30 @@ static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
   const int vecs16 = (int)(a.dim * sizeof(WT) / 16);
   if constexpr (L0 && std::is_same<GT, WT>::value)
   if ((a.dim * sizeof(WT)) % 16 == 0 && (vecs16 == 16 || vecs16 == 32)) {
-    const bool plain = a.spg == 1 && !a.slot_weight && !a.grad_row_scale;
+    const bool plain = a.spg == 1 && !a.slot_weight && !a.grad_row_scale && !(a.hp.grad_div > 0.f);
     SegArgs f = a;
     f.vecs = vecs16;
     const SegArgs& a = f;
+    static const int pre = env_flag("RECEMB_SEG_PRE", 1);
+    if (pre && (a.update == RECEMB_UPD_ROWWISE_ADAGRAD || a.update == RECEMB_UPD_SGD)) {
+      int tb, tp, tm;
+      tune_params(&tb, &tp, &tm);
+      if (vecs16 == 16) {
+        if (plain && tb == 4) launched = launch_pre<16, WT, true, 4, 1, 3>(a, s);
+        else if (plain && tb == 2 && tm == 3) launched = launch_pre<16, WT, true, 2, 1, 3>(a, s);
+        else if (plain && tb == 2 && tp == 0) launched = launch_pre<16, WT, true, 2, 0, 4>(a, s);
+        else if (plain && tb == 2 && tp == 2) launched = launch_pre<16, WT, true, 2, 2, 4>(a, s);
+        else if (plain) launched = launch_pre<16, WT, true, 2, 1, 4>(a, s);
+        else launched = launch_pre<16, WT, false, 2, 1, 4>(a, s);
+      } else {
+        if (plain) launched = launch_pre<32, WT, true, 2, 2, 4>(a, s);
+        else launched = launch_pre<32, WT, false, 2, 2, 4>(a, s);
+      }
+      if (launched) {
+        RECEMB_LAUNCHED();
+        return RECEMB_OK;
+      }
+    }
     if (vecs16 == 16) {
       int tb, tp, tm;
       tune_params(&tb, &tp, &tm);

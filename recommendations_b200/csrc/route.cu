@@ -98,17 +98,33 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, i
   const int world = (int)a.h.shard_world;
   const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (o < world) {
+    // each lane owns kScanItems consecutive CTAs per round: that many loads in flight per lane
+    // instead of one dependent global load per 32 CTAs
+    constexpr int kScanItems = 8;
     uint32_t carry = 0;
-    for (int c0 = 0; c0 < num_ctas; c0 += 32) {
-      const int c = c0 + lane;
-      const uint32_t v = c < num_ctas ? a.block_hist[(int64_t)c * world + o] : 0u;
-      uint32_t inc = v;
+    for (int c0 = 0; c0 < num_ctas; c0 += 32 * kScanItems) {
+      uint32_t v[kScanItems];
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j) {
+        const int c = c0 + lane * kScanItems + j;
+        v[j] = c < num_ctas ? a.block_hist[(int64_t)c * world + o] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j) mine += v[j];
+      uint32_t inc = mine;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
       }
-      if (c < num_ctas) a.block_base[(int64_t)c * world + o] = carry + inc - v;
+      uint32_t run = carry + inc - mine;
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j) {
+        const int c = c0 + lane * kScanItems + j;
+        if (c < num_ctas) a.block_base[(int64_t)c * world + o] = run;
+        run += v[j];
+      }
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) s_total[o] = carry;

@@ -91,8 +91,18 @@ class _KShiftFn(torch.autograd.Function):
         ids, inv, out = ctx.saved_tensors
         holder, k = ctx.holder, ctx.k
         dim = grad_out.shape[-1]
-        dx = ops.epilogue_bwd(grad_out.contiguous().view(-1, dim), out, inv, ctx.epilogue, k)
-        if holder.sparse and holder.fused is None:
+        g2d = grad_out.contiguous().view(-1, dim)
+        sparse_coo = holder.sparse and holder.fused is None
+        if ctx.epilogue == N.EPI_RSQRT_K and not sparse_coo:
+            # x / sqrt(k) (commons/layers.py:170): its backward is a division of every gradient
+            # element -- folded into the segmented reduction, dx is never materialised
+            plan = ops.BackwardPlan.build(
+                ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
+            return (holder.consume(plan, g2d, slots_per_grad_row=k, grad_div=math.sqrt(k)),
+                    None, None, None, None, None)
+        dx = ops.epilogue_bwd(g2d, out, inv, ctx.epilogue, k)
+        if sparse_coo:
             flat = ids.contiguous().view(-1)
             rows = torch.cat([ops.row_index(flat, N.HASH_ROTL_FLOORMOD, holder.num_embeddings, c)
                               for c in range(k)])

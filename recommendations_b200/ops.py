@@ -174,10 +174,11 @@ class BackwardPlan:
 
 
 def make_optim_params(lr: float = 0.0, eps: float = 0.0, weight_decay: float = 0.0,
-                      beta1: float = 0.9, beta2: float = 0.999, step: int = 1) -> N.OptimParams:
+                      beta1: float = 0.9, beta2: float = 0.999, step: int = 1,
+                      grad_div: float = 0.0) -> N.OptimParams:
     return N.OptimParams(lr=lr, eps=eps, weight_decay=weight_decay, beta1=beta1, beta2=beta2,
                          bias_correction1=1.0 - beta1 ** step, bias_correction2=1.0 - beta2 ** step,
-                         reserved=0.0)
+                         grad_div=grad_div)
 
 
 def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, update: int,
@@ -185,8 +186,9 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
               state2: Optional[torch.Tensor] = None, hp: Optional[N.OptimParams] = None,
               slot_weight: Optional[torch.Tensor] = None,
               grad_row_scale: Optional[torch.Tensor] = None,
-              workspace: Optional[torch.Tensor] = None) -> None:
-    """Segmented reduction of `grad` rows over the plan + `update` on `table` (in place)."""
+              workspace: Optional[torch.Tensor] = None, grad_div: float = 0.0) -> None:
+    """Segmented reduction of `grad` rows over the plan + `update` on `table` (in place).
+    grad_div > 0: gradient elements are divided by it on the fly (k-shift 1/sqrt(k) backward)."""
     dim = table.shape[1]
     grad2d = grad.contiguous().view(-1, dim)
     if plan.slots_cover_grad and grad2d.shape[0] * slots_per_grad_row != plan.n_slots:
@@ -198,6 +200,11 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=table.device)
     hp = hp or make_optim_params()
+    if grad_div:
+        if slot_weight is not None or grad_row_scale is not None:
+            raise N.NativeError("grad_div cannot be combined with slot_weight / grad_row_scale")
+        hp = N.OptimParams.from_buffer_copy(hp)
+        hp.grad_div = grad_div
     N.check(lib.recemb_bwd_apply(
         N.ptr(plan.buf), plan.buf.numel(), plan.n_slots, N.ptr(grad2d), N.dtype_code(grad2d.dtype),
         grad2d.shape[0], dim, slots_per_grad_row, N.ptr(slot_weight), N.ptr(grad_row_scale), update,

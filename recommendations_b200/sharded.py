@@ -236,18 +236,47 @@ class _RoutedPoolFn(torch.autograd.Function):
 
 
 class _PeerPoolFn(torch.autograd.Function):
-    """exchange="peer": rows pulled / entries and gradients pushed through peer-mapped memory."""
+    """exchange="peer": rows pulled / entries and gradients pushed through peer-mapped memory.
+
+    Stream plan of one training step (main = the caller's stream, side = the module's own):
+      forward   main: [barrier ch0 if rows changed] -> pull-pool kernel (NVLink-bound)
+                side: bucket + push entries -> barrier ch1 -> sort of my inbox -> barrier ch1
+                      (the backward plan only depends on the ids: it is built in the shadow of
+                      the forward pull and of whatever the model computes before backward)
+      backward  main: push-all-gather of the pooled gradients -> barrier ch0 -> wait(side) ->
+                      segmented reduction + fused update of MY rows
+    Hazards: a peer may overwrite my inbox only after I sorted it (2nd ch1 barrier), my gradient
+    buffer only after my update read it and my rows may be read only after the update (ch0
+    barrier at the start of the next forward)."""
 
     @staticmethod
     def forward(ctx, anchor, ids, lengths, module):
         pg = module.peer_group()
         pg.raise_on_status()
+        main = torch.cuda.current_stream(ids.device)
         _mark(module, "start")
         if module._peer_dirty:
             # rows updated since the last barrier (backward / optimizer.step / a weight load) must
             # be complete on every rank before anybody reads them
-            ops.peer_barrier(pg)
+            ops.peer_barrier(pg, channel=0)
             module._peer_dirty = False
+        ctx.plan, ctx.plan_ready = None, None
+        if ctx.needs_input_grad[0]:
+            side = module._side_stream(ids.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths,
+                                     last_n=module.last_n, zero_pad=module.skip_pad, pad_id=module.pad_id,
+                                     **module._own_batching(ids))
+                ops.peer_barrier(pg, channel=1)
+                ctx.plan = ops.peer_plan(pg, module.emb.weight.shape[0])
+                ops.peer_barrier(pg, channel=1)
+                ctx.plan_ready = torch.cuda.Event()
+                ctx.plan_ready.record(side)
+            ids.record_stream(side)
+            if lengths is not None:
+                lengths.record_stream(side)
+            ctx.plan.buf.record_stream(main)
         out = ops.peer_pool_fwd(
             pg, ids, num_rows=module.num_embeddings, dim=module.emb_dim, dtype=module.emb.weight.dtype,
             lengths=lengths, last_n=module.last_n,
@@ -259,12 +288,12 @@ class _PeerPoolFn(torch.autograd.Function):
             scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad,
                                         module.pad_id).clamp_(min=1).float()
         ctx.module = module
-        ctx.save_for_backward(ids, lengths, scale)
+        ctx.save_for_backward(scale)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        ids, lengths, scale = ctx.saved_tensors
+        (scale,) = ctx.saved_tensors
         module = ctx.module
         pg = module.peer_group()
         g = grad_out.contiguous()
@@ -272,26 +301,17 @@ class _PeerPoolFn(torch.autograd.Function):
             g = g * scale.unsqueeze(1).to(g.dtype)
         if g.dtype != module.emb.weight.dtype:
             g = g.to(module.emb.weight.dtype)
-        _mark(module, "bwd_start")
-        # the gradients travel on a side stream with their own barrier channel, under the
-        # bucketing / entry push / sort of the main stream: NVLink and the SMs work in parallel
         main = torch.cuda.current_stream(g.device)
-        side = module._side_stream(g.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
-            ops.peer_barrier(pg, channel=1)
-        g.record_stream(side)
-        ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths, last_n=module.last_n,
-                             zero_pad=module.skip_pad, pad_id=module.pad_id, **module._own_batching(ids))
-        _mark(module, "bucket_push")
+        _mark(module, "bwd_start")
+        ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
+        _mark(module, "grads_push")
         ops.peer_barrier(pg, channel=0)
-        _mark(module, "barrier")
-        plan = ops.peer_plan(pg, module.emb.weight.shape[0])
-        _mark(module, "plan")
-        main.wait_stream(side)
-        res = module.emb.consume(plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype), slots_per_grad_row=1)
+        main.wait_event(ctx.plan_ready)
+        _mark(module, "barrier+plan")
+        res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype),
+                                 slots_per_grad_row=1)
         _mark(module, "apply")
+        ctx.plan = None
         pg.snapshot_status()
         module._peer_dirty = True
         return res, None, None, None

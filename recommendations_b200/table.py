@@ -118,7 +118,7 @@ class EmbeddingTable(nn.Module):
     # ------------------------------------------------------------- backward ----
     def consume(self, plan: ops.BackwardPlan, grad2d: torch.Tensor, slots_per_grad_row: int = 1,
                 slot_weight: Optional[torch.Tensor] = None,
-                grad_row_scale: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                grad_row_scale: Optional[torch.Tensor] = None, grad_div: float = 0.0) -> Optional[torch.Tensor]:
         """Reduce grad rows over `plan`; fused: update in place and return None,
         torch-compatible: return the dense gradient of `weight`."""
         w = self.weight
@@ -128,7 +128,7 @@ class EmbeddingTable(nn.Module):
             gw = torch.zeros_like(w)
             ops.bwd_apply(plan, grad2d, table=gw, update=N.UPD_DENSE_GRAD,
                           slots_per_grad_row=slots_per_grad_row, slot_weight=slot_weight,
-                          grad_row_scale=grad_row_scale)
+                          grad_row_scale=grad_row_scale, grad_div=grad_div)
             return gw
         cfg = self.fused
         self._ensure_state()
@@ -143,7 +143,7 @@ class EmbeddingTable(nn.Module):
                           slots_per_grad_row=slots_per_grad_row,
                           state1=self._buffers.get("opt_state1"),
                           state2=self._buffers.get("opt_state2"), hp=hp, slot_weight=slot_weight,
-                          grad_row_scale=grad_row_scale)
+                          grad_row_scale=grad_row_scale, grad_div=grad_div)
         return None
 
     def extra_repr(self) -> str:

@@ -614,3 +614,41 @@ def test_cfg1_lthm_product_front_end():
     got = ks2.emb.weight.cpu()
     err = (got - w_ref).abs()
     assert (err <= 1e-5 + 1e-5 * w_ref.abs()).float().mean().item() >= 0.999 and err.max().item() <= 1.01
+
+
+@pytest.mark.parametrize("dim,dtype,k", [(64, torch.float32, 8), (32, torch.float32, 16), (128, torch.bfloat16, 4),
+                                         (24, torch.float32, 3)])
+@pytest.mark.parametrize("update", ["dense_grad", "adagrad", "rowwise_adagrad"])
+def test_grad_div_equals_materialised_epilogue_backward(dim, dtype, k, update):
+    """The x / sqrt(k) backward folded into the segmented reduction (grad_div) is bit-identical to
+    running epilogue_bwd first and reducing its fp32 dx rows (commons/layers.py:170 autograd)."""
+    n, n_rows = 5003, 997
+    ids = seeded_ids(n, 123).to(DEV)
+    grad = torch.randn(n, dim, generator=torch.Generator().manual_seed(9)).to(dtype).to(DEV)
+    plan = ops.BackwardPlan.build(ids, num_rows=n_rows, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k)
+    hp = ops.make_optim_params(lr=0.5, eps=1e-10)
+    results = []
+    for fused in (False, True):
+        torch.manual_seed(5)
+        w = (torch.zeros(n_rows, dim) if update == "dense_grad" else torch.randn(n_rows, dim)).to(dtype).to(DEV)
+        st = None
+        if update == "adagrad":
+            st = torch.zeros(n_rows, dim, device=DEV)
+        elif update == "rowwise_adagrad":
+            st = torch.zeros(n_rows, device=DEV)
+        if fused:
+            ops.bwd_apply(plan, grad, table=w, update=N.UPDATE_BY_NAME[update], state1=st, slots_per_grad_row=k,
+                          hp=hp, grad_div=math.sqrt(k))
+        else:
+            dx = ops.epilogue_bwd(grad, None, None, N.EPI_RSQRT_K, k)
+            ops.bwd_apply(plan, dx, table=w, update=N.UPDATE_BY_NAME[update], state1=st, slots_per_grad_row=k, hp=hp)
+        results.append((w, st))
+    if update == "rowwise_adagrad" and dtype == torch.bfloat16:
+        # bf16 gradients take the 16-byte-per-lane instantiation: the row's mean of squares is
+        # reduced over a different lane grouping than with fp32 dx rows -> equal within rounding
+        torch.testing.assert_close(results[0][0].float(), results[1][0].float(), rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(results[0][1], results[1][1], rtol=1e-5, atol=1e-6)
+        return
+    assert torch.equal(results[0][0], results[1][0])
+    if results[0][1] is not None:
+        assert torch.equal(results[0][1], results[1][1])
