@@ -193,7 +193,16 @@ def run_b200(args):
 
     ev_apply, ev_gather = [], []  # (start, stop) around the two dominant launches
 
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+
     def step(timed: bool):
+        # the backward plan (hash + radix sort of the slots) only depends on the ids: it is built on
+        # a second stream while the forward gather streams rows on the first
+        if args.overlap_plan:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                plan = ops.BackwardPlan.build(ids_dev, num_rows=ROWS, ids_per_table=n, buf=plan_buf)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -201,7 +210,10 @@ def run_b200(args):
         if timed:
             b.record()
             ev_gather.append((a, b))
-        plan = ops.BackwardPlan.build(ids_dev, num_rows=ROWS, ids_per_table=n, buf=plan_buf)
+        if args.overlap_plan:
+            main.wait_stream(side)
+        else:
+            plan = ops.BackwardPlan.build(ids_dev, num_rows=ROWS, ids_per_table=n, buf=plan_buf)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()  # creates the underlying cudaEvent_t; the library re-records both
@@ -326,6 +338,7 @@ def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads
     plan_bytes = int(lib.recemb_bwd_plan_bytes(n_all, rows_all))
     ws_bytes = int(lib.recemb_bwd_apply_workspace_bytes(n_all, DIM))
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    plan_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     scratch = [torch.empty(n_all, dtype=torch.int64, device=dev) for _ in range(2)]
     plans = [torch.empty(plan_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -340,7 +353,8 @@ def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads
             ids_host.data_ptr(), n_all, n, scratch[k].data_ptr(), table_all.data_ptr(), ROWS, DIM, N.F32,
             outs.data_ptr(), grads.data_ptr(), N.UPD_ADAGRAD, state_all.data_ptr(), None, C.byref(hp),
             plans[k].data_ptr(), plan_bytes, wss[k].data_ptr(), ws_bytes, counters[k].data_ptr(),
-            done[1 - k].cuda_event if overlap else None, dev.index, streams[k].cuda_stream),
+            done[1 - k].cuda_event if overlap else None,
+            plan_streams[k].cuda_stream if args.overlap_plan else None, dev.index, streams[k].cuda_stream),
             "recemb_flat_step_host")
         done[k].record(streams[k])
 
@@ -382,7 +396,8 @@ def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads
             "ms_per_step": ms / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
             "serial_ms_per_step": out["serial"][0] / args.steps,
             "api": "recemb_flat_step_host (C ABI; pinned host ids in, counters out, every step); H2D of "
-                   "step s+1 overlaps the kernels of step s on a second stream"}
+                   "step s+1 overlaps the kernels of step s on a second stream; the plan's sort runs on a "
+                   "third stream next to the gather"}
 
 
 def main():
@@ -393,6 +408,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-overlap-plan", dest="overlap_plan", action="store_false",
+                    help="build the backward plan after the gather on the same stream (default: concurrently)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print(f"[bench] note: warmup {args.warmup} < 3", file=sys.stderr)

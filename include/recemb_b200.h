@@ -403,14 +403,17 @@ RECEMB_API int recemb_pad_histories(const int64_t* values, const int64_t* offset
  * selects the table-batched mode of recemb_gather_fwd (num_rows per table, stacked table).
  * wait_event_after_copy (optional cudaEvent_t): `stream` waits for it after the H2D copy and
  * before the first kernel, so a caller alternating two streams can copy step s+1's ids while
- * step s still computes without letting the two steps' kernels overlap. */
+ * step s still computes without letting the two steps' kernels overlap.
+ * plan_stream (optional, != stream): the backward plan (hash + radix sort, a function of the ids
+ * only) is built there while the forward gather runs on `stream`; the update joins both. */
 RECEMB_API int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t ids_per_table,
                           int64_t* ids_dev_scratch,
                           void* table, int64_t num_rows, int32_t dim, int dtype, void* out,
                           const void* grad, int update, void* state1, void* state2,
                           const recemb_optim_params* hp_host, void* plan, size_t plan_bytes,
                           void* workspace, size_t workspace_bytes, int64_t* counters_host,
-                          void* wait_event_after_copy, int device, recemb_stream_t stream);
+                          void* wait_event_after_copy, recemb_stream_t plan_stream, int device,
+                          recemb_stream_t stream);
 
 #ifdef __cplusplus
 }

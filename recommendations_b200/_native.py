@@ -139,7 +139,7 @@ SIGNATURES = {
     "recemb_xxh64_ids": (_INT, [_P, _P, _I64, C.c_uint64, _INT, _P, _INT, _P]),
     "recemb_pad_histories": (_INT, [_P, _P, _P, _I64, _I32, _I64, _P, _INT, _P]),
     "recemb_flat_step_host": (_INT, [_P, _I64, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
-                                     C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _P, _INT, _P]),
+                                     C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _P, _P, _INT, _P]),
 }
 
 _lib = None

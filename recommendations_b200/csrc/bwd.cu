@@ -795,8 +795,7 @@ static void launch_kernel(const SegArgs& a_in, cudaStream_t s) {
     const int64_t chunks64 = ((int64_t)a.n + CH - 1) / CH;
     if (fit && chunks64 > resident) {
       const int64_t waves = chunks64 / resident;
-      int64_t c = ((int64_t)a.n + waves * resident - 1) / (waves * resident);
-      c += c & 1;
+      const int64_t c = ((int64_t)a.n + waves * resident - 1) / (waves * resident);
       if (c > CH && c <= 2 * CH) a.chunk = (int32_t)c;
     }
     t_chunk_used = a.chunk;

@@ -119,13 +119,24 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
                                      void* out, const void* grad, int update, void* state1,
                                      void* state2, const recemb_optim_params* hp_host, void* plan,
                                      size_t plan_bytes, void* workspace, size_t workspace_bytes,
-                                     int64_t* counters_host, void* wait_event_after_copy, int device,
-                                     recemb_stream_t stream) {
+                                     int64_t* counters_host, void* wait_event_after_copy,
+                                     recemb_stream_t plan_stream, int device, recemb_stream_t stream) {
   RECEMB_CHECK_ARG(ids_host && ids_dev_scratch, "null ids");
   RECEMB_CHECK_ARG(n >= 0, "n < 0");
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t ps = (cudaStream_t)plan_stream;
+  const bool fork = plan_stream != nullptr && plan_stream != stream;
+  // fork / join events of this thread (one pair per device, created on first use)
+  static thread_local cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
+  if (fork) {
+    RECEMB_CHECK_ARG(device >= 0 && device < 64, "device index out of range");
+    if (!ev_fork[device]) {
+      RECEMB_CUDA(cudaEventCreateWithFlags(&ev_fork[device], cudaEventDisableTiming));
+      RECEMB_CUDA(cudaEventCreateWithFlags(&ev_join[device], cudaEventDisableTiming));
+    }
+  }
   if (n > 0)
     RECEMB_CUDA(cudaMemcpyAsync(ids_dev_scratch, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
   // software pipelining across steps: the copy above may run while the previous step (on
@@ -133,13 +144,28 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   if (wait_event_after_copy)
     RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
   recemb_layout layout = {ids_per_table, 0, 1, 0, 0};  // no sharding, no flip
-  int rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
-                             &layout, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
-                             stream);
+  int rc;
+  if (fork) {
+    // the plan (hash + radix sort) only needs the ids: it runs on plan_stream while the gather
+    // streams rows on `stream`; both wait for the copy, the update waits for both
+    RECEMB_CUDA(cudaEventRecord(ev_fork[device], s));
+    RECEMB_CUDA(cudaStreamWaitEvent(ps, ev_fork[device], 0));
+    rc = recemb_bwd_plan(ids_dev_scratch, n, &layout, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
+                         0, -1, 0, nullptr, 0, plan, plan_bytes, device, plan_stream);
+    if (rc) return rc;
+    RECEMB_CUDA(cudaEventRecord(ev_join[device], ps));
+  }
+  rc = recemb_gather_fwd(table, num_rows, nullptr, 0, dim, dtype, ids_dev_scratch, n,
+                         &layout, RECEMB_HASH_FLOORMOD, 0, 0, RECEMB_EPI_NONE, 0, 0, out, nullptr, device,
+                         stream);
   if (rc) return rc;
-  rc = recemb_bwd_plan(ids_dev_scratch, n, &layout, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
-                       0, -1, 0, nullptr, 0, plan, plan_bytes, device, stream);
-  if (rc) return rc;
+  if (fork) {
+    RECEMB_CUDA(cudaStreamWaitEvent(s, ev_join[device], 0));
+  } else {
+    rc = recemb_bwd_plan(ids_dev_scratch, n, &layout, 1, RECEMB_HASH_FLOORMOD, num_rows, 0, 0,
+                         0, -1, 0, nullptr, 0, plan, plan_bytes, device, stream);
+    if (rc) return rc;
+  }
   const int64_t total_rows = recemb_layout_total_rows(num_rows, &layout, n);
   rc = recemb_bwd_apply(plan, plan_bytes, n, grad, dtype, n, dim, 1, nullptr, nullptr, update, table,
                         dtype, total_rows, state1, state2, hp_host, workspace, workspace_bytes, device,

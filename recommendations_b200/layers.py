@@ -23,6 +23,47 @@ from .table import EmbeddingTable, FusedOptimizerConfig
 
 
 # ---------------------------------------------------------- autograd glue ----
+# The backward plan (id hashing + radix sort of the lookup slots) is a function of the ids alone.
+# When a lookup will need a gradient it is therefore built during FORWARD, on a side stream next
+# to the gather / pooling kernel (which is HBM-bound and leaves the sort's latency-bound passes
+# room), and backward only waits for it: ~0.5 ms per step off the critical path at cfg 2.
+# RECEMB_PLAN_IN_FORWARD=0 (or layers.PLAN_IN_FORWARD = False) builds it in backward instead --
+# needed when only the forward pass is captured into a CUDA graph.
+import os as _os
+
+PLAN_IN_FORWARD = _os.environ.get("RECEMB_PLAN_IN_FORWARD", "1") != "0"
+_side_streams = {}
+
+
+def _plan_early(ctx, ids: torch.Tensor, wanted: bool, build) -> None:
+    ctx.plan, ctx.plan_ready = None, None
+    if not (wanted and PLAN_IN_FORWARD and ids.is_cuda):
+        return
+    dev = ids.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        ctx.plan = build()
+        ctx.plan_ready = torch.cuda.Event()
+        ctx.plan_ready.record(side)
+    ids.record_stream(side)
+    ctx.plan.buf.record_stream(main)
+
+
+def _plan_take(ctx, build):
+    """The plan built in forward (after waiting for it on the current stream) or a fresh one."""
+    if getattr(ctx, "plan", None) is None:
+        return build()
+    plan = ctx.plan
+    torch.cuda.current_stream(plan.buf.device).wait_event(ctx.plan_ready)
+    plan.buf.record_stream(torch.cuda.current_stream(plan.buf.device))
+    ctx.plan = None
+    return plan
+
+
 class _GatherFn(torch.autograd.Function):
     """out = epilogue(table[h(ids)] (+ table2[h2(ids)])); backward = plan + segmented reduce."""
 
@@ -39,6 +80,11 @@ class _GatherFn(torch.autograd.Function):
         ctx.flip_len = flip_len
         ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
+        _plan_early(ctx, ids, holder2 is None and anchor.requires_grad and not (holder.sparse and holder.fused is None),
+                    lambda: ops.BackwardPlan.build(
+                        ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
+                        zero_pad=zero_pad, pad_id=pad_id,
+                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
         return out
 
     @staticmethod
@@ -61,10 +107,10 @@ class _GatherFn(torch.autograd.Function):
                     vals = vals.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
                 grads[i] = _coo(rows, vals, holder)
                 continue
-            plan = ops.BackwardPlan.build(
+            plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
                 ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
                 zero_pad=zero_pad, pad_id=pad_id,
-                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
             grads[i] = holder.consume(plan, g)
         return (grads[0], grads[1]) + (None,) * 10
 
@@ -84,6 +130,10 @@ class _KShiftFn(torch.autograd.Function):
                                   want_inv_norm=anchor.requires_grad, flip_len=flip_len)
         ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
+        _plan_early(ctx, ids, anchor.requires_grad and not (holder.sparse and holder.fused is None),
+                    lambda: ops.BackwardPlan.build(
+                        ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=num_shifts,
+                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
         return out
 
     @staticmethod
@@ -96,9 +146,9 @@ class _KShiftFn(torch.autograd.Function):
         if ctx.epilogue == N.EPI_RSQRT_K and not sparse_coo:
             # x / sqrt(k) (commons/layers.py:170): its backward is a division of every gradient
             # element -- folded into the segmented reduction, dx is never materialised
-            plan = ops.BackwardPlan.build(
+            plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
                 ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
-                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
             return (holder.consume(plan, g2d, slots_per_grad_row=k, grad_div=math.sqrt(k)),
                     None, None, None, None, None)
         dx = ops.epilogue_bwd(g2d, out, inv, ctx.epilogue, k)
@@ -110,9 +160,9 @@ class _KShiftFn(torch.autograd.Function):
                 dx = dx.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
             vals = dx.to(holder.weight.dtype).repeat(k, 1)
             return (_coo(rows, vals, holder), None, None, None, None, None)
-        plan = ops.BackwardPlan.build(
+        plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
-            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len)
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
         return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None)
 
 
@@ -126,6 +176,13 @@ class _PoolFn(torch.autograd.Function):
         ctx.holder = holder
         ctx.cfg = (hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id)
         ctx.save_for_backward(ids, lengths, per_slot_weight)
+        _plan_early(ctx, ids, anchor.requires_grad, lambda: ops.BackwardPlan.build(
+            ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
+            zero_pad=zero_pad, pad_id=pad_id,
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=ids.shape[1],
+            lengths=lengths, last_n=last_n))
+        if ctx.plan is not None and lengths is not None:
+            lengths.record_stream(_side_streams[ids.device])
         return out
 
     @staticmethod
@@ -134,11 +191,11 @@ class _PoolFn(torch.autograd.Function):
         holder = ctx.holder
         hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id = ctx.cfg
         m, p = ids.shape
-        plan = ops.BackwardPlan.build(
+        plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
             zero_pad=zero_pad, pad_id=pad_id,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=p,
-            lengths=lengths, last_n=last_n)
+            lengths=lengths, last_n=last_n))
         scale = None
         if pool_mode == N.POOL_MEAN:
             scale = 1.0 / pooled_counts(ids, lengths, last_n, zero_pad, pad_id).clamp_(min=1).float()
