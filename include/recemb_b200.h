@@ -315,6 +315,8 @@ typedef struct recemb_peer_arena {
   int64_t off_grads;   /* [world][bags_total][dim] pooled gradients, slice s written by rank s */
   int64_t cap;         /* inbox capacity per sender (entries) */
   int64_t bags_total;
+  int64_t off_parts;   /* [world][bags_total][dim] partial pools of MY bags, slice o written by owner o
+                          (push forward; the requester zero-fills it before the owners write) */
 } recemb_peer_arena;
 
 /* handle_out identifies the whole allocation that contains ptr; *offset_out = ptr - its base. */
@@ -347,6 +349,15 @@ RECEMB_API int recemb_peer_pool_fwd(const recemb_peer_group* group, int64_t num_
                          int32_t last_n, const float* per_slot_weight, int hash_mode, int64_t hash_arg,
                          int pool_mode, int zero_pad, int64_t pad_id, const recemb_layout* layout,
                          void* out, int device, recemb_stream_t stream);
+
+/* Forward, "push" variant (fewer NVLink bytes than the pull: one partial row per (bag, owner) pair
+ * instead of one row per lookup).  Owner side, after recemb_peer_bucket_push + barrier: every run
+ * of equal (sender, bag) in MY inbox is pooled from MY shard (fp32 accumulation in slot order) and
+ * the partial row is stored straight into the sender's arena at parts[rank][bag] over NVLink.
+ * Pairs without an entry are not written: the requester zero-fills its parts region before the
+ * barrier and sums the world slices afterwards (recemb_sum_partials, fixed owner order). */
+RECEMB_API int recemb_peer_pool_push(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
+                          int dtype, int device, recemb_stream_t stream);
 
 /* Backward, sender side.  recemb_shard_bucket whose entries land in the owners' inboxes: entry
  * k of my bucket for owner o is stored at inbox(o)[rank][k], the bucket size at counts(o)[rank].

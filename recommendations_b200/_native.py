@@ -71,7 +71,7 @@ class PeerArena(C.Structure):
     """recemb_peer_arena: byte offsets inside one rank's exchange arena."""
     _fields_ = [(name, C.c_int64) for name in
                 ("bytes", "off_flags", "off_epoch", "off_status", "off_counts", "off_inbox", "off_grads",
-                 "cap", "bags_total")]
+                 "cap", "bags_total", "off_parts")]
 
 
 def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
@@ -129,6 +129,7 @@ SIGNATURES = {
     "recemb_peer_barrier": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _INT, _P]),
     "recemb_peer_pool_fwd": (_INT, [C.POINTER(PeerGroupStruct), _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P,
                                     _INT, _I64, _INT, _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
+    "recemb_peer_pool_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _INT, _P]),
     "recemb_peer_bucket_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
                                        C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32, _P, _SZ,
                                        _INT, _P]),

@@ -179,6 +179,8 @@ extern "C" int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
   off += (int64_t)align_up((size_t)((int64_t)world * cap * 8), 256);
   out->off_grads = off;
   off += (int64_t)align_up((size_t)((int64_t)world * bags_total * row_bytes), 256);
+  out->off_parts = off;
+  off += (int64_t)align_up((size_t)((int64_t)world * bags_total * row_bytes), 256);
   out->bytes = off;
   out->cap = cap;
   out->bags_total = bags_total;

@@ -276,6 +276,87 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_entries_kernel(const PoolE
   }
 }
 
+// Owner side of the push forward: the same run pooling over MY inbox ([world][cap] regions with
+// per-sender counts), each partial row stored into the requesting rank's parts[rank][bag] over
+// NVLink (256-byte contiguous stores: posted writes, no round trip).
+struct PoolInboxArgs {
+  const int64_t* inbox;
+  const int64_t* counts;
+  int64_t cap;
+  int64_t bags_total;
+  int32_t world;
+  int32_t chunks_per_sender;
+  const void* table;
+  int32_t vecs;
+  uint4* parts[RECEMB_MAX_PEERS];  // requester s: its parts region, slice of THIS owner
+};
+
+template <int G, typename T>
+__global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const PoolInboxArgs a) {
+  constexpr int E = Vec16<T>::kElems;
+  constexpr int B = 4;
+  __shared__ uint4* s_parts[RECEMB_MAX_PEERS];
+  if (threadIdx.x < RECEMB_MAX_PEERS) s_parts[threadIdx.x] = a.parts[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, lig = lane % G;
+  const int64_t chunk_global = (int64_t)blockIdx.x * (kRtThreads / G) + threadIdx.x / G;
+  const int sender = (int)(chunk_global / a.chunks_per_sender);
+  if (sender >= a.world) return;
+  const int n = (int)a.counts[sender];
+  const int start = (int)(chunk_global - (int64_t)sender * a.chunks_per_sender) * kPeChunk;
+  if (start >= n) return;
+  const int end = min(start + kPeChunk, n);
+  const int64_t* entries = a.inbox + (int64_t)sender * a.cap;
+  const uint4* table = reinterpret_cast<const uint4*>(a.table);
+  uint4* out = s_parts[sender];
+  const uint32_t key_base = (uint32_t)((int64_t)sender * a.bags_total);
+  auto key_of = [&](int i) { return (uint32_t)((uint64_t)entries[i] & 0xffffffffull); };
+
+  int i = start;
+  if (start > 0) {  // skip the tail of a run that started in an earlier chunk
+    const uint32_t prev = key_of(start - 1);
+    while (i < n && i < end && key_of(i) == prev) ++i;
+    if (i == end && i < n && key_of(i) == prev) return;
+  }
+  float acc[E];
+  while (i < end) {  // runs starting in [start, end)
+    const uint32_t key = key_of(i);
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    bool more = true;
+    while (more) {
+      uint4 v[B];
+      bool use[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int j = i + u;
+        use[u] = false;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (j < n) {
+          const uint64_t ent = (uint64_t)entries[j];
+          if ((uint32_t)(ent & 0xffffffffull) == key) {
+            use[u] = true;
+            if (lig < a.vecs) v[u] = ldg_nc_v4(table + (size_t)(ent >> 32) * a.vecs + lig);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        if (use[u] && more) {
+          float f[E];
+          Vec16<T>::unpack(v[u], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] += f[e];
+          ++i;
+        } else {
+          more = false;
+        }
+      }
+    }
+    if (lig < a.vecs) stg_v4(out + (size_t)(key - key_base) * a.vecs + lig, Vec16<T>::pack(acc));
+  }
+}
+
 // ------------------------------------------------------------------ plan from entries ----
 __global__ void __launch_bounds__(kRtThreads) unpack_entries_kernel(const int64_t* __restrict__ entries, int64_t n,
                                                                    uint32_t* __restrict__ keys,
@@ -546,5 +627,53 @@ extern "C" int recemb_peer_plan(const recemb_peer_group* group, const recemb_pee
   RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
                                               (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return RECEMB_OK;
+}
+
+
+extern "C" int recemb_peer_pool_push(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
+                                     int dtype, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena && group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
+                       group->rank < group->world,
+                   "bad peer group");
+  RECEMB_CHECK_ARG(dim > 0 && (dtype == RECEMB_F32 || dtype == RECEMB_BF16), "bad dim / dtype");
+  const int64_t row_bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED(row_bytes % 16 == 0 && row_bytes <= 512, "row of %lld bytes unsupported (16-byte multiple, <= 512)",
+                     (long long)row_bytes);
+  RECEMB_CHECK_ARG(arena->cap >= 1 && arena->bags_total >= 0, "bad arena");
+  if (arena->bags_total == 0) return RECEMB_OK;
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  PoolInboxArgs a;
+  const char* mine = (const char*)group->arena[group->rank];
+  RECEMB_CHECK_ARG(mine && group->table[group->rank], "local arena / table missing");
+  a.inbox = (const int64_t*)(mine + arena->off_inbox);
+  a.counts = (const int64_t*)(mine + arena->off_counts);
+  a.cap = arena->cap;
+  a.bags_total = arena->bags_total;
+  a.world = group->world;
+  a.chunks_per_sender = (int32_t)((arena->cap + kPeChunk - 1) / kPeChunk);
+  a.table = group->table[group->rank];
+  a.vecs = (int32_t)(row_bytes / 16);
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.parts[i] = nullptr;
+  for (int sd = 0; sd < group->world; ++sd) {
+    RECEMB_CHECK_ARG(group->arena[sd], "peer arena %d not mapped", sd);
+    a.parts[sd] = (uint4*)((char*)group->arena[sd] + arena->off_parts +
+                           (int64_t)group->rank * arena->bags_total * row_bytes);
+  }
+  int G = 1;
+  while (G < a.vecs) G <<= 1;
+  const int64_t chunks = (int64_t)a.chunks_per_sender * group->world;
+  cudaStream_t s = (cudaStream_t)stream;
+#define PIP(G_)                                                                                       \
+  if (G == G_) {                                                                                      \
+    const int groups = kRtThreads / G_;                                                               \
+    const unsigned grid = (unsigned)((chunks + groups - 1) / groups);                                 \
+    if (dtype == RECEMB_F32) pool_inbox_push_kernel<G_, float><<<grid, kRtThreads, 0, s>>>(a);         \
+    else pool_inbox_push_kernel<G_, __nv_bfloat16><<<grid, kRtThreads, 0, s>>>(a);                     \
+  }
+  PIP(1) PIP(2) PIP(4) PIP(8) PIP(16) PIP(32)
+#undef PIP
+  RECEMB_LAUNCHED();
   return RECEMB_OK;
 }

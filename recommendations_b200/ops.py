@@ -336,6 +336,13 @@ def peer_bucket_push(group, ids: torch.Tensor, *, num_rows: int, lengths: Option
             "recemb_peer_bucket_push")
 
 
+def peer_pool_push(group, dim: int, dtype: torch.dtype) -> None:
+    """Owner side of the push forward: pool the (sender, bag) runs of my inbox from my shard and
+    store every partial row into the sender's parts region over NVLink."""
+    N.check(N.load().recemb_peer_pool_push(C.byref(group.struct), C.byref(group.layout), dim, N.dtype_code(dtype),
+                                           group.device, N.stream_ptr(group.device)), "recemb_peer_pool_push")
+
+
 def peer_allgather_push(group, src: torch.Tensor, dst_offset: int) -> None:
     """src -> slice `rank` at dst_offset of every rank's arena (push all-gather over NVLink)."""
     src = src.contiguous()

@@ -115,6 +115,13 @@ class PeerGroup:
         off = int(self.layout.off_grads)
         return self.arena[off:off + nbytes].view(dtype).view(rows, dim)
 
+    def parts_view(self, dim: int, dtype: torch.dtype) -> torch.Tensor:
+        """[world, bags_total, dim] view of my partial-pool region (slice o written by owner o)."""
+        rows = int(self.layout.bags_total)
+        nbytes = self.world * rows * dim * dtype.itemsize
+        off = int(self.layout.off_parts)
+        return self.arena[off:off + nbytes].view(dtype).view(self.world, rows, dim)
+
     def counts_view(self) -> torch.Tensor:
         off = int(self.layout.off_counts)
         return self.arena[off:off + 8 * self.world].view(torch.int64)

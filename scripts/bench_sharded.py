@@ -35,13 +35,17 @@ def ids_for(rank, t_tables, b, p, seed=5000):
     return torch.randint(-2 ** 63, 2 ** 63 - 1, (t_tables, b, p), generator=g, dtype=torch.int64)
 
 
+PEER_FORWARD = None   # None: the module's default (pull on one rank, push otherwise)
+
+
 def check(world, rank, dev, exchange=None):
     """sharded == unsharded at N = 100003 rows x 4 tables, fp32, both directions."""
     from oracle import embedding_oracle as O
     n_rows, dim, t, b, p = 100003, 64, 4, 257, 20
     torch.manual_seed(99)
     full = torch.randn(t, n_rows, dim)
-    mod = RowWiseShardedEmbeddingBag(n_rows, dim, num_tables=t, device=dev, exchange=exchange)
+    mod = RowWiseShardedEmbeddingBag(n_rows, dim, num_tables=t, device=dev, exchange=exchange,
+                                     peer_forward=PEER_FORWARD)
     mod.load_full_weight(full)
     ids = ids_for(rank, t, b, p, seed=7000)
     lengths = torch.randint(0, p + 1, (t, b), generator=torch.Generator().manual_seed(rank))
@@ -49,7 +53,7 @@ def check(world, rank, dev, exchange=None):
     out = mod(ids.to(dev), lengths.to(dev))
     for ti in range(t):
         want = O.pooled_bag(full[ti], ids[ti], lengths=lengths[ti])
-        if mod.exchange == "peer":   # rows pulled from their owners, pooled here in slot order
+        if mod.exchange == "peer" and mod.peer_forward == "pull":   # rows pulled from their owners, pooled here in slot order
             assert torch.equal(out[ti].cpu(), want), "peer forward is not bit-identical to the unsharded bag"
         torch.testing.assert_close(out[ti].cpu(), want, rtol=1e-5, atol=1e-5)
     out.backward(go.to(dev))
@@ -70,7 +74,7 @@ def check(world, rank, dev, exchange=None):
         # second step on the same group (barrier bookkeeping, inbox reuse), then the status word
         mod.emb.weight.grad = None
         out2 = mod(ids.to(dev), lengths.to(dev))
-        assert torch.equal(out2, out)
+        assert torch.equal(out2, out)   # deterministic: fixed owner order, fixed slot order
         out2.backward(go.to(dev))
         torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
         mod.peer_group().raise_on_status(synchronize=True)
@@ -87,6 +91,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     args.steps, args.warmup, args.rows_per_gpu = steps, warmup, rows_per_gpu
     n_rows = args.rows_per_gpu * world
     mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange=exchange,
+                                     peer_forward=PEER_FORWARD,
                                      fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
     ids_host = ids_for(rank, T, B_LOCAL, P).pin_memory()
     ids = ids_host.to(dev)
@@ -139,8 +144,14 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
         # rows pulled from remote owners (fwd) + entries pushed into my inbox + gathered gradients (bwd)
         remote = (world - 1) / world
         nv_in = int(remote * T * B_LOCAL * P * (row_bytes + 8) + (world - 1) * T * B_LOCAL * row_bytes)
+        if mod.peer_forward == "push":
+            # entries in + one partial row per non-empty (bag, remote owner) pair + gathered gradients
+            pairs = (world - 1) * (1.0 - (1.0 - 1.0 / world) ** P)
+            nv_in = int(remote * T * B_LOCAL * P * 8 + pairs * T * B_LOCAL * row_bytes
+                        + (world - 1) * T * B_LOCAL * row_bytes)
     t_step = ms / args.steps * 1e-3
     mod_exchange = mod.exchange
+    mod_peer_forward = mod.peer_forward
     phases = None
     if graph:
         step = eager_step
@@ -170,7 +181,8 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 row-wise sharded over {world} GPU(s), "
                                    f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
-                       "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange},
+                       "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange,
+                       "peer_forward": mod_peer_forward if mod_exchange == "peer" else None},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
             "gpu_launches": (launches_per_step * args.steps if graph else N.launch_count() - launches0),
@@ -217,6 +229,11 @@ def phase_bench(world, rank, dev, rows_per_gpu=25_000_000, reps=10):
                                                      **batching))
     timed("bucket_push", lambda: ops.peer_bucket_push(pg, flat, num_rows=n_rows, **batching))
     timed("grads_push", lambda: ops.peer_allgather_push(pg, grad, int(pg.layout.off_grads)))
+    parts = pg.parts_view(DIM, torch.bfloat16)
+    timed("zero_parts", lambda: parts.zero_())
+    ops.peer_bucket_push(pg, flat, num_rows=n_rows, **batching)
+    timed("pool_push(owner pools inbox, stores partial rows)", lambda: ops.peer_pool_push(pg, DIM, torch.bfloat16))
+    timed("sum_partials", lambda: ops.sum_partials(parts))
     timed("barrier", lambda: ops.peer_barrier(pg, 0))
     plan = ops.peer_plan(pg, total_rows)
     timed("plan(unpack+sort)", lambda: ops.peer_plan(pg, total_rows))
@@ -235,8 +252,11 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default=None, choices=["route", "gather", "peer"])
     ap.add_argument("--phase-bench", action="store_true", help="time the phases of the peer exchange one by one")
+    ap.add_argument("--peer-forward", default=None, choices=["pull", "push"])
     ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (peer exchange only)")
     args = ap.parse_args()
+    global PEER_FORWARD
+    PEER_FORWARD = args.peer_forward
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

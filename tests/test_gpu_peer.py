@@ -134,6 +134,49 @@ def test_peer_backward_exchange(world, tables):
         torch.testing.assert_close(w_o.cpu(), w_want, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("world,tables", [(1, 1), (2, 1), (8, 1), (4, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_peer_push_forward(world, tables, dtype):
+    """Push forward: every virtual sender buckets into the owners' inboxes, every owner pools its
+    inbox and stores the partial rows into the senders' parts regions, every sender sums them."""
+    n_rows, dim, b, p = 30011, 64, 301, 20
+    m = tables * b
+    torch.manual_seed(world + 20)
+    full = torch.randn(tables, n_rows, dim).to(dtype)
+    shards, arenas, groups = make_groups(world, full.float(), m * p, m, dtype)
+    batching = dict(bags_per_table=b if tables > 1 else 0, num_tables=tables if tables > 1 else 0)
+    inputs = []
+    for r in range(world):
+        ids = seeded_ids(m * p, 60 + r, (m, p))
+        lengths = torch.randint(0, p + 1, (m,), generator=torch.Generator().manual_seed(40 + r))
+        groups[r].parts_view(dim, dtype).zero_()
+        ops.peer_bucket_push(groups[r], ids.to(DEV), num_rows=n_rows, lengths=lengths.to(DEV), **batching)
+        inputs.append((ids, lengths))
+    for o in range(world):                      # (barrier) owners pool and push
+        ops.peer_pool_push(groups[o], dim, dtype)
+    stacked = full.reshape(-1, dim).contiguous().to(DEV)
+    for r, (ids, lengths) in enumerate(inputs):  # (barrier) requesters sum in owner order
+        parts = groups[r].parts_view(dim, dtype)
+        got = ops.sum_partials(parts)
+        want = ops.pool_fwd(stacked, ids.to(DEV), lengths=lengths.to(DEV), num_rows=n_rows, **batching)
+        if world == 1:
+            assert torch.equal(got, want)        # one owner: same fp32 order as the unsharded sum
+        elif dtype == torch.float32:
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+        else:                                    # partials are rounded to bf16 before they travel
+            torch.testing.assert_close(got.float(), want.float(), rtol=1e-2, atol=8e-2)
+        # each partial equals the oracle's pool restricted to that owner's rows (fp32: exactly)
+        if dtype == torch.float32 and tables == 1:
+            rows = O.row_index(ids, n_rows, 0)
+            use = torch.arange(p).unsqueeze(0) < lengths.unsqueeze(1)
+            for o in range(world):
+                sel = use & (rows % world == o)
+                ref = torch.zeros(m, dim)
+                for j in range(p):
+                    ref = torch.where(sel[:, j:j + 1], ref + full[0].float()[rows[:, j]], ref)
+                assert torch.equal(parts[o].cpu(), ref)
+
+
 def test_peer_inbox_overflow_sets_status():
     world, n_rows, dim, m, p = 4, 1009, 32, 64, 20
     full = torch.randn(1, n_rows, dim)
@@ -174,6 +217,28 @@ def test_peer_module_single_rank_matches_other_exchanges(mode, tables):
     assert torch.equal(oa2, oa)
     oa2.backward(go)
     torch.testing.assert_close(a.emb.weight.grad, c.emb.weight.grad, rtol=1e-5, atol=1e-6)
+    a.peer_group().raise_on_status(synchronize=True)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_peer_module_push_forward_single_rank(mode):
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    n_rows, dim, b, p, tables = 9973, 64, 257, 20, 3
+    ids = seeded_ids(tables * b * p, 74, (tables, b, p)).to(DEV)
+    lengths = torch.randint(0, p + 1, (tables, b), generator=torch.Generator().manual_seed(6)).to(DEV)
+    a = RowWiseShardedEmbeddingBag(n_rows, dim, mode=mode, exchange="peer", peer_forward="push", num_tables=tables,
+                                   device=DEV)
+    c = RowWiseShardedEmbeddingBag(n_rows, dim, mode=mode, exchange="gather", num_tables=tables, device=DEV)
+    c.load_state_dict(a.state_dict())
+    go = torch.randn(tables, b, dim, device=DEV)
+    for _ in range(2):
+        a.emb.weight.grad = None
+        c.emb.weight.grad = None
+        oa, oc = a(ids, lengths), c(ids, lengths)
+        torch.testing.assert_close(oa, oc, rtol=1e-6, atol=1e-6)
+        oa.backward(go)
+        oc.backward(go)
+        torch.testing.assert_close(a.emb.weight.grad, c.emb.weight.grad, rtol=1e-5, atol=1e-6)
     a.peer_group().raise_on_status(synchronize=True)
 
 
