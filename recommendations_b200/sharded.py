@@ -535,15 +535,52 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         self._peer_dirty = True
 
     @torch.no_grad()
-    def gather_full_weight(self) -> torch.Tensor:
-        """Global [N, D] ([T, N, D]) table under the unsharded module's key (checkpoint / export)."""
+    def _gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        """[T * local_rows, ...] of every rank -> global [T, N, ...] (row r of rank s = global row r * W + s)."""
         w, t = self.comm.world, self.num_tables
         rows_max = local_rows_of(self.num_embeddings, w, 0)
-        mine = self.emb.weight.view(t, self.local_rows, self.emb_dim)
-        pad = torch.zeros((t, rows_max, self.emb_dim), dtype=mine.dtype, device=mine.device)
+        tail = tuple(local.shape[1:])
+        mine = local.reshape((t, self.local_rows) + tail)
+        pad = torch.zeros((t, rows_max) + tail, dtype=mine.dtype, device=mine.device)
         pad[:, :self.local_rows] = mine
-        shards = self.comm.all_gather(pad)                                  # [W, T, rows_max, D]
-        full = torch.empty((t, self.num_embeddings, self.emb_dim), dtype=pad.dtype, device=pad.device)
+        shards = self.comm.all_gather(pad)                                  # [W, T, rows_max, ...]
+        full = torch.empty((t, self.num_embeddings) + tail, dtype=pad.dtype, device=pad.device)
         for s in range(w):
             full[:, s::w] = shards[s, :, :local_rows_of(self.num_embeddings, w, s)]
         return full[0] if t == 1 else full
+
+    @torch.no_grad()
+    def gather_full_weight(self) -> torch.Tensor:
+        """Global [N, D] ([T, N, D]) table under the unsharded module's key (checkpoint / export)."""
+        return self._gather_rows(self.emb.weight)
+
+    @torch.no_grad()
+    def gather_full_optimizer_state(self) -> dict:
+        """Fused-optimizer state of the GLOBAL table(s), laid out like an unsharded EmbeddingTable's
+        (`state1` [N] for row-wise Adagrad, [N, D] otherwise; `state2` for Adam) + the step count:
+        what a rank-0 checkpoint stores next to gather_full_weight() (collective)."""
+        if self.emb.fused is None:
+            raise N.NativeError("gather_full_optimizer_state needs the fused optimizer mode")
+        self.emb._ensure_state()
+        out = {"kind": self.emb.fused.kind, "step": self.emb.fused_step}
+        for name, key in (("opt_state1", "state1"), ("opt_state2", "state2")):
+            buf = self.emb._buffers.get(name)
+            out[key] = None if buf is None else self._gather_rows(buf)
+        return out
+
+    @torch.no_grad()
+    def load_full_optimizer_state(self, state: dict) -> None:
+        """Inverse of gather_full_optimizer_state: every rank keeps the rows it owns (resume, also
+        onto a different world size)."""
+        if self.emb.fused is None or state["kind"] != self.emb.fused.kind:
+            raise N.NativeError("optimizer kind of the checkpoint does not match this module")
+        self.emb._ensure_state()
+        self.emb.fused_step = int(state["step"])
+        t, w, r = self.num_tables, self.comm.world, self.comm.rank
+        for name, key in (("opt_state1", "state1"), ("opt_state2", "state2")):
+            buf = self.emb._buffers.get(name)
+            if buf is None:
+                continue
+            full = state[key]
+            full = full.reshape((t, self.num_embeddings) + tuple(full.shape[(1 if t == 1 else 2):]))
+            buf.copy_(full[:, r::w].reshape(buf.shape).to(buf.device, buf.dtype))

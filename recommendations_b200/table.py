@@ -189,3 +189,40 @@ class FusedEmbeddingOptimizer(torch.optim.Optimizer):
         return {i: {"step": t.fused_step,
                     "state1": t._buffers.get("opt_state1"),
                     "state2": t._buffers.get("opt_state2")} for i, t in enumerate(self.tables)}
+
+    # Checkpoint / resume through the standard optimizer API (the reference saves optimizers with
+    # accelerator.save_state, accelerate_training_strategy.py:260-266; resume was absent there):
+    # the in-kernel optimizer state of every table travels inside state_dict()["fused"].
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["fused"] = {i: {"kind": t.fused.kind, "step": t.fused_step,
+                           "state1": None if st["state1"] is None else st["state1"].detach().clone(),
+                           "state2": None if st["state2"] is None else st["state2"].detach().clone()}
+                       for (i, t), st in zip(enumerate(self.tables), self.fused_state_dict().values())}
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        fused = state_dict.pop("fused", None)
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            for t in self.tables:
+                t.fused.lr = float(group["lr"])
+        if fused is None:
+            return
+        if len(fused) != len(self.tables):
+            raise ValueError(f"checkpoint holds {len(fused)} fused tables, optimizer has {len(self.tables)}")
+        for i, t in enumerate(self.tables):
+            rec = fused[i] if i in fused else fused[str(i)]
+            if rec["kind"] != t.fused.kind:
+                raise ValueError(f"table {i}: checkpoint optimizer {rec['kind']!r} != {t.fused.kind!r}")
+            t.fused_step = int(rec["step"])
+            t._ensure_state()
+            for name, key in (("opt_state1", "state1"), ("opt_state2", "state2")):
+                buf = t._buffers.get(name)
+                if buf is None:
+                    continue
+                if rec[key] is None or tuple(rec[key].shape) != tuple(buf.shape):
+                    raise ValueError(f"table {i}: optimizer state {key} missing or of the wrong shape")
+                buf.copy_(rec[key].to(buf.device, buf.dtype))

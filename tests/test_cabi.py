@@ -67,3 +67,65 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(N, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(N.NativeLibraryMissing):
         N.load()
+
+
+def test_peer_arena_layout_is_pure_host_arithmetic():
+    """recemb_peer_arena_layout: regions in order, 256-byte aligned, sized for world x cap entries and
+    two [world, bags, dim] row buffers (gathered gradients, partial pools)."""
+    lib = N.load()
+    a = N.PeerArena()
+    assert lib.recemb_peer_arena_layout(8, 245824, 65536, 128, N.BF16, C.byref(a)) == 0
+    offs = [a.off_flags, a.off_epoch, a.off_status, a.off_counts, a.off_inbox, a.off_grads, a.off_parts, a.bytes]
+    assert offs == sorted(offs) and len(set(offs)) == len(offs)
+    assert all(o % 128 == 0 for o in offs) and a.off_inbox % 256 == 0 and a.off_grads % 256 == 0
+    assert a.off_epoch - a.off_flags >= 2 * 16 * 8                  # 2 barrier channels x 16 ranks x u64
+    assert a.off_grads - a.off_inbox >= 8 * 245824 * 8
+    assert a.off_parts - a.off_grads >= 8 * 65536 * 128 * 2
+    assert a.bytes - a.off_parts >= 8 * 65536 * 128 * 2
+    assert (a.cap, a.bags_total) == (245824, 65536)
+    # bad arguments are codes, not crashes
+    assert lib.recemb_peer_arena_layout(0, 16, 16, 128, N.BF16, C.byref(a)) == -1
+    assert lib.recemb_peer_arena_layout(17, 16, 16, 128, N.BF16, C.byref(a)) == -1
+    assert lib.recemb_peer_arena_layout(2, 16, 16, 3, N.F32, C.byref(a)) == -3    # row not a 16-byte multiple
+    assert C.sizeof(N.PeerGroupStruct) == 8 + 2 * 16 * 8
+    assert int(re.search(r"#define RECEMB_MAX_PEERS (\d+)", HEADER).group(1)) == N.MAX_PEERS
+
+
+def test_peer_entry_points_validate_before_touching_the_gpu():
+    lib = N.load()
+    g = N.PeerGroupStruct()
+    a = N.PeerArena()
+    lib.recemb_peer_arena_layout(2, 64, 16, 64, N.F32, C.byref(a))
+    g.world, g.rank = 2, 5                                            # rank outside the group
+    assert lib.recemb_peer_barrier(C.byref(g), C.byref(a), 0, 0, None) == -1
+    g.rank = 0                                                        # arenas not mapped
+    assert lib.recemb_peer_barrier(C.byref(g), C.byref(a), 0, 0, None) == -1
+    assert b"arena" in lib.recemb_last_error()
+    assert lib.recemb_peer_barrier(C.byref(g), C.byref(a), 7, 0, None) == -1     # channel out of range
+    assert lib.recemb_peer_pool_fwd(None, 10, 64, N.F32, None, 4, 2, None, 0, None, N.HASH_FLOORMOD, 0,
+                                    N.POOL_SUM, 0, 0, None, None, 0, None) == -1
+    assert lib.recemb_peer_allgather_push(C.byref(g), None, 32, 0, 0, None) == -1
+    assert lib.recemb_peer_plan(None, None, 10, None, 0, 0, None) == -1
+
+
+def test_sharded_module_peer_capacity_and_modes():
+    """Host logic of the peer exchange that needs no GPU: inbox capacity, forward-mode default."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag, SingleProcess
+
+    class FakeComm(SingleProcess):
+        def __init__(self, world, rank):
+            super().__init__()
+            self.world, self.rank = world, rank
+
+    one = RowWiseShardedEmbeddingBag(1000, 16, exchange="peer", comm=FakeComm(1, 0))
+    assert one.peer_forward == "pull" and one.peer_capacity(1000) == 1000
+    eight = RowWiseShardedEmbeddingBag(1000, 16, exchange="peer", comm=FakeComm(8, 3))
+    assert eight.peer_forward == "push"
+    cap = eight.peer_capacity(1_310_720)
+    assert cap % 2 == 0 and 1.5 * 1_310_720 / 8 <= cap <= 1.5 * 1_310_720 / 8 + 66
+    skew = RowWiseShardedEmbeddingBag(1000, 16, exchange="peer", comm=FakeComm(8, 3), capacity_factor=100.0)
+    assert skew.peer_capacity(4096) == 4096                           # never more than a rank can send
+    with pytest.raises(ValueError):
+        RowWiseShardedEmbeddingBag(1000, 16, exchange="peer", comm=FakeComm(2, 0), peer_forward="sideways")
+    with pytest.raises(N.NativeError):
+        one.peer_group()                                              # built on the first forward only

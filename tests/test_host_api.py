@@ -70,3 +70,31 @@ def test_bad_config_is_rejected():
         R.FusedOptimizerConfig(kind="lion")
     with pytest.raises(ValueError):
         R.PooledEmbeddingBag(10, 4, mode="max")
+
+
+def test_fused_optimizer_checkpoint_round_trip():
+    """Optimizer-state save / resume through the standard torch API (CPU tensors: no kernel runs)."""
+    import io
+    import recommendations_b200 as R
+    from recommendations_b200.table import EmbeddingTable, FusedEmbeddingOptimizer
+
+    tabs = [EmbeddingTable(50, 8), EmbeddingTable(30, 8)]
+    opt = FusedEmbeddingOptimizer(tabs, kind="adagrad", lr=0.25)
+    for i, t in enumerate(tabs):
+        t._ensure_state()
+        t._buffers["opt_state1"].fill_(i + 1.5)
+        t.fused_step = 7 + i
+    buf = io.BytesIO()
+    torch.save(opt.state_dict(), buf)
+    buf.seek(0)
+    tabs2 = [EmbeddingTable(50, 8), EmbeddingTable(30, 8)]
+    opt2 = FusedEmbeddingOptimizer(tabs2, kind="adagrad", lr=0.5)
+    opt2.load_state_dict(torch.load(buf))
+    for i, t in enumerate(tabs2):
+        assert t.fused_step == 7 + i and t.fused.lr == 0.25
+        assert torch.equal(t._buffers["opt_state1"], torch.full((([50, 30][i]), 8), i + 1.5))
+    other = FusedEmbeddingOptimizer([EmbeddingTable(50, 8), EmbeddingTable(30, 8)], kind="rowwise_adagrad", lr=0.5)
+    with pytest.raises(ValueError, match="optimizer"):
+        other.load_state_dict(opt.state_dict())
+    # the tables' own state_dict keeps the reference keys only
+    assert set(tabs[0].state_dict().keys()) == {"weight"}

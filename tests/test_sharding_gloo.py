@@ -120,6 +120,22 @@ def _worker(rank, world, port, mode, last_n, exchange, result):
             pooled.backward(gg)
         torch.testing.assert_close(mod.emb.weight.grad, wr.grad[rank::world], rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(mod.gather_full_weight(), full)
+        # checkpoint of the fused-optimizer state: global layout out, owned rows back in
+        from recommendations_b200.table import FusedOptimizerConfig
+        for kind, shape in (("rowwise_adagrad", (N_ROWS,)), ("adam", (N_ROWS, DIM))):
+            fm = RowWiseShardedEmbeddingBag(N_ROWS, DIM, exchange=exchange, fused_optimizer=FusedOptimizerConfig(kind=kind),
+                                            **_make_hooks(world, rank, last_n))
+            glob = torch.arange(N_ROWS, dtype=torch.float32)
+            glob = glob if len(shape) == 1 else glob.unsqueeze(1).expand(*shape).contiguous()
+            state = {"kind": kind, "step": 5, "state1": glob, "state2": glob * 2 if kind == "adam" else None}
+            fm.load_full_optimizer_state(state)
+            assert fm.emb.fused_step == 5
+            assert torch.equal(fm.emb._buffers["opt_state1"].reshape(-1)[:3],
+                               glob[rank::world].reshape(-1)[:3])
+            back = fm.gather_full_optimizer_state()
+            assert back["step"] == 5 and torch.equal(back["state1"], glob)
+            if kind == "adam":
+                assert torch.equal(back["state2"], glob * 2)
         result[rank] = 1
     finally:
         dist.destroy_process_group()
