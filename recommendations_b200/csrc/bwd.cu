@@ -403,6 +403,9 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
     if (chunk == num_chunks - 1) a.out_keys[2 * chunk + 1] = kNoKey;
   }
 
+  // dropped slots (pad ids, positions outside a bag's window, unused inbox capacity) carry the
+  // sentinel key and sort last: a chunk that starts with one holds nothing else
+  if (L0 && a.keys[start] >= a.sentinel) return;
   const int upd = Cfg::UPD >= 0 ? Cfg::UPD : a.update;
   const GT* gbase = reinterpret_cast<const GT*>(a.grad) + lig * E;
   const WT* tbase = reinterpret_cast<const WT*>(a.table) + lig * E;
@@ -603,6 +606,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
     a.out_keys[2 * chunk] = kNoKey;
     if (chunk == num_chunks - 1) a.out_keys[2 * chunk + 1] = kNoKey;
   }
+  if (a.keys[start] >= a.sentinel) return;  // sentinel keys sort last: nothing but dropped slots here
   const T* gbase = reinterpret_cast<const T*>(a.grad) + lig * E;
   T* tbase = reinterpret_cast<T*>(a.table) + lig * E;
   const recemb_optim_params& hp = a.hp;
@@ -891,6 +895,8 @@ static int launch_seg(const SegArgs& a, QuadShape shape, cudaStream_t s) {
         else if (plain && tb == 2 && tp == 0) launched = launch_pre<16, WT, true, 2, 0, 4>(a, s);
         else if (plain && tb == 2 && tp == 2) launched = launch_pre<16, WT, true, 2, 2, 4>(a, s);
         else if (plain) launched = launch_pre<16, WT, true, 2, 1, 4>(a, s);
+        else if (tb == 2 && tp == 0) launched = launch_pre<16, WT, false, 2, 0, 4>(a, s);
+        else if (tb == 4) launched = launch_pre<16, WT, false, 4, 0, 3>(a, s);
         else launched = launch_pre<16, WT, false, 2, 1, 4>(a, s);
       } else {
         if (plain) launched = launch_pre<32, WT, true, 2, 2, 4>(a, s);
