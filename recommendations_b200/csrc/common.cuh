@@ -191,6 +191,16 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// 128-bit read-only load that MAY stay in L1: for rows a whole batch keeps hitting (the k-shift
+// collapse rows [N - 2^(c-1), N), Zipf heads) -- served from every SM's L1 instead of all SMs
+// queueing on the one or two L2 slices that hold the row
+__device__ __forceinline__ uint4 ldg_nc_l1_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 // streaming (evict-first) 128-bit store for write-once outputs
 __device__ __forceinline__ void stg_cs_v4(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),

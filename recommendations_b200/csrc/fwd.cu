@@ -86,6 +86,7 @@ struct GatherArgs {
   int64_t pad_id;
   int bulk_ok;
   int prefetch_iters;  // L2 prefetch distance in warp iterations (0 = off)
+  int l1_rows;         // rows may stay in L1 (skewed ids: hot rows are re-read by every SM)
 };
 
 template <int G, int V, typename T, int EPI, bool TWO>
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
         for (int j = 0; j < V; ++j) {
           const int vec = j * G + lig;
           v[u][j] = make_uint4(0, 0, 0, 0);
-          if (r >= 0 && vec < a.row_vecs) v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+          if (r >= 0 && vec < a.row_vecs)
+            v[u][j] = a.l1_rows ? ldg_nc_l1_v4(a.table + r * a.row_vecs + vec) : ldg_nc_v4(a.table + r * a.row_vecs + vec);
           if (TWO) {
             w[u][j] = make_uint4(0, 0, 0, 0);
             if (r2 >= 0 && vec < a.row_vecs) w[u][j] = ldg_nc_v4(a.table2 + r2 * a.row_vecs + vec);
@@ -230,6 +232,7 @@ struct KShiftArgs {
   float sqrt_k;
   int bulk_ok;
   uint32_t flip_len;
+  int l1_hot;  // rows of shifts >= 1 may stay in L1
 };
 
 template <int G, int V, typename T>
@@ -285,8 +288,12 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
             for (int j = 0; j < V; ++j) {
               const int vec = j * G + lig;
               v[u][j] = make_uint4(0, 0, 0, 0);
-              if (live && cc < span && vec < a.row_vecs)
-                v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+              if (live && cc < span && vec < a.row_vecs) {
+                // shift c >= 1 sends every negative id to one of 2^(c-1) rows (commons/layers.py:182,
+                // arithmetic >>): those rows are read by every SM all the time -> keep them in L1
+                if (a.l1_hot && c0 + cc > 0) v[u][j] = ldg_nc_l1_v4(a.table + r * a.row_vecs + vec);
+                else v[u][j] = ldg_nc_v4(a.table + r * a.row_vecs + vec);
+              }
             }
           }
 #pragma unroll
@@ -684,6 +691,17 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
     }
     a.prefetch_iters = pf;
   }
+  {
+    // rows may stay in L1 (evict_last): Zipf heads are then served by every SM's L1 instead of
+    // the one L2 slice that holds them (cfg 4 fwd 2.53 -> 2.47 ms); neutral-to-better for uniform
+    // ids (cfg 2 step 3.82 -> 3.77 ms).  RECEMB_GATHER_L1=0 restores L1::no_allocate.
+    static int l1 = -1;
+    if (l1 < 0) {
+      const char* e = getenv("RECEMB_GATHER_L1");
+      l1 = e ? atoi(e) : 1;
+    }
+    a.l1_rows = l1;
+  }
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   const int64_t tiles = (n + kTileIds - 1) / kTileIds;
@@ -720,6 +738,14 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
   RECEMB_CHECK_ARG(flip_len >= 0 && (flip_len == 0 || n % flip_len == 0), "n is not a multiple of flip_len");
   a.flip_len = (uint32_t)flip_len;
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
+  {
+    static int l1 = -1;  // RECEMB_KSHIFT_L1=0 turns the L1 residency of the collapse rows off
+    if (l1 < 0) {
+      const char* e = getenv("RECEMB_KSHIFT_L1");
+      l1 = e ? atoi(e) : 1;
+    }
+    a.l1_hot = l1;
+  }
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
   const int64_t tiles = (n + kTileIds - 1) / kTileIds;
