@@ -117,10 +117,12 @@ typedef struct recemb_optim_params {
   float beta2;
   float bias_correction1; /* 1 - beta1^step (host-computed) */
   float bias_correction2; /* 1 - beta2^step */
-  float grad_div;         /* > 0: every gradient element is divided by it (IEEE division) before the
+  float grad_div;         /* > 0: every gradient element is scaled by 1 / grad_div before the
                              reduction -- the backward of KShiftEmbedding's x / sqrt(num_shifts)
                              (commons/layers.py:170) folded into the segmented reduction instead of
-                             a separate pass that materialises dx; 0 = off */
+                             a separate pass that materialises dx (one multiply by the rounded
+                             reciprocal: <= 1 ulp from the reference's division, exact when
+                             sqrt(num_shifts) is a power of two, e.g. k = 4, 16); 0 = off */
 } recemb_optim_params;
 
 /* ---- library info -------------------------------------------------------- */

@@ -620,8 +620,10 @@ def test_cfg1_lthm_product_front_end():
                                          (24, torch.float32, 3)])
 @pytest.mark.parametrize("update", ["dense_grad", "adagrad", "rowwise_adagrad"])
 def test_grad_div_equals_materialised_epilogue_backward(dim, dtype, k, update):
-    """The x / sqrt(k) backward folded into the segmented reduction (grad_div) is bit-identical to
-    running epilogue_bwd first and reducing its fp32 dx rows (commons/layers.py:170 autograd)."""
+    """The x / sqrt(k) backward folded into the segmented reduction (grad_div: one multiply by the
+    rounded reciprocal) equals running epilogue_bwd (true division) first and reducing its fp32 dx
+    rows (commons/layers.py:170 autograd): bit-identical when sqrt(k) is a power of two (k = 4, 16),
+    within 1 ulp per gradient element otherwise."""
     n, n_rows = 5003, 997
     ids = seeded_ids(n, 123).to(DEV)
     grad = torch.randn(n, dim, generator=torch.Generator().manual_seed(9)).to(dtype).to(DEV)
@@ -643,11 +645,18 @@ def test_grad_div_equals_materialised_epilogue_backward(dim, dtype, k, update):
             dx = ops.epilogue_bwd(grad, None, None, N.EPI_RSQRT_K, k)
             ops.bwd_apply(plan, dx, table=w, update=N.UPDATE_BY_NAME[update], state1=st, slots_per_grad_row=k, hp=hp)
         results.append((w, st))
-    if update == "rowwise_adagrad" and dtype == torch.bfloat16:
+    if math.sqrt(k) != int(math.sqrt(k)) and update != "rowwise_adagrad":
+        # reciprocal multiply vs division: <= 1 ulp per TERM; the collapse rows sum thousands of
+        # terms of magnitude ~1 that largely cancel, so the bound is absolute (1e-5 of the sum's scale)
+        torch.testing.assert_close(results[0][0].float(), results[1][0].float(), rtol=1e-5, atol=2e-4)
+        if results[0][1] is not None:   # state = (sum)^2: twice the relative error of a cancelling sum
+            torch.testing.assert_close(results[0][1], results[1][1], rtol=1e-4, atol=1e-4)
+        return
+    if update == "rowwise_adagrad" and (dtype == torch.bfloat16 or math.sqrt(k) != int(math.sqrt(k))):
         # bf16 gradients take the 16-byte-per-lane instantiation: the row's mean of squares is
         # reduced over a different lane grouping than with fp32 dx rows -> equal within rounding
         torch.testing.assert_close(results[0][0].float(), results[1][0].float(), rtol=1e-2, atol=1e-2)
-        torch.testing.assert_close(results[0][1], results[1][1], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(results[0][1], results[1][1], rtol=1e-4, atol=1e-4)
         return
     assert torch.equal(results[0][0], results[1][0])
     if results[0][1] is not None:
