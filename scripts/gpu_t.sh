@@ -1,2 +1,7 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_parity.py -q 2>&1 | grep -E "^FAILED|passed|failed|Error" | head -20
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+fails=0
+for i in $(seq 1 25); do
+  python __graft_entry__.py --smoke > /tmp/smoke_$i.log 2>&1 || { fails=$((fails+1)); echo "run $i FAILED"; tail -12 /tmp/smoke_$i.log; }
+done
+echo "smoke failures: $fails / 25"
