@@ -213,11 +213,16 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
                                                             int64_t batch, int F) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NB = DIM / 64;            // MN atoms (64 dims each) of the B operand
-  constexpr int STG = DIM * 2 + 16;       // padded staging row (bytes)
+  constexpr int STG = DIM * 2;            // staging row (bytes); 16-byte chunks XOR-swizzled by the row
+  constexpr int CHS = DIM / 8;            // 16-byte chunks per staging row (8 or 16: a power of two)
   uint8_t* s_tile = smem;                 // B operand: NB x 16 KB (rows = K index, 128 B = 64 dims)
   uint8_t* s_a = smem + NB * kKBlockBytes;            // A = blockdiag(G+G^T): 2 K-blocks x 16 KB
-  uint8_t* s_stage = s_a + 2 * kKBlockBytes;          // 128 x STG
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + ((128 * STG + 15) & ~15));
+  // the output staging (128 x STG = the size of the B operand) reuses the B operand's memory: it is
+  // written after the MMAs have committed (B is dead) and the next tile reloads B anyway.  64 KB per
+  // CTA instead of 99 KB: 3 CTAs (12 warps, 3 x 128 TMEM columns) per SM overlap load / MMA / epilogue
+  uint8_t* s_stage = s_tile;
+  uint16_t* s_ij = reinterpret_cast<uint16_t*>(s_a + 2 * kKBlockBytes);   // e -> (i << 8 | j), P entries
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + 2 * kKBlockBytes + 1024);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
   constexpr uint32_t TMEM_COLS = DIM <= 64 ? 64 : (DIM <= 128 ? 128 : 256);
 
@@ -231,6 +236,13 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
   // the off-diagonal blocks of A are zero for every tile: clear once
   for (int i = threadIdx.x; i < 2 * kKBlockBytes / 16; i += kIxThreads)
     reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0, 0, 0, 0);
+  // triangle index e = i(i-1)/2 + j -> (i, j), once per CTA instead of a sqrt per element per tile
+  for (int e = threadIdx.x; e < P; e += kIxThreads) {
+    int i = (int)((1.f + sqrtf(1.f + 8.f * (float)e)) * 0.5f);
+    while (i * (i - 1) / 2 > e) --i;
+    while ((i + 1) * i / 2 <= e) ++i;
+    s_ij[e] = (uint16_t)((i << 8) | (e - i * (i - 1) / 2));
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -243,12 +255,8 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
     load_feature_tile<DIM>(s_tile, feats, tile, batch, F);
     // A[(s,i)][(s,j)] = A[(s,j)][(s,i)] = grad_out[b, i(i-1)/2 + j]
     for (int idx = threadIdx.x; idx < kIxSamples * P; idx += kIxThreads) {
-      const int s = idx / P, e = idx % P;
-      // invert e = i(i-1)/2 + j
-      int i = (int)((1.f + sqrtf(1.f + 8.f * (float)e)) * 0.5f);
-      while (i * (i - 1) / 2 > e) --i;
-      while ((i + 1) * i / 2 <= e) ++i;
-      const int j = e - i * (i - 1) / 2;
+      const int s = idx / P, e = idx - s * P;
+      const int ij = s_ij[e], i = ij >> 8, j = ij & 0xff;
       const int64_t b = tile * kIxSamples + s;
       __nv_bfloat16 g = __float2bfloat16_rn(0.f);
       if (b < batch) g = grad_out[b * P + e];
@@ -276,7 +284,10 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
     tc_fence_after();
 
     // lane i of warp w holds row (sample w, feature i): DIM fp32 columns -> bf16 staging row
-    uint8_t* srow = s_stage + (warp * 32 + lane) * STG;
+    // (chunk c of row r lives at chunk position c ^ (r % CHS): the 32 lanes of a warp write 32
+    // different rows at the same logical chunk -> spread over all chunk positions, no bank pile-up)
+    const int srow_i = warp * 32 + lane;
+    uint8_t* srow = s_stage + srow_i * STG;
 #pragma unroll
     for (int c0 = 0; c0 < DIM; c0 += 32) {
       float v[32];
@@ -289,7 +300,8 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
           __nv_bfloat162 p = __floats2bfloat162_rn(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]);
           w[t] = *reinterpret_cast<uint32_t*>(&p);
         }
-        *reinterpret_cast<uint4*>(srow + (c0 + q * 8) * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(srow + ((((c0 >> 3) + q) ^ (srow_i & (CHS - 1))) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     tc_fence_before();
@@ -299,7 +311,8 @@ __global__ void __launch_bounds__(kIxThreads) dot_bwd_kernel(const __nv_bfloat16
     for (int idx = threadIdx.x; idx < nsamp * F * CH; idx += kIxThreads) {
       const int c = idx % CH, rowi = idx / CH;
       const int s = rowi / F, i = rowi % F;
-      const uint4 val = *reinterpret_cast<const uint4*>(s_stage + (s * 32 + i) * STG + c * 16);
+      const int sr = s * 32 + i;
+      const uint4 val = *reinterpret_cast<const uint4*>(s_stage + sr * STG + ((c ^ (sr & (CHS - 1))) << 4));
       stg_cs_v4(grad_feats + ((tile * kIxSamples + s) * F + i) * DIM + c * 8, val);
     }
     __syncthreads();
@@ -314,7 +327,8 @@ static size_t fwd_smem(int dim, int F) {
   return (size_t)(dim / 64) * kKBlockBytes + ((kIxSamples * P * 2 + 15) & ~15) + 32;
 }
 static size_t bwd_smem(int dim) {
-  return (size_t)(dim / 64) * kKBlockBytes + 2 * kKBlockBytes + ((128 * (dim * 2 + 16) + 15) & ~15) + 32;
+  // B operand (also the output staging) + A + (i, j) table (1 KB) + barrier / TMEM slot
+  return (size_t)(dim / 64) * kKBlockBytes + 2 * kKBlockBytes + 1024 + 32;
 }
 
 }  // namespace recemb
@@ -363,7 +377,7 @@ extern "C" int recemb_dot_interaction_bwd(const void* feats, const void* grad_ou
   RECEMB_CUDA(g.err);
   const size_t smem = bwd_smem(dim);
   const int64_t tiles = (batch + kIxSamples - 1) / kIxSamples;
-  int64_t grid = (int64_t)sm_count(device) * 2;
+  int64_t grid = (int64_t)sm_count(device) * 3;
   if (grid > tiles) grid = tiles;
   cudaStream_t s = (cudaStream_t)stream;
 #define LAUNCH_BWD(D_)                                                                                  \

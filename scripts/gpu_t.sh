@@ -1,7 +1,6 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-fails=0
-for i in $(seq 1 25); do
-  python __graft_entry__.py --smoke > /tmp/smoke_$i.log 2>&1 || { fails=$((fails+1)); echo "run $i FAILED"; tail -12 /tmp/smoke_$i.log; }
-done
-echo "smoke failures: $fails / 25"
+timeout 300 python -m pytest tests/test_gpu_interaction.py -q 2>&1 | tail -3
+timeout 300 python scripts/bench_configs.py cfg3 2>&1 | grep "interaction" | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['name'][:40], d['ms'], d['frac_of_measured_hbm'])"
