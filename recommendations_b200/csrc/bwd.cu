@@ -630,14 +630,12 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
       if (u < B) ss[u] = i < a.n ? a.slots[i] : 0u;
     }
   };
-  auto prefetch_batch = [&](int e0) {
-    if (e0 >= end) return;
-    uint32_t kk[B + 1], ss[B];
-    load_meta(e0, kk, ss);
+  // L2 prefetch of what a batch will touch, from its (already loaded) meta data
+  auto prefetch_meta = [&](int e0, const uint32_t(&kk)[B + 1], const uint32_t(&gr)[B]) {
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       if (e0 + u < end && kk[u] < a.sentinel) {
-        prefetch_vec<T, E>(gbase + (size_t)grad_row_of(ss[u]) * a.dim);
+        prefetch_vec<T, E>(gbase + (size_t)gr[u] * a.dim);
         if (kk[u + 1] != kk[u]) {
           prefetch_vec<T, E>(tbase + (size_t)kk[u] * a.dim);
           if (UPD == RECEMB_UPD_ROWWISE_ADAGRAD && lig == 0) prefetch_l2(a.state1 + kk[u]);
@@ -645,8 +643,17 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
       }
     }
   };
+  auto load_batch = [&](int e0, uint32_t(&kk)[B + 1], uint32_t(&ss)[B], uint32_t(&gr)[B]) {
+    load_meta(e0, kk, ss);
 #pragma unroll
-  for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
+    for (int u = 0; u < B; ++u) gr[u] = grad_row_of(ss[u]);
+  };
+  auto prefetch_batch = [&](int e0) {
+    if (e0 >= end) return;
+    uint32_t kk[B + 1], ss[B], gr[B];
+    load_batch(e0, kk, ss, gr);
+    prefetch_meta(e0, kk, gr);
+  };
 
   const bool left_open = start > 0 && a.keys[start - 1] == a.keys[start];
   bool first = true;
@@ -654,10 +661,30 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
 
+  // The meta data (keys, slots, gradient rows) of batch b+1 is loaded while batch b is processed
+  // and carried in registers (PD == 1: the same data drives the L2 prefetch): no dependent key
+  // load at the top of an iteration and no second hash of the same slots -- the walk is
+  // issue-bound (61-75 % issue-active), not DRAM-bound.
+  uint32_t k[B + 1], sl[B], gr[B];
+  load_batch(start, k, sl, gr);
+  if (PD == 1) {
+    prefetch_meta(start, k, gr);
+  } else {
+#pragma unroll
+    for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
+  }
+
   for (int e0 = start; e0 < end; e0 += B) {
-    if (PD > 0) prefetch_batch(e0 + PD * B);
-    uint32_t k[B + 1], sl[B];
-    load_meta(e0, k, sl);
+    uint32_t nk[B + 1] = {}, ns[B] = {}, ngr[B] = {};
+    if (PD == 1) {
+      if (e0 + B < end) {
+        load_batch(e0 + B, nk, ns, ngr);
+        prefetch_meta(e0 + B, nk, ngr);
+      }
+    } else {
+      if (PD > 0) prefetch_batch(e0 + PD * B);
+      if (e0 > start) load_batch(e0, k, sl, gr);
+    }
     uint4 gv[B], wv[B];
     float sv[B], wt[B];
     bool closes[B];
@@ -670,7 +697,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
       wt[u] = 1.f;
       closes[u] = live && k[u + 1] != k[u];
       if (live) {
-        const uint32_t grow = grad_row_of(sl[u]);
+        const uint32_t grow = gr[u];
         gv[u] = ldg_nc_v4(gbase + (size_t)grow * a.dim);
         if (!PLAIN) {
           if (a.slot_weight) wt[u] = a.slot_weight[sl[u]];
@@ -747,6 +774,15 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
 #pragma unroll
           for (int e = 0; e < E; ++e) acc[e] = 0.f;
         }
+      }
+    }
+    if (PD == 1) {
+#pragma unroll
+      for (int u = 0; u <= B; ++u) k[u] = nk[u];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        sl[u] = ns[u];
+        gr[u] = ngr[u];
       }
     }
   }
