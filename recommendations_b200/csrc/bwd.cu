@@ -432,10 +432,8 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
       if (u < B) ss[u] = (L0 && in) ? a.slots[i] : 0u;
     }
   };
-  auto prefetch_batch = [&](int e0) {
-    if (e0 >= end) return;
-    uint32_t kk[B + 1], ss[B];
-    load_meta(e0, kk, ss);
+  // L2 prefetch of what a batch will touch, from its already loaded keys / slots
+  auto prefetch_from = [&](int e0, const uint32_t(&kk)[B + 1], const uint32_t(&ss)[B]) {
     if constexpr (L0 && EXACT) {
       if (a.pf_bulk) {
         if (lig == 0) {
@@ -478,11 +476,26 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
       }
     }
   };
+  auto prefetch_batch = [&](int e0) {
+    if (e0 >= end) return;
+    uint32_t kk[B + 1], ss[B];
+    load_meta(e0, kk, ss);
+    prefetch_from(e0, kk, ss);
+  };
 
+  // PD == 1: the keys / slots of batch b+1 are loaded while batch b is processed and carried in
+  // registers -- they drive the L2 prefetch and then the walk itself (no dependent key load at the
+  // top of an iteration; the non-plain walks are issue-bound, not DRAM-bound)
+  uint32_t k[B + 1], sl[B];
+  load_meta(start, k, sl);
+  if (PD == 1) {
+    prefetch_from(start, k, sl);
+  } else {
 #pragma unroll
-  for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
+    for (int d = 0; d < PD; ++d) prefetch_batch(start + d * B);
+  }
 
-  uint32_t cur = a.keys[start];
+  uint32_t cur = k[0];
   const bool left_open = start > 0 && a.keys[start - 1] == cur;
   bool first = true;
   float acc[V][E];
@@ -516,9 +529,16 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
   };
 
   for (int e0 = start; e0 < end; e0 += B) {
-    prefetch_batch(e0 + PD * B);
-    uint32_t k[B + 1], sl[B];
-    load_meta(e0, k, sl);
+    uint32_t nk[B + 1] = {}, ns[B] = {};
+    if (PD == 1) {
+      if (e0 + B < end) {
+        load_meta(e0 + B, nk, ns);
+        prefetch_from(e0 + B, nk, ns);
+      }
+    } else {
+      prefetch_batch(e0 + PD * B);
+      if (e0 > start) load_meta(e0, k, sl);
+    }
     float g[B][V][E];
     float wt[B];
 #pragma unroll
@@ -573,6 +593,12 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegAr
           }
         }
       }
+    }
+    if (PD == 1) {
+#pragma unroll
+      for (int u = 0; u <= B; ++u) k[u] = nk[u];
+#pragma unroll
+      for (int u = 0; u < B; ++u) sl[u] = ns[u];
     }
   }
   const bool right_open = end < a.n && a.keys[end] == cur;
