@@ -64,13 +64,16 @@ class PeerGroup:
         return torch.zeros((int(layout.bytes),), dtype=torch.uint8, device=device)
 
     @classmethod
-    def connect(cls, table: torch.Tensor, *, cap: int, bags_total: int, group=None) -> "PeerGroup":
-        """Collective: every rank of `group` calls it with its own shard."""
+    def connect(cls, table: torch.Tensor, *, cap: int, bags_total: int, group=None,
+                table_ptrs: Optional[Sequence[int]] = None) -> "PeerGroup":
+        """Collective: every rank of `group` calls it with its own shard.  `table_ptrs` (the mapped
+        shard pointers of an earlier group over the same table) skips the export / mapping of the
+        table: a second batch shape only needs a second arena."""
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = N.require_cuda(table)
         layout = arena_layout(world, cap, bags_total, table.shape[1], table.dtype)
         arena = cls.new_arena(layout, table.device)
-        mine = (export_handle(arena), export_handle(table))
+        mine = (export_handle(arena), export_handle(table) if table_ptrs is None else (b"", 0))
         everyone: List = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
         lib = N.load()
@@ -93,7 +96,7 @@ class PeerGroup:
                 tables.append(table.data_ptr())
             else:
                 arenas.append(resolve(ah, ao))
-                tables.append(resolve(th, to))
+                tables.append(resolve(th, to) if table_ptrs is None else int(table_ptrs[r]))
         self = cls(world, rank, arenas, tables, layout, arena, dev, opened)
         # nobody may touch a peer arena before every rank has zero-filled its own
         torch.cuda.synchronize(dev)
@@ -151,6 +154,9 @@ class PeerGroup:
                 "raise capacity_factor -- the ids are more skewed across ranks than the inbox allows")
         if st & STATUS_BARRIER_TIMEOUT:
             raise N.NativeError("peer exchange: device barrier timed out (a rank did not reach it within ~2 s)")
+
+    def table_ptrs(self) -> List[int]:
+        return [int(self.struct.table[i] or 0) for i in range(self.world)]
 
     def close(self) -> None:
         lib = N.load()

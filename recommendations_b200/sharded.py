@@ -255,7 +255,7 @@ class _PeerPoolFn(torch.autograd.Function):
         pg.raise_on_status()
         main = torch.cuda.current_stream(ids.device)
         _mark(module, "start")
-        ctx.plan, ctx.plan_ready = None, None
+        ctx.plan, ctx.plan_ready, ctx.pg = None, None, pg
         if module.peer_forward == "push":
             return _PeerPoolFn._forward_push(ctx, ids, lengths, module, pg, main)
         if module._peer_dirty:
@@ -337,7 +337,7 @@ class _PeerPoolFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         (scale,) = ctx.saved_tensors
         module = ctx.module
-        pg = module.peer_group()
+        pg = ctx.pg                      # the group (arena) of the batch shape this forward used
         g = grad_out.contiguous()
         if scale is not None:
             g = g * scale.unsqueeze(1).to(g.dtype)
@@ -345,6 +345,10 @@ class _PeerPoolFn(torch.autograd.Function):
             g = g.to(module.emb.weight.dtype)
         main = torch.cuda.current_stream(g.device)
         _mark(module, "bwd_start")
+        if module._peer_dirty:
+            # two backward passes without a forward in between (several outstanding forwards): the
+            # peers' previous update may still be reading the gradient buffer this pass overwrites
+            ops.peer_barrier(pg, channel=0)
         ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
         _mark(module, "grads_push")
         ops.peer_barrier(pg, channel=0)
@@ -472,15 +476,23 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         key = (w.data_ptr(), tuple(ids.shape))
         if self._peer is not None and self._peer_key == key:
             return
-        self.close_peer()
-        cap = self.peer_capacity(ids.numel())
-        if self.comm.world == 1:
-            layout = arena_layout(1, cap, ids.shape[0], self.emb_dim, w.dtype)
-            arena = PeerGroup.new_arena(layout, w.device)
-            self._peer = PeerGroup.local(1, 0, [arena], [w.detach()], layout)
-        else:
-            self._peer = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group)
-        self._peer_key = key
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        if cache and (next(iter(cache))[0] != w.data_ptr() or len(cache) >= 8):
+            self.close_peer()                      # the weight moved (or too many shapes): start over
+            cache = self.__dict__.setdefault("_peer_cache", {})
+        if key not in cache:
+            # a new batch shape (e.g. the last, smaller batch of an epoch) needs its own arena; the
+            # 51 GB shard stays mapped once
+            cap = self.peer_capacity(ids.numel())
+            if self.comm.world == 1:
+                layout = arena_layout(1, cap, ids.shape[0], self.emb_dim, w.dtype)
+                arena = PeerGroup.new_arena(layout, w.device)
+                cache[key] = PeerGroup.local(1, 0, [arena], [w.detach()], layout)
+            else:
+                first = next(iter(cache.values())) if cache else None
+                cache[key] = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group,
+                                               table_ptrs=None if first is None else first.table_ptrs())
+        self._peer, self._peer_key = cache[key], key
         self._peer_dirty = True
 
     def _side_stream(self, device) -> "torch.cuda.Stream":
@@ -490,15 +502,17 @@ class RowWiseShardedEmbeddingBag(nn.Module):
 
     def close_peer(self) -> None:
         """Collective: unmap the peers' memory (before this rank's shard / arena may be freed)."""
-        if self._peer is None:
+        cache = self.__dict__.get("_peer_cache") or {}
+        if self._peer is None and not cache:
             return
         torch.cuda.synchronize(self.emb.weight.device)
         if self.comm.world > 1:
             dist.barrier(group=self.comm.group)
-        self._peer.close()
+        for pg in cache.values():
+            pg.close()
         if self.comm.world > 1:
             dist.barrier(group=self.comm.group)
-        self._peer, self._peer_key = None, None
+        self._peer, self._peer_key, self._peer_cache = None, None, {}
 
     def _batching(self, ids_all):
         """gathered bags are [W, T, b]: bag g belongs to table (g // b) % T."""

@@ -78,6 +78,14 @@ def check(world, rank, dev, exchange=None):
         out2.backward(go.to(dev))
         torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
         mod.peer_group().raise_on_status(synchronize=True)
+        # a smaller batch (last batch of an epoch): second arena over the same mapped shards
+        first_group = mod.peer_group()
+        ids_s, len_s = ids[:, :101].contiguous(), lengths[:, :101].contiguous()
+        out_s = mod(ids_s.to(dev), len_s.to(dev))
+        assert mod.peer_group() is not first_group and mod.peer_group().table_ptrs() == first_group.table_ptrs()
+        torch.testing.assert_close(out_s.cpu(), out[:, :101].cpu(), rtol=1e-5, atol=1e-5)
+        out_s.sum().backward()
+        mod.peer_group().raise_on_status(synchronize=True)
     if rank == 0:
         print(f"[check] sharded == unsharded on {world} rank(s), exchange={mod.exchange}: ok", flush=True)
 

@@ -242,6 +242,30 @@ def test_peer_module_push_forward_single_rank(mode):
     a.peer_group().raise_on_status(synchronize=True)
 
 
+def test_peer_module_changing_batch_shapes():
+    """A second batch shape gets its own arena (cached), the first one keeps working afterwards."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    n_rows, dim, p = 9973, 64, 20
+    a = RowWiseShardedEmbeddingBag(n_rows, dim, exchange="peer", device=DEV)
+    c = RowWiseShardedEmbeddingBag(n_rows, dim, exchange="gather", device=DEV)
+    c.load_state_dict(a.state_dict())
+    groups = []
+    for b in (257, 31, 257, 64, 31):
+        ids = seeded_ids(b * p, 200 + b, (b, p)).to(DEV)
+        go = torch.randn(b, dim, device=DEV)
+        a.emb.weight.grad = None
+        c.emb.weight.grad = None
+        oa, oc = a(ids), c(ids)
+        assert torch.equal(oa, oc)
+        oa.backward(go)
+        oc.backward(go)
+        torch.testing.assert_close(a.emb.weight.grad, c.emb.weight.grad, rtol=1e-5, atol=1e-6)
+        groups.append(id(a.peer_group()))
+    assert groups[0] == groups[2] and groups[1] == groups[4] and len(set(groups)) == 3
+    a.close_peer()
+    assert a._peer is None and not a._peer_cache
+
+
 def test_peer_module_fused_step_in_cuda_graph():
     """The peer step has fixed shapes and no host synchronisation: forward + backward + fused
     row-wise Adagrad replay from one CUDA graph and match the eager steps."""
