@@ -155,3 +155,32 @@ def test_dot_interaction_restatement():
     for i, j in ((1, 0), (2, 1), (26, 25), (13, 4)):
         want = (f[:, i].float() * f[:, j].float()).sum(-1)
         torch.testing.assert_close(out[:, i * (i - 1) // 2 + j], want)
+
+
+def _py_row(x: int, c: int, n: int) -> int:
+    """commons/layers.py:174-185 in unbounded Python integers: wrapping << and ARITHMETIC >> on a
+    two's-complement int64, then Python's floor modulo (== torch.remainder)."""
+    def wrap(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+    if c:
+        x = wrap(wrap(x << c) | (x >> (64 - c)))        # Python >> on a negative int is arithmetic
+    return x % n
+
+
+def test_row_index_against_big_integer_model():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(-2 ** 63, 2 ** 63 - 1), min_size=1, max_size=16),
+           st.integers(0, 63), st.integers(1, 2 ** 40))
+    def check(ids, c, n):
+        want = [_py_row(x, c, n) for x in ids]
+        assert O.row_index(torch.tensor(ids, dtype=torch.int64), n, c).tolist() == want
+        assert O.row_index_np(np.array(ids, dtype=np.int64), n, c).tolist() == want
+
+    check()
+    # the collapse of SURVEY section 0.5: a negative id and shift c >= 1 land in the last 2^(c-1) rows
+    for c in (1, 2, 8, 15):
+        for x in (-1, -2 ** 63, -987654321, -(2 ** 40) - 7):
+            assert _py_row(x, c, 1_000_003) >= 1_000_003 - 2 ** (c - 1)
