@@ -38,6 +38,35 @@ def export_handle(t: torch.Tensor):
     return bytes(handle), int(off.value)
 
 
+# A CUDA IPC handle names a whole allocation and may be opened once per process: two exported tensors
+# that the caching allocator carved out of one segment (e.g. the arenas of two batch shapes) share a
+# handle.  Process-wide table: (device, handle) -> [mapped base, reference count].
+_OPENED: dict = {}
+
+
+def _open_shared(handle: bytes, dev: int) -> int:
+    key = (dev, handle)
+    ent = _OPENED.get(key)
+    if ent is None:
+        base = C.c_void_p()
+        buf = (C.c_uint8 * N.PEER_HANDLE_BYTES).from_buffer_copy(handle)
+        N.check(N.load().recemb_peer_open(buf, C.byref(base), dev), "recemb_peer_open")
+        ent = _OPENED[key] = [int(base.value), 0]
+    ent[1] += 1
+    return ent[0]
+
+
+def _close_shared(handle: bytes, dev: int) -> None:
+    key = (dev, handle)
+    ent = _OPENED.get(key)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        N.load().recemb_peer_close(ent[0], dev)
+        del _OPENED[key]
+
+
 class PeerGroup:
     """Mapped views of every rank's table shard and arena + the arena layout.
 
@@ -46,7 +75,7 @@ class PeerGroup:
     kernel tests -- the kernels cannot tell the difference, only the barrier must be skipped)."""
 
     def __init__(self, world: int, rank: int, arenas: Sequence[int], tables: Sequence[int],
-                 layout: N.PeerArena, arena: torch.Tensor, device: int, opened: Optional[List[int]] = None):
+                 layout: N.PeerArena, arena: torch.Tensor, device: int, opened: Optional[List[bytes]] = None):
         if not (1 <= world <= N.MAX_PEERS):
             raise N.NativeError(f"peer exchange supports 1..{N.MAX_PEERS} ranks, got {world}")
         self.world, self.rank, self.layout, self.arena, self.device = world, rank, layout, arena, device
@@ -76,17 +105,13 @@ class PeerGroup:
         mine = (export_handle(arena), export_handle(table) if table_ptrs is None else (b"", 0))
         everyone: List = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
-        lib = N.load()
-        mapped = {}            # handle bytes -> mapped base (a handle is opened once per process)
-        opened: List[int] = []
+        mapped = {}            # handle bytes -> mapped base, references held by THIS group
+        opened: List[bytes] = []
 
         def resolve(handle: bytes, offset: int) -> int:
             if handle not in mapped:
-                base = C.c_void_p()
-                buf = (C.c_uint8 * N.PEER_HANDLE_BYTES).from_buffer_copy(handle)
-                N.check(lib.recemb_peer_open(buf, C.byref(base), dev), "recemb_peer_open")
-                mapped[handle] = int(base.value)
-                opened.append(int(base.value))
+                mapped[handle] = _open_shared(handle, dev)
+                opened.append(handle)
             return mapped[handle] + offset
 
         arenas, tables = [], []
@@ -159,7 +184,6 @@ class PeerGroup:
         return [int(self.struct.table[i] or 0) for i in range(self.world)]
 
     def close(self) -> None:
-        lib = N.load()
-        for base in self._opened:
-            lib.recemb_peer_close(base, self.device)
+        for handle in self._opened:
+            _close_shared(handle, self.device)
         self._opened = []

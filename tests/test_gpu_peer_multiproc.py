@@ -66,7 +66,16 @@ def _worker(rank, world, port, peer_forward, result):
             out.backward(go.to(dev))
             torch.testing.assert_close(mod.emb.weight.grad.cpu(), mine, rtol=1e-4, atol=1e-5)
         mod.peer_group().raise_on_status(synchronize=True)
+        # a second batch shape: its own arena, the shard stays mapped once (shared IPC handles)
+        first = mod.peer_group()
+        out_s = mod(ids[:, :40].contiguous().to(dev), lengths[:, :40].contiguous().to(dev))
+        assert mod.peer_group() is not first and mod.peer_group().table_ptrs() == first.table_ptrs()
+        torch.testing.assert_close(out_s.cpu(), out[:, :40].cpu(), rtol=1e-5, atol=1e-5)
+        out_s.sum().backward()
+        mod.peer_group().raise_on_status(synchronize=True)
         mod.close_peer()
+        from recommendations_b200 import peer
+        assert not peer._OPENED, "every mapped IPC handle must be closed again"
         result[rank] = 1
     finally:
         dist.destroy_process_group()
