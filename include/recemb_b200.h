@@ -5,7 +5,7 @@
  * FFI of its own.  The boundary this library sits behind is the nn.Module
  * surface of commons/layers.py and commons/transformers/layers.py; every entry
  * point below names the reference call site whose ATen library call it
- * replaces.  The Python host layer (recommendations_b200/*.py) binds these
+ * replaces.  The Python host layer (the modules under recommendations_b200/) binds these
  * symbols with ctypes and keeps the reference constructors / forward /
  * state_dict keys (see INTEGRATION.md for the binding a maintainer would add).
  *
