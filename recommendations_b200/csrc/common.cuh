@@ -136,7 +136,7 @@ int64_t layout_tables(const recemb_layout* layout, int64_t n_ids);
 
 // global row -> local row on this shard, or -1 when another rank owns it
 __device__ __forceinline__ int64_t shard_local_row(int64_t row, const HashSpec& h) {
-  if (h.shard_world <= 1) return row;
+  if (h.shard_world <= 1 || row < 0) return row;
   uint64_t q;
   const uint64_t r = udivmod((uint64_t)row, h.mod_world, &q);
   return r == h.shard_rank ? (int64_t)q : -1;
@@ -159,7 +159,9 @@ __device__ __forceinline__ int64_t signed_rotl(int64_t x, int c) {
 __device__ __forceinline__ int64_t row_of(int64_t id, const HashSpec& h) {
   switch (h.mode) {
     case RECEMB_HASH_IDENTITY:
-      return id;
+      // ids ARE rows: anything outside [0, num_rows) is dropped (-1) by every kernel instead of
+      // reading / updating out of bounds (nn.EmbeddingBag raises there; the host layer checks)
+      return ((uint64_t)id < h.mod_rows.n) ? id : -1;
     case RECEMB_HASH_FLOORMOD:
       return floor_mod(id, h.mod_rows);
     case RECEMB_HASH_ROTL_FLOORMOD:

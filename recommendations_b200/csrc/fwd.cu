@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
       const int64_t id = rows[i];
       const bool pad = a.zero_pad && id == a.pad_id;
       if (TWO) s_rows2[i] = pad ? -1 : row_of(id, a.h2);
-      rows[i] = pad ? -1 : row_of(id, a.h1) + table_offset(tile * kTileIds + i, a.h1);
+      const int64_t r1 = pad ? -1 : row_of(id, a.h1);  // -1: pad position or out-of-range identity id
+      rows[i] = r1 < 0 ? -1 : r1 + table_offset(tile * kTileIds + i, a.h1);
     }
     __syncthreads();
 
@@ -434,9 +435,10 @@ __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const 
         // address of the slot's row (0 = nothing to pool), shuffled to the lanes that load it
         uint64_t my_src = 0;
         if constexpr (PEER) {
-          if (my_use) {
+          const int64_t my_grow = my_use ? row_of(my_id, a.h) : -1;
+          if (my_grow >= 0) {
             uint64_t q;
-            const uint32_t o = (uint32_t)udivmod((uint64_t)row_of(my_id, a.h), a.h.mod_world, &q);
+            const uint32_t o = (uint32_t)udivmod((uint64_t)my_grow, a.h.mod_world, &q);
             if (a.h.ids_per_table) {
               uint32_t t = (uint32_t)(bag * P + my_p) / a.h.ids_per_table;
               if (a.h.num_tables) t %= a.h.num_tables;

@@ -75,6 +75,8 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
   h.mod_sq = make_modn(1);
   switch (hash_mode) {
     case RECEMB_HASH_IDENTITY:
+      RECEMB_CHECK_ARG(num_rows >= 1, "IDENTITY needs num_rows >= 1 (the range ids are checked against)");
+      h.mod_rows.n = (uint64_t)num_rows;  // range bound only; no division in this mode
       break;
     case RECEMB_HASH_FLOORMOD:
       RECEMB_CHECK_ARG(num_rows >= 1, "FLOORMOD needs num_rows >= 1");

@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketAr
     }
     uint8_t owner = 0xff;
     uint32_t lrow = 0;
-    if (ok) {
-      const uint64_t row = (uint64_t)row_of(id, a.h);
+    const int64_t srow = ok ? row_of(id, a.h) : -1;  // -1 also for an out-of-range identity id
+    if (srow >= 0) {
+      const uint64_t row = (uint64_t)srow;
       uint64_t q;
       const uint32_t o = (uint32_t)udivmod(row, a.h.mod_world, &q);
       // stacked shard of owner o: table t starts at t * local_rows(o)

@@ -56,9 +56,14 @@ def hash_feature_name_to_int(feature_name: str) -> int:
     return xxh32(feature_name.lower().encode("utf-8"), 0)
 
 
-def pack_strings(values: Iterable, device) -> Tuple[torch.Tensor, torch.Tensor]:
-    """str(value) UTF-8 bytes back to back + offsets [n + 1] on `device`."""
-    enc = [str(v).encode("utf-8") for v in values]
+def pack_strings(values: Iterable, device, lower_non_ascii: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """str(value) UTF-8 bytes back to back + offsets [n + 1] on `device`.  lower_non_ascii: values
+    with non-ASCII characters are lower-cased HERE with Python's Unicode str.lower() (what the
+    reference calls, commons/feature_utils.py:43-44); the kernel only folds ASCII A-Z."""
+    strs = [str(v) for v in values]
+    if lower_non_ascii:
+        strs = [s if s.isascii() else s.lower() for s in strs]
+    enc = [s.encode("utf-8") for s in strs]
     offsets = np.zeros(len(enc) + 1, dtype=np.int64)
     np.cumsum([len(b) for b in enc], out=offsets[1:])
     blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8).copy()
@@ -67,12 +72,20 @@ def pack_strings(values: Iterable, device) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def hash_strings_to_long(values: Sequence, seed: int, value_to_lower: bool, device="cuda") -> torch.Tensor:
     """Vector form of hash_string_to_long (commons/feature_utils.py:40-46): int64 ids on `device`."""
-    blob, offsets = pack_strings(values, device)
-    return hash_packed_to_long(blob, offsets, seed, value_to_lower)
+    blob, offsets = pack_strings(values, device, lower_non_ascii=value_to_lower)
+    return hash_packed_to_long(blob, offsets, seed, value_to_lower, assume_ascii=True)
 
 
-def hash_packed_to_long(blob: torch.Tensor, offsets: torch.Tensor, seed: int, value_to_lower: bool) -> torch.Tensor:
+def hash_packed_to_long(blob: torch.Tensor, offsets: torch.Tensor, seed: int, value_to_lower: bool,
+                        assume_ascii: bool = False) -> torch.Tensor:
+    """ids of pre-packed UTF-8 strings.  With value_to_lower the kernel folds ASCII A-Z only, so a
+    blob holding non-ASCII bytes is refused (one device reduction + sync) unless the caller states
+    that those strings were already lower-cased (`assume_ascii=True`, as hash_strings_to_long does
+    after lower-casing them with str.lower() on the host)."""
     dev = N.require_cuda(blob, offsets)
+    if value_to_lower and not assume_ascii and bool((blob >= 128).any().item()):
+        raise N.NativeError("value_to_lower on a blob with non-ASCII bytes: lower-case those strings on the host "
+                            "(str.lower() is Unicode-aware, the kernel folds ASCII only) and pass assume_ascii=True")
     n = offsets.numel() - 1
     out = torch.empty((n,), dtype=torch.int64, device=blob.device)
     N.check(N.load().recemb_xxh64_ids(N.ptr(blob), N.ptr(offsets), n, seed, int(value_to_lower), N.ptr(out), dev,

@@ -70,7 +70,8 @@ class _GatherFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, anchor2, ids, holder, holder2, hash_mode, hash_mode2, hash_arg,
                 epilogue, zero_pad, pad_id, flip_len=0):
-        need_grad = anchor.requires_grad or (anchor2 is not None and anchor2.requires_grad)
+        # needs_input_grad is all-False under torch.no_grad() / inference: no inverse norms, no plan
+        need_grad = ctx.needs_input_grad[0] or (anchor2 is not None and ctx.needs_input_grad[1])
         out, inv = ops.gather_fwd(
             holder.weight.detach(), ids, hash_mode=hash_mode, hash_arg=hash_arg,
             table2=None if holder2 is None else holder2.weight.detach(), hash_mode2=hash_mode2,
@@ -80,7 +81,7 @@ class _GatherFn(torch.autograd.Function):
         ctx.flip_len = flip_len
         ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
-        _plan_early(ctx, ids, holder2 is None and anchor.requires_grad and not (holder.sparse and holder.fused is None),
+        _plan_early(ctx, ids, holder2 is None and ctx.needs_input_grad[0] and not (holder.sparse and holder.fused is None),
                     lambda: ops.BackwardPlan.build(
                         ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
                         zero_pad=zero_pad, pad_id=pad_id,
@@ -105,7 +106,10 @@ class _GatherFn(torch.autograd.Function):
                 vals = g.to(holder.weight.dtype)
                 if ctx.flip_len:  # gradient rows are in mirrored order
                     vals = vals.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
-                grads[i] = _coo(rows, vals, holder)
+                # fused pad mask: the forward never read the table at id == pad_id positions, so they
+                # carry no gradient (the plan-based modes drop those slots the same way)
+                keep = (ids.reshape(-1) != pad_id) if zero_pad else None
+                grads[i] = _coo(rows, vals, holder, keep)
                 continue
             plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
                 ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
@@ -115,10 +119,14 @@ class _GatherFn(torch.autograd.Function):
         return (grads[0], grads[1]) + (None,) * 10
 
 
-def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable) -> torch.Tensor:
-    """The uncoalesced COO gradient nn.Embedding(sparse=True) produces (nnz == lookups)."""
+def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable,
+         keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The uncoalesced COO gradient nn.Embedding(sparse=True) produces (nnz == lookups that
+    read the table; `keep` masks positions the forward zero-filled)."""
     if holder.padding_idx is not None:
-        keep = rows != holder.padding_idx
+        k2 = rows != holder.padding_idx
+        keep = k2 if keep is None else (keep & k2)
+    if keep is not None:
         rows, vals = rows[keep], vals[keep]
     return torch.sparse_coo_tensor(rows.view(1, -1), vals, holder.weight.shape)
 
@@ -127,10 +135,10 @@ class _KShiftFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0):
         out, inv = ops.kshift_fwd(holder.weight.detach(), ids, num_shifts, epilogue,
-                                  want_inv_norm=anchor.requires_grad, flip_len=flip_len)
+                                  want_inv_norm=ctx.needs_input_grad[0], flip_len=flip_len)
         ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
-        _plan_early(ctx, ids, anchor.requires_grad and not (holder.sparse and holder.fused is None),
+        _plan_early(ctx, ids, ctx.needs_input_grad[0] and not (holder.sparse and holder.fused is None),
                     lambda: ops.BackwardPlan.build(
                         ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=num_shifts,
                         pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
@@ -176,7 +184,7 @@ class _PoolFn(torch.autograd.Function):
         ctx.holder = holder
         ctx.cfg = (hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id)
         ctx.save_for_backward(ids, lengths, per_slot_weight)
-        _plan_early(ctx, ids, anchor.requires_grad, lambda: ops.BackwardPlan.build(
+        _plan_early(ctx, ids, ctx.needs_input_grad[0], lambda: ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
             zero_pad=zero_pad, pad_id=pad_id,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=ids.shape[1],
@@ -326,7 +334,7 @@ class PooledEmbeddingBag(nn.Module):
     def __init__(self, num_embeddings: int, emb_dim: int, mode: str = "sum", *, last_n: int = 0,
                  hash_ids: bool = True, skip_pad: bool = False, pad_id: int = 0,
                  padding_idx: Optional[int] = None, dtype: torch.dtype = torch.float32, device=None,
-                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None, validate_ids: bool = True):
         super().__init__()
         if mode not in ("sum", "mean"):
             raise ValueError("mode must be 'sum' or 'mean' (use last_n for the last-N window)")
@@ -334,11 +342,20 @@ class PooledEmbeddingBag(nn.Module):
                                   device=device)
         self.mode, self.last_n = mode, int(last_n)
         self.hash_ids, self.skip_pad, self.pad_id = hash_ids, skip_pad, pad_id
+        # hash_ids=False: ids are rows.  nn.EmbeddingBag raises on an out-of-range index; the kernels
+        # only DROP such slots (never read or update out of bounds), so the module checks the range
+        # itself (one device reduction + sync per call; validate_ids=False skips it).
+        self.validate_ids = validate_ids
         if fused_optimizer is not None:
             self.emb.enable_fused_optimizer(fused_optimizer)
 
     def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                 per_sample_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not self.hash_ids and self.validate_ids and ids.numel():
+            lo, hi = torch.aminmax(ids)
+            if int(lo) < 0 or int(hi) >= self.emb.num_embeddings:
+                raise IndexError(f"index out of range in PooledEmbeddingBag(hash_ids=False): ids span "
+                                 f"[{int(lo)}, {int(hi)}], table has {self.emb.num_embeddings} rows")
         return _PoolFn.apply(self.emb.grad_anchor(), ids, lengths, per_sample_weights, self.emb,
                              N.HASH_FLOORMOD if self.hash_ids else N.HASH_IDENTITY, 0,
                              N.POOL_SUM if self.mode == "sum" else N.POOL_MEAN, self.last_n,

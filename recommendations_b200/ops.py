@@ -121,6 +121,9 @@ class BackwardPlan:
     num_rows: int
     slots_per_id: int
     slots_cover_grad: bool = True  # False: slots are explicit gradient-row indices (routed entries)
+    # (ids, build keyword arguments) of a plan built from ids: lets table.commit_step() rebuild ONE
+    # plan over the concatenated ids of several lookups of a table (accumulate mode)
+    recipe: Optional[tuple] = None
 
     @staticmethod
     def build(ids: torch.Tensor, *, num_rows: int, hash_mode: int = N.HASH_FLOORMOD,
@@ -148,7 +151,12 @@ class BackwardPlan:
                                     hash_arg, int(zero_pad), pad_id, pad_row, bag_size,
                                     N.ptr(lengths), last_n, N.ptr(buf), buf.numel(), dev,
                                     N.stream_ptr(dev)), "recemb_bwd_plan")
-        return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=total_rows, slots_per_id=slots_per_id)
+        recipe = (ids, dict(num_rows=num_rows, hash_mode=hash_mode, hash_arg=hash_arg, slots_per_id=slots_per_id,
+                            zero_pad=zero_pad, pad_id=pad_id, pad_row=pad_row, bag_size=bag_size, lengths=lengths,
+                            last_n=last_n, ids_per_table=ids_per_table, num_tables=num_tables,
+                            shard_world=shard_world, shard_rank=shard_rank, flip_len=flip_len))
+        return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=total_rows, slots_per_id=slots_per_id,
+                            recipe=recipe)
 
     def _arr(self, which: int) -> torch.Tensor:
         arr_bytes = (self.n_slots * 4 + 255) // 256 * 256

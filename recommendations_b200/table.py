@@ -35,6 +35,13 @@ class FusedOptimizerConfig:
     betas: Tuple[float, float] = (0.9, 0.999)
     lr_decay: float = 0.0
     initial_accumulator_value: float = 0.0
+    # A table looked up more than once per optimizer step (a shared table serving history and
+    # target lookups, gradient accumulation) must see ONE update with the SUMMED gradient, as
+    # torch.optim does on .grad.  accumulate=False (default) applies the update inside backward
+    # and refuses a second backward of the same table before FusedEmbeddingOptimizer.step();
+    # accumulate=True keeps every lookup's (ids, gradient rows) until step(), which merges them
+    # into one plan and applies one update.
+    accumulate: bool = False
 
     def __post_init__(self):
         if self.kind not in ("sgd", "adagrad", "rowwise_adagrad", "adam", "adamw"):
@@ -71,8 +78,11 @@ class EmbeddingTable(nn.Module):
             w = _weight
         self.weight = nn.Parameter(w)
         self.fused: Optional[FusedOptimizerConfig] = None
-        self.fused_step = 0
+        self.fused_step = 0          # completed optimizer steps
         self._anchor: Optional[torch.Tensor] = None
+        self._has_facade = False     # a FusedEmbeddingOptimizer drives the step boundaries
+        self._applied_in_step = 0    # updates applied since the last step boundary
+        self._pending = []           # accumulate mode: lookups waiting for step()
 
     # ---------------------------------------------------------------- modes ----
     def enable_fused_optimizer(self, config: Optional[FusedOptimizerConfig] = None, **kw) -> "EmbeddingTable":
@@ -130,21 +140,54 @@ class EmbeddingTable(nn.Module):
                           slots_per_grad_row=slots_per_grad_row, slot_weight=slot_weight,
                           grad_row_scale=grad_row_scale, grad_div=grad_div)
             return gw
+        if self.fused.accumulate:
+            if not self._has_facade:
+                raise N.NativeError("FusedOptimizerConfig(accumulate=True) needs a FusedEmbeddingOptimizer: its "
+                                    "step() applies the accumulated lookups")
+            self._pending.append((plan, grad2d, slots_per_grad_row, slot_weight, grad_row_scale, grad_div))
+            return None
+        if self._has_facade and self._applied_in_step >= 1:
+            raise N.NativeError(
+                "this fused table already applied an update in the current optimizer step: a second backward "
+                "through it before FusedEmbeddingOptimizer.step() would apply two separate updates instead of "
+                "one with the summed gradient (Adagrad would accumulate g1^2 + g2^2, not (g1 + g2)^2).  Use "
+                "FusedOptimizerConfig(accumulate=True) for tables looked up more than once per step.")
+        self._apply_fused(plan, grad2d, slots_per_grad_row, slot_weight, grad_row_scale, grad_div)
+        if self._has_facade:
+            self._applied_in_step += 1
+        else:
+            self.fused_step += 1  # no facade: every backward is one optimizer step
+        return None
+
+    def _apply_fused(self, plan, grad2d, slots_per_grad_row, slot_weight, grad_row_scale, grad_div) -> None:
         cfg = self.fused
         self._ensure_state()
-        self.fused_step += 1
+        step = self.fused_step + 1
         lr = cfg.lr
         if cfg.kind in ("adagrad", "rowwise_adagrad"):
-            lr = cfg.lr / (1.0 + (self.fused_step - 1) * cfg.lr_decay)
+            lr = cfg.lr / (1.0 + (step - 1) * cfg.lr_decay)
         hp = ops.make_optim_params(lr=lr, eps=cfg.eps, weight_decay=cfg.weight_decay,
-                                   beta1=cfg.betas[0], beta2=cfg.betas[1], step=self.fused_step)
+                                   beta1=cfg.betas[0], beta2=cfg.betas[1], step=step)
         with torch.no_grad():
-            ops.bwd_apply(plan, grad2d, table=w.data, update=N.UPDATE_BY_NAME[cfg.kind],
+            ops.bwd_apply(plan, grad2d, table=self.weight.data, update=N.UPDATE_BY_NAME[cfg.kind],
                           slots_per_grad_row=slots_per_grad_row,
                           state1=self._buffers.get("opt_state1"),
                           state2=self._buffers.get("opt_state2"), hp=hp, slot_weight=slot_weight,
                           grad_row_scale=grad_row_scale, grad_div=grad_div)
-        return None
+
+    def commit_step(self) -> None:
+        """Step boundary (FusedEmbeddingOptimizer.step): applies the lookups accumulated since the
+        last boundary as ONE update with the summed gradient, then advances the step count."""
+        pending, self._pending = self._pending, []
+        if pending:
+            if len(pending) == 1:
+                self._apply_fused(*pending[0])
+            else:
+                self._apply_fused(*_merge_lookups(pending))
+            self._applied_in_step += 1
+        if self._applied_in_step:
+            self.fused_step += 1
+        self._applied_in_step = 0
 
     def extra_repr(self) -> str:
         mode = "torch-grad" if self.fused is None else f"fused-{self.fused.kind}"
@@ -152,11 +195,40 @@ class EmbeddingTable(nn.Module):
                 f"dtype={self.weight.dtype}, mode={mode}")
 
 
+def _merge_lookups(pending):
+    """Several lookups of one table inside one optimizer step -> one plan over the concatenated ids
+    and one concatenated gradient: the segmented reduction then sums every row's gradient over all
+    lookups before the single update (what autograd's accumulation into .grad + one optim.step()
+    does in the reference)."""
+    recipes = [p[0].recipe for p in pending]
+    if any(r is None for r in recipes):
+        raise N.NativeError("accumulate=True: a lookup's plan was not built from ids and cannot be merged")
+    kw0 = recipes[0][1]
+    spg0, gdiv0 = pending[0][2], pending[0][5]
+    for (_, kw), p in zip(recipes, pending):
+        if kw.get("lengths") is not None or kw.get("ids_per_table") or kw.get("shard_world", 1) > 1 \
+                or kw != kw0 or p[2] != spg0 or p[5] != gdiv0:
+            raise N.NativeError("accumulate=True merges lookups of one kind only (same hashing, pad mask, flip and "
+                                "bag shape; no per-bag lengths, table batching or sharding)")
+    if any((p[3] is None) != (pending[0][3] is None) or (p[4] is None) != (pending[0][4] is None) for p in pending):
+        raise N.NativeError("accumulate=True: lookups with and without per-slot weights cannot be merged")
+    ids = torch.cat([r[0].reshape(-1) for r in recipes])
+    grads = [p[1] for p in pending]
+    dt = torch.float32 if any(g.dtype == torch.float32 for g in grads) else grads[0].dtype
+    grad = torch.cat([g.to(dt) for g in grads])
+    sw = None if pending[0][3] is None else torch.cat([p[3].reshape(-1) for p in pending])
+    gs = None if pending[0][4] is None else torch.cat([p[4].reshape(-1) for p in pending])
+    plan = ops.BackwardPlan.build(ids, **kw0)
+    return plan, grad, spg0, sw, gs, gdiv0
+
+
 class FusedEmbeddingOptimizer(torch.optim.Optimizer):
     """Facade returned from optimizers_for_param_groups
-    (commons/base_model_wrapper.py:64-72) for tables in fused mode: the update has
-    already happened inside backward, so step() / zero_grad() do nothing; the
-    object carries the hyper-parameters and exposes the optimizer state."""
+    (commons/base_model_wrapper.py:64-72) for tables in fused mode: the update happens
+    inside backward (or, accumulate=True, inside step() with the gradient summed over
+    every lookup of the step); step() marks the step boundary, the object carries the
+    hyper-parameters and exposes the optimizer state.  Without a facade every backward
+    through a fused table counts as one optimizer step."""
 
     def __init__(self, tables, **overrides):
         self.tables = [t for t in tables if isinstance(t, EmbeddingTable)]
@@ -168,6 +240,8 @@ class FusedEmbeddingOptimizer(torch.optim.Optimizer):
             else:
                 for k, v in overrides.items():
                     setattr(t.fused, k, v)
+        for t in self.tables:
+            t._has_facade = True
         params = [t.grad_anchor() for t in self.tables]
         super().__init__(params, dict(lr=self.tables[0].fused.lr))
 
@@ -178,6 +252,11 @@ class FusedEmbeddingOptimizer(torch.optim.Optimizer):
         for group in self.param_groups:
             for t in self.tables:
                 t.fused.lr = float(group["lr"])
+        # step boundary: accumulate-mode tables apply their summed update now, every table that
+        # was updated advances its step count (bias correction / lr_decay count optimizer steps,
+        # not backward calls)
+        for t in self.tables:
+            t.commit_step()
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

@@ -32,6 +32,22 @@ def test_gpu_xxh64_golden_and_random(golden):
 
 
 @pytest.mark.gpu
+def test_gpu_xxh64_unicode_lower_matches_python_str_lower():
+    """hash_string_to_long lower-cases with Python's Unicode str.lower() (commons/feature_utils.py:43-44):
+    non-ASCII upper-case text must give the reference id, a pre-packed non-ASCII blob is refused."""
+    vals = ["ÀÉÎÕÜ", "Ünïcode-MIXED", "ΑΒΓ δ", "ascii ONLY", "İstanbul", "ǅ", "日本語ABC", ""]
+    seed = 396283771
+    for lower in (False, True):
+        assert FU.hash_strings_to_long(vals, seed, lower).cpu().tolist() == \
+            [O.hash_string_to_id(v, seed, lower) for v in vals]
+    blob, off = FU.pack_strings(vals, "cuda")
+    with pytest.raises(RuntimeError, match="non-ASCII"):
+        FU.hash_packed_to_long(blob, off, seed, True)
+    assert FU.hash_packed_to_long(blob, off, seed, False).cpu().tolist() == \
+        [O.hash_string_to_id(v, seed, False) for v in vals]
+
+
+@pytest.mark.gpu
 def test_gpu_pad_histories_matches_reference_loop():
     rng = np.random.default_rng(1)
     rows, L = 300, 20
