@@ -58,13 +58,17 @@ enum recemb_dtype { RECEMB_F32 = 0, RECEMB_BF16 = 1 };
  *   QR_QUOTIENT   d = hash_arg; x = floor_mod(id, d*d); row = floor_mod(floor(x / d), d)
  *   QR_REMAINDER  d = hash_arg; x = floor_mod(id, d*d); row = floor_mod(x, d)
  *                                                             commons/layers.py:115-119
+ *   DIV_FLOORMOD  row = floor_mod(floor_divide(id, hash_arg), num_rows)
+ *                 PatternFromTimelocal (hour-of-day / hour-of-week / day-of-week tables of
+ *                 QueryTower, models/lthm/sequence/query_tower.py:27-33)  commons/layers.py:39-41
  */
 enum recemb_hash {
   RECEMB_HASH_IDENTITY = 0,
   RECEMB_HASH_FLOORMOD = 1,
   RECEMB_HASH_ROTL_FLOORMOD = 2,
   RECEMB_HASH_QR_QUOTIENT = 3,
-  RECEMB_HASH_QR_REMAINDER = 4
+  RECEMB_HASH_QR_REMAINDER = 4,
+  RECEMB_HASH_DIV_FLOORMOD = 5
 };
 
 /* forward epilogues */
@@ -406,6 +410,30 @@ RECEMB_API int recemb_xxh64_ids(const uint8_t* bytes, const int64_t* offsets, in
 RECEMB_API int recemb_pad_histories(const int64_t* values, const int64_t* offsets, const int64_t* remove_ids,
                          int64_t rows, int32_t history_length, int64_t pad_token, int64_t* out, int device,
                          recemb_stream_t stream);
+
+/* ---- streaming logQ correction ------------------------------- */
+/* The D = 1 cousin of the gather / scatter: num_tables cascaded bucket tables b_m [num_buckets]
+ * fp32 with hash h_m(id) = floor_mod(id + hash_offsets[m], num_buckets) (int64 wrap-around add).
+ * b_tables_host / a_tables_host / hash_offsets_host are HOST arrays of num_tables device
+ * pointers / offsets (num_tables <= 16; lthm.yaml: 7 offsets x 2^24 buckets).
+ *   fwd     out[i] = min_m( -log(b_m[h_m(ids[i])]) )
+ *           StreamingLogQCorrectionModule.forward (commons/layers.py:202-204) under
+ *           CascadedStreamingLogQCorrectionModule.forward (:224-232, torch.minimum over modules) */
+RECEMB_API int recemb_logq_fwd(const float* const* b_tables_host, int32_t num_tables,
+                    const int64_t* hash_offsets_host, int64_t num_buckets, const int64_t* ids, int64_t n,
+                    float* out, int device, recemb_stream_t stream);
+/*   update  for every id (skip_mask[i] == 0): b_m[h] = (1 - alpha) * b_m[h] + alpha * (batch_idx - a_m[h]),
+ *           a_m[h] = batch_idx -- StreamingLogQCorrectionModule.train_step (commons/layers.py:210-213;
+ *           its last line assigns into the float `alpha`, read here as `self.a[hash] = batch_idx`).
+ *           The right-hand side is evaluated from the OLD tables for all ids before anything is
+ *           written (torch's gather-then-index_put order); duplicates of a bucket write the same
+ *           value.  skip_mask (optional, uint8 [n]) fuses the reference's boolean compaction
+ *           `product_ids.view(-1)[mask.view(-1) == 0]` (models/lthm/sequence/wrapper.py:133).
+ *           scratch: fp32 [n * num_tables]. */
+RECEMB_API int recemb_logq_update(float* const* b_tables_host, float* const* a_tables_host, int32_t num_tables,
+                       const int64_t* hash_offsets_host, int64_t num_buckets, const int64_t* ids, int64_t n,
+                       const uint8_t* skip_mask, double alpha, int64_t batch_idx, float* scratch,
+                       int device, recemb_stream_t stream);
 
 /* ---- host-buffer entry points (end-to-end path) ---------------------------- */
 /* One fused training step of a FlatEmbedding-style table with HOST ids:

@@ -234,6 +234,36 @@ def hash_string_to_id(value, seed: int, lower: bool = False) -> int:
     return xxhash.xxh64(s, seed).intdigest() - TWO63
 
 
+# ------------------------------------------------- time patterns / streaming logQ ----
+def pattern_index(x: torch.Tensor, div: int, mod: int) -> torch.Tensor:
+    """PatternFromTimelocal index, commons/layers.py:39-40."""
+    return torch.remainder(torch.floor_divide(x.long(), div), mod)
+
+
+def logq_hash(products: torch.Tensor, hash_offset: int, num_buckets: int) -> torch.Tensor:
+    """StreamingLogQCorrectionModule.hash_fn, commons/layers.py:206-208 (`%` on tensors is floor-mod)."""
+    return (products + hash_offset) % num_buckets
+
+
+def logq_forward(b_tables, hash_offsets, products: torch.Tensor) -> torch.Tensor:
+    """CascadedStreamingLogQCorrectionModule.forward, commons/layers.py:224-232 over :202-204."""
+    result = None
+    for b, off in zip(b_tables, hash_offsets):
+        lq = -b[logq_hash(products, off, b.numel())].log().reshape(*products.shape)
+        result = lq if result is None else torch.minimum(result, lq)
+    return result
+
+
+def logq_train_step(b_tables, a_tables, hash_offsets, products: torch.Tensor, alpha: float, batch_idx: int) -> None:
+    """StreamingLogQCorrectionModule.train_step for every cascaded table, commons/layers.py:210-213 and
+    :234-237 with the two evident repairs (`self.a[hash] = batch_idx`; iterate the modules and call
+    train_step).  In place."""
+    for b, a, off in zip(b_tables, a_tables, hash_offsets):
+        h = logq_hash(products, off, b.numel())
+        b[h] = ((1 - alpha) * b[h]) + (alpha * (batch_idx - a[h])).float()
+        a[h] = batch_idx
+
+
 # ------------------------------------------------- the reference's train step ----
 class FlatTableCPU(torch.nn.Module):
     """nn.Embedding-backed FlatEmbedding restatement used as the timed CPU baseline: the same

@@ -5,8 +5,9 @@
     python oracle/make_golden.py            # rewrites tests/golden/
 
 Every fixture stores the inputs, the initial weights and the reference's outputs, so both
-the oracle (tests/test_oracle_golden.py) and the CUDA path (tests/test_gpu_golden.py) can
-be checked against what the reference itself computed.  torch version is recorded.
+the oracle (tests/test_oracle_golden.py) and the CUDA path (tests/test_gpu_parity.py,
+tests/test_gpu_lthm_step.py) can be checked against what the reference itself computed.
+torch version is recorded.
 """
 from __future__ import annotations
 
@@ -164,6 +165,82 @@ def main():
                         ids_lower=np.array([fu.hash_string_to_long(s, seed, True) for s in strings], dtype=np.int64),
                         pad_short=fu.pad_array([5, 6, 7], 5), pad_long=fu.pad_array(list(range(10)), 4),
                         **meta)
+    # ---- 11. train_mask_model loop body (embedding_module_gen.py:70-118): KShift(D = 4, k = 16) + MLP + BCE ----
+    torch.manual_seed(1240)
+    n_prod, mdim, k = 2048, 4, 16
+    prod_ids = seeded_ids(n_prod, 14)
+    mask_model = nn.Sequential(cl.KShiftEmbedding(int(1.15 * n_prod), mdim, num_shifts=k, normalize_output=False),
+                               cl.MLP(mdim, 1, [mdim * 16]))
+    sd0 = {k_: v.detach().numpy().copy() for k_, v in mask_model.state_dict().items()}
+    optim = torch.optim.Adagrad(mask_model.parameters(), lr=5e-1)
+    crit = nn.BCEWithLogitsLoss()
+    gneg = torch.Generator().manual_seed(15)
+    losses, negs = [], []
+    for step in range(3):  # loop body of embedding_module_gen.py:104-115
+        pos = prod_ids[torch.randperm(n_prod, generator=gneg)[:1024]]
+        neg = torch.randint(-2 ** 63, 2 ** 63 - 1, (pos.size(0),), dtype=torch.int64, generator=gneg)
+        ids_this = torch.cat([pos, neg], dim=0)
+        target_this = torch.cat([torch.ones_like(pos), torch.zeros_like(neg)], dim=0)
+        prediction = mask_model(ids_this).squeeze(1)
+        loss = crit(prediction, target_this.float())
+        loss.backward()
+        optim.step()
+        optim.zero_grad()
+        losses.append(loss.item())
+        negs.append(ids_this.numpy().copy())
+    np.savez_compressed(OUT / "mask_model_train.npz", ids=np.stack(negs), losses=np.array(losses, dtype=np.float64),
+                        k=k, lr=0.5, **{f"sd0/{k_}": v for k_, v in sd0.items()},
+                        **{f"sd3/{k_}": v.detach().numpy() for k_, v in mask_model.state_dict().items()}, **meta)
+
+    # ---- 9. streaming logQ (commons/layers.py:189-237; train_step with the two evident repairs) ----
+    sys.path.insert(0, str(OUT.parent))
+    import harness_lthm as H  # tests/harness_lthm.py: the repaired LTHM-step harness
+    L = H.reference_layers()
+    lq = L.LogQ(num_buckets=257, hash_offsets=[0, 34144, 7465477], alpha=0.05, p_init=0.01)
+    lq_ids = torch.cat([torch.tensor(EDGE_IDS, dtype=torch.int64), seeded_ids(400, 13) % 3000])
+    fwd0 = lq(lq_ids).numpy().copy()
+    steps_fwd = []
+    for step in range(4):
+        sub = lq_ids[torch.randperm(lq_ids.numel(), generator=torch.Generator().manual_seed(step))[:300]]
+        lq.train_step(sub, step)
+        steps_fwd.append(lq(lq_ids).numpy().copy())
+    np.savez_compressed(OUT / "streaming_logq.npz", ids=lq_ids.numpy(), fwd0=fwd0, fwd_steps=np.stack(steps_fwd),
+                        b=np.stack([m.b.numpy() for m in lq.models]), a=np.stack([m.a.numpy() for m in lq.models]),
+                        offsets=np.array([0, 34144, 7465477], dtype=np.int64), num_buckets=257, alpha=0.05,
+                        p_init=0.01, **meta)
+
+    # ---- 10. the repaired-harness LTHM training step (BASELINE configs[0]), reference classes on CPU ----
+    cfg = H.HarnessConfig()
+    torch.manual_seed(cfg.seed)
+    model = H.LTHMStep(cfg, L)
+    model._model.product_emb_module.emb.weight.data.copy_(H.kshift_table(cfg))
+    batch = H.make_batch(cfg)
+    replaced = H.fix_margins(model, batch)
+    margin = H.bucket_margin(model, batch)
+    big = "_model.product_emb_module.emb.weight"
+    sd0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items() if k != big}
+    res = H.run_step(model, batch, steps=2)
+    names = H.embedding_param_names(model)
+    sd2 = model.state_dict()
+    out = res["output"]
+    fixture = {f"sd0/{k}": v for k, v in sd0.items()}
+    fixture.update({f"grad/{n}": res["grads"][n].numpy() for n in names if n != big})
+    fixture.update({f"sd2/{n}": sd2[n].numpy() for n in names if n != big})
+    fixture.update({f"sd2/{k}": v.numpy() for k, v in sd2.items() if "_log_q_calc" in k})
+    w0 = H.kshift_table(cfg)
+    np.savez_compressed(
+        OUT / "lthm_step.npz", product_ids=batch["product_ids"].numpy(), labels=batch["labels"].numpy(),
+        timestamp=batch["timestamp"].numpy(), losses=np.array(res["losses"], dtype=np.float64),
+        kshift_checksum=np.array([w0.double().sum().item(), (w0.double() ** 2).sum().item()]),
+        kshift_grad_absmax=float(res["grads"][big].abs().max()),
+        kshift_after=sd2[big][::97].numpy(),  # AdamW on a detached table is pure decay
+        next_token_emb=out["next_token_emb"][::8].numpy(), next_token_rowsum=out["next_token_emb"].sum(-1).numpy(),
+        current_token_emb=out["current_token_emb"][::8].numpy(),
+        current_token_rowsum=out["current_token_emb"].sum(-1).numpy(),
+        current_token_mask=out["current_token_mask"].numpy(), current_token_ids=out["current_token_ids"].numpy(),
+        margin=margin, ids_replaced=replaced, **fixture, **meta)
+    print(f"lthm_step: losses {res['losses']}, trim -> {out['current_token_ids'].shape}, margin {margin:.2e}, "
+          f"{replaced} ids re-drawn")
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name:36s} {f.stat().st_size / 1024:8.1f} KiB")
 

@@ -7,11 +7,13 @@ any op does, and a missing library raises instead of falling back.
 """
 from . import _native
 from .interaction import DotInteraction, dot_interaction
-from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PooledEmbeddingBag,
-                     QREmbedding)
+from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PatternFromTimelocal,
+                     PooledEmbeddingBag, QREmbedding)
+from .logq import CascadedStreamingLogQCorrectionModule, StreamingLogQCorrectionModule
 from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
 
 __all__ = [
     "CosineVectorEmbedding", "DotInteraction", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
-    "FusedOptimizerConfig", "KShiftEmbedding", "PooledEmbeddingBag", "QREmbedding",
+    "FusedOptimizerConfig", "KShiftEmbedding", "PatternFromTimelocal", "PooledEmbeddingBag", "QREmbedding",
+    "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule",
 ]

@@ -15,7 +15,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "librecemb_b200.so"
 
 # enums (mirror include/recemb_b200.h)
 F32, BF16 = 0, 1
-HASH_IDENTITY, HASH_FLOORMOD, HASH_ROTL_FLOORMOD, HASH_QR_QUOTIENT, HASH_QR_REMAINDER = range(5)
+HASH_IDENTITY, HASH_FLOORMOD, HASH_ROTL_FLOORMOD, HASH_QR_QUOTIENT, HASH_QR_REMAINDER, HASH_DIV_FLOORMOD = range(6)
 EPI_NONE, EPI_L2NORM, EPI_RSQRT_K = range(3)
 POOL_SUM, POOL_MEAN = 0, 1
 UPD_DENSE_GRAD, UPD_SGD, UPD_ADAGRAD, UPD_ROWWISE_ADAGRAD, UPD_ADAM, UPD_ADAMW = range(6)
@@ -139,6 +139,8 @@ SIGNATURES = {
     "recemb_dot_interaction_bwd": (_INT, [_P, _P, _I64, _I32, _I32, _P, _INT, _P]),
     "recemb_xxh64_ids": (_INT, [_P, _P, _I64, C.c_uint64, _INT, _P, _INT, _P]),
     "recemb_pad_histories": (_INT, [_P, _P, _P, _I64, _I32, _I64, _P, _INT, _P]),
+    "recemb_logq_fwd": (_INT, [_P, _I32, _P, _I64, _P, _I64, _P, _INT, _P]),
+    "recemb_logq_update": (_INT, [_P, _P, _I32, _P, _I64, _P, _I64, _P, C.c_double, _I64, _P, _INT, _P]),
     "recemb_flat_step_host": (_INT, [_P, _I64, _I64, _P, _P, _I64, _I32, _INT, _P, _P, _INT, _P, _P,
                                      C.POINTER(OptimParams), _P, _SZ, _P, _SZ, _P, _P, _P, _INT, _P]),
 }

@@ -172,6 +172,19 @@ __device__ __forceinline__ int64_t row_of(int64_t id, const HashSpec& h) {
       udivmod(x, h.mod_rows, &q);  // floor(x / d), already in [0, d)
       return (int64_t)q;
     }
+    case RECEMB_HASH_DIV_FLOORMOD: {
+      // floor_mod(floor_divide(id, div), num_rows), div = mod_sq.n  (PatternFromTimelocal)
+      uint64_t q;
+      int64_t fq;
+      if (id >= 0) {
+        udivmod((uint64_t)id, h.mod_sq, &q);
+        fq = (int64_t)q;
+      } else {  // floor(x / d) = -floor((-x - 1) / d) - 1 for x < 0
+        udivmod(~(uint64_t)id, h.mod_sq, &q);
+        fq = -(int64_t)q - 1;
+      }
+      return floor_mod(fq, h.mod_rows);
+    }
     default: {  // RECEMB_HASH_QR_REMAINDER
       uint64_t x = (uint64_t)floor_mod(id, h.mod_sq);
       return (int64_t)udivmod(x, h.mod_rows, nullptr);

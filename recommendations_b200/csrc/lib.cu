@@ -96,6 +96,12 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
       h.mod_rows = make_modn((uint64_t)hash_arg);
       h.mod_sq = make_modn((uint64_t)hash_arg * (uint64_t)hash_arg);
       break;
+    case RECEMB_HASH_DIV_FLOORMOD:
+      RECEMB_CHECK_ARG(num_rows >= 1, "DIV_FLOORMOD needs num_rows >= 1");
+      RECEMB_CHECK_ARG(hash_arg >= 1, "DIV_FLOORMOD divisor %lld < 1", (long long)hash_arg);
+      h.mod_rows = make_modn((uint64_t)num_rows);
+      h.mod_sq = make_modn((uint64_t)hash_arg);
+      break;
     default:
       set_error("unknown hash mode %d", hash_mode);
       return RECEMB_ERR_INVALID;

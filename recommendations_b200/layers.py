@@ -270,6 +270,31 @@ class FlatEmbedding(nn.Module):
                                self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences))
 
 
+class PatternFromTimelocal(nn.Module):
+    """commons/layers.py:13-41: index = floor_mod(floor_divide(t, div), mod); out = emb[index]
+    (hour-of-day / hour-of-week / day-of-week tables of QueryTower,
+    models/lthm/sequence/query_tower.py:27-33).  The reference chains floor_divide, remainder and an
+    embedding lookup; here the index arithmetic runs inside the gather kernel (DIV_FLOORMOD).
+    The reference constructor forgets super().__init__() and passes `emb_dim=` to nn.Embedding
+    (both TypeErrors); semantics otherwise identical.  state_dict key: `emb.weight`."""
+
+    def __init__(self, div, mod, emb_dim, *, dtype: torch.dtype = torch.float32, device=None):
+        super().__init__()
+        self.div = div
+        self.mod = mod
+        self.emb_dim = emb_dim
+        self.emb = EmbeddingTable(mod, emb_dim, dtype=dtype, device=device) if emb_dim > 0 else nn.Identity()
+
+    def index(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.row_index(x.long(), N.HASH_DIV_FLOORMOD, self.mod, self.div)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.emb_dim <= 0:
+            return self.index(x)
+        return _GatherFn.apply(self.emb.grad_anchor(), None, x.long(), self.emb, None, N.HASH_DIV_FLOORMOD, 0,
+                               self.div, N.EPI_NONE, False, 0, 0)
+
+
 class KShiftEmbedding(nn.Module):
     """commons/layers.py:125-185: k hashed lookups into one shared table, summed in the
     order c = 0..k-1, then L2-normalised or scaled by 1/sqrt(k).  One kernel instead of
@@ -388,9 +413,11 @@ class CosineVectorEmbedding(nn.Module):
         z = F.normalize(x, p=2.0, dim=-1) @ self.projection_mat
         return (torch.bucketize(z, self.grid).view(-1, self.n_proj) + self.pos_offset.unsqueeze(0))
 
+    def bag(self, idxs: torch.Tensor) -> torch.Tensor:
+        """EmbeddingBag(mode='sum') half (commons/transformers/layers.py:469): idxs [M, n_proj] -> [M, emb_dim]."""
+        return _PoolFn.apply(self.emb.grad_anchor(), idxs, None, None, self.emb, N.HASH_IDENTITY, 0,
+                             N.POOL_SUM, 0, False, 0)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         bs, seq_len, _ = x.size()
-        idxs = self.bucket_indices(x)
-        out = _PoolFn.apply(self.emb.grad_anchor(), idxs, None, None, self.emb, N.HASH_IDENTITY, 0,
-                            N.POOL_SUM, 0, False, 0)
-        return out.view(bs, seq_len, self.emb_dim)
+        return self.bag(self.bucket_indices(x)).view(bs, seq_len, self.emb_dim)

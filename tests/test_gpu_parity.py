@@ -12,6 +12,9 @@ from recommendations_b200 import _native as N
 from recommendations_b200 import ops
 from oracle import embedding_oracle as O
 from conftest import seeded_ids
+from tolerances import (assert_sums_close, dense_grad64 as _dense_grad64, kshift_adagrad_budget,
+                        kshift_adagrad_error_bound as _kshift_adagrad_error_bound,
+                        assert_adagrad_trajectory_close as _assert_adagrad_trajectory_close)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -213,11 +216,13 @@ def test_cosine_vector_embedding_golden(golden):
     # the bag-sum op itself on the reference's own indices: exact
     got = ops.pool_fwd(m.emb.weight.detach(), T(g["idxs"]).to(DEV), hash_mode=N.HASH_IDENTITY)
     assert torch.equal(got.cpu().view(g["out"].shape), T(g["out"]))
-    if agree == 1.0:
-        out = m(x)
-        assert torch.equal(out.cpu(), T(g["out"]))
-        out.backward(T(g["grad_out"]).to(DEV))
-        close(m.emb.weight.grad, T(g["grad_weight"]))
+    # the module's own bag + backward on the reference's indices: unconditional
+    out = m.bag(T(g["idxs"]).to(DEV)).view(g["out"].shape)
+    assert torch.equal(out.cpu(), T(g["out"]))
+    out.backward(T(g["grad_out"]).to(DEV))
+    close(m.emb.weight.grad, T(g["grad_weight"]))
+    if agree == 1.0:  # and end to end when no projection sits on a bucket edge of this GPU's matmul
+        assert torch.equal(m(x).cpu(), T(g["out"]))
 
 
 # -------------------------------------------------------------- backward: plan ----
@@ -277,8 +282,10 @@ def test_dense_grad_vs_oracle(n, n_rows, dim):
     ids = seeded_ids(n, 41)
     grad = torch.randn(n, dim, generator=torch.Generator().manual_seed(n))
     got = _dense_grad_gpu(ids, grad, n_rows, dim)
-    want = O.dense_grad(O.row_index(ids, n_rows, 0), grad, n_rows)
-    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4 * max(1.0, math.sqrt(n / n_rows)))
+    rows = O.row_index(ids, n_rows, 0)
+    assert_sums_close(got, *_dense_grad64(rows, grad, n_rows))
+    # and the oracle's own fp32 sum (torch index_add_) obeys the same bound -- it is not tighter than ours
+    assert_sums_close(O.dense_grad(rows, grad, n_rows), *_dense_grad64(rows, grad, n_rows))
     untouched = torch.ones(n_rows, dtype=torch.bool)
     untouched[O.row_index(ids, n_rows, 0)] = False
     assert got.cpu()[untouched].abs().sum() == 0
@@ -292,10 +299,12 @@ def test_dense_grad_hot_rows_multi_level():
     got = _dense_grad_gpu(ids, dx, n_rows, dim, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
                           slots_per_grad_row=k)
     want = torch.zeros(n_rows, dim, dtype=torch.float64)
+    asum = torch.zeros(n_rows, dim, dtype=torch.float64)
     for c in range(k):
         want.index_add_(0, O.row_index(ids, n_rows, c), dx.double())
-    # integers-with-noise sums over up to n addends: compare against a float64 oracle
-    torch.testing.assert_close(got.cpu().double(), want, rtol=1e-4, atol=2e-2)
+        asum.index_add_(0, O.row_index(ids, n_rows, c), dx.double().abs())
+    # sums over up to n addends: float64 oracle, fp32 summation bound on the collapse rows
+    assert_sums_close(got, want, asum)
     assert got.cpu()[n_rows - 1].abs().sum() > 0  # the shift-1 collapse row
 
 
@@ -337,7 +346,7 @@ def test_pooled_backward_mean_weights_and_window():
     ref = (wr[rows] * use.unsqueeze(-1)).sum(1) / use.sum(1, keepdim=True).clamp(min=1)
     close(out, ref)
     ref.backward(go)
-    torch.testing.assert_close(mod.emb.weight.grad.cpu(), wr.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(mod.emb.weight.grad.cpu(), wr.grad, rtol=1e-5, atol=1e-5)
 
 
 # ----------------------------------------------------- backward: fused updates ----
@@ -374,6 +383,8 @@ def test_kshift_train_loop_golden(golden):
     k = int(g["k"])
     ids, target = T(g["ids"]).to(DEV), T(g["target"]).to(DEV)
     n_rows = g["weight0"].shape[0]
+    bound = _kshift_adagrad_error_bound(g)
+    # the fixture itself (torch fp32, dense CPU backward) sits inside the same budget around float64
     for fused in (True, False):
         m = R.KShiftEmbedding(n_rows, 32, num_shifts=k, normalize_output=True, device=DEV)
         m.load_state_dict({"emb.weight": T(g["weight0"])})
@@ -390,16 +401,8 @@ def test_kshift_train_loop_golden(golden):
             opt.step()
             losses.append(loss.item())
         np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
-        # Adagrad divides by sqrt(sum g^2): an update is lr * g / |g|-ish, so the few rows whose
-        # gradient is a heavily cancelling sum of hundreds of k-shift-collapsed terms
-        # amplify fp32 summation-order noise.  Contract: >= 99.9 % of the weights inside the
-        # north-star 1e-5, every weight inside 2e-3 (torch's own dense / sparse / CUDA backward
-        # orders differ from each other in the same way).
         got, want = m.emb.weight.detach().cpu(), T(g["weight3"])
-        err = (got - want).abs()
-        ok = err <= 1e-5 + 1e-5 * want.abs()
-        assert ok.float().mean().item() >= 0.999, ok.float().mean().item()
-        assert err.max().item() <= 2e-3, err.max().item()
+        _assert_adagrad_trajectory_close(got, want, bound, f"fused={fused}")
 
 
 @pytest.mark.parametrize("kind", ["sgd", "adagrad", "rowwise_adagrad", "adam", "adamw"])
@@ -445,10 +448,11 @@ def test_fused_optimizers_vs_oracle(kind, dtype):
             O.lazy_adam_step(w, gw, touched, s1, s2, cfg.lr, cfg.betas, cfg.eps, wd, step,
                              decoupled=(kind == "adamw"))
     got = m._emb_table.weight.detach().cpu().float()
+    # north-star tolerances: 1e-5 (fp32) / 1e-2 (bf16) on updated weights and optimizer state
     torch.testing.assert_close(got, w.bfloat16().float() if bf else w,
-                               rtol=2e-2 if bf else 1e-4, atol=2e-2 if bf else 1e-5)
+                               rtol=RTOL16 if bf else RTOL32, atol=ATOL16 if bf else ATOL32)
     if not bf and kind != "sgd":
-        torch.testing.assert_close(m._emb_table.opt_state1.cpu(), s1, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(m._emb_table.opt_state1.cpu(), s1, rtol=RTOL32, atol=1e-6)
 
 
 def test_sparse_flag_gives_coo_grad():
@@ -611,9 +615,11 @@ def test_cfg1_lthm_product_front_end():
     w_ref, s_ref = w.clone(), torch.zeros_like(w)
     O.adagrad_step(w_ref, wr.grad, s_ref, lr=0.5)
     assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item()) + 1e-9
-    got = ks2.emb.weight.cpu()
-    err = (got - w_ref).abs()
-    assert (err <= 1e-5 + 1e-5 * w_ref.abs()).float().mean().item() >= 0.999 and err.max().item() <= 1.01
+    # Adagrad from a zero accumulator moves an element by lr * G / |G|: 1e-5 wherever G is well above the
+    # fp32 summation noise of its terms, the demonstrated budget (tests/tolerances.py) elsewhere -- a full
+    # +-lr sign flip is only admitted where float64 says |G| is below that noise
+    budget = kshift_adagrad_budget(ids, target, w, k, 0.5, steps=1)
+    _assert_adagrad_trajectory_close(ks2.emb.weight.cpu(), w_ref, budget, "cfg1 table update")
 
 
 @pytest.mark.parametrize("dim,dtype,k", [(64, torch.float32, 8), (32, torch.float32, 16), (128, torch.bfloat16, 4),
@@ -661,3 +667,39 @@ def test_grad_div_equals_materialised_epilogue_backward(dim, dtype, k, update):
     assert torch.equal(results[0][0], results[1][0])
     if results[0][1] is not None:
         assert torch.equal(results[0][1], results[1][1])
+
+
+def test_mask_model_train_loop_golden(golden):
+    """embedding_module_gen.train_mask_model body (:70-118): nn.Sequential(KShiftEmbedding(N, 4, k = 16),
+    MLP(4, 1, [64])) + BCEWithLogits + Adagrad(lr 0.5) over positives and uniform-random int64 negatives,
+    three steps, against the fixture the reference classes produced.  D = 4: 16-byte rows, one lane per row."""
+    from tolerances import mask_mlp, mask_model_budget
+    g = golden("mask_model_train")
+    k = int(g["k"])
+    n_rows = g["sd0/0.emb.weight"].shape[0]
+    budget = mask_model_budget(g)
+    for fused in (False, True):
+        ks = R.KShiftEmbedding(n_rows, 4, num_shifts=k, normalize_output=False, device=DEV)
+        model = torch.nn.Sequential(ks, mask_mlp(4).to(DEV))
+        model.load_state_dict({n[4:]: T(g[n]) for n in g.files if n.startswith("sd0/")})
+        if fused:
+            ks.emb.enable_fused_optimizer(kind="adagrad", lr=float(g["lr"]))
+            opts = [R.FusedEmbeddingOptimizer([ks.emb]), torch.optim.Adagrad(model[1].parameters(), lr=float(g["lr"]))]
+        else:
+            opts = [torch.optim.Adagrad(model.parameters(), lr=float(g["lr"]))]
+        losses = []
+        for step in range(3):
+            ids = T(g["ids"][step]).to(DEV)
+            target = torch.cat([torch.ones(ids.numel() // 2), torch.zeros(ids.numel() // 2)]).to(DEV)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(model(ids).squeeze(1), target)
+            loss.backward()
+            for o in opts:
+                o.step()
+                o.zero_grad()
+            losses.append(loss.item())
+        np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
+        _assert_adagrad_trajectory_close(ks.emb.weight.detach().cpu(), T(g["sd3/0.emb.weight"]), budget,
+                                         f"mask model fused={fused}")
+        for n in ("1.model.0.weight", "1.model.2.weight"):  # dense torch layers (cuBLAS vs CPU GEMM): sanity only
+            e = (model.state_dict()[n].cpu() - T(g[f"sd3/{n}"])).abs()
+            assert (e <= 1e-3 + 1e-3 * T(g[f"sd3/{n}"]).abs()).float().mean().item() >= 0.99, n
