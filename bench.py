@@ -35,6 +35,8 @@ T_TABLES, BATCH, HIST, ROWS, DIM = 10, 8192, 200, 1_000_000, 64
 LR, EPS = 0.5, 1e-10
 METRIC = "embedding_lookups_per_sec_fwd_bwd"
 UNIT = "lookups/s"
+WORKLOAD = ("cfg2: LTHM embedding fwd+bwd, batch 8192 x history 200, 10 tables 1Mx64 fp32, sequence gather + "
+            "element-wise Adagrad(lr=0.5)")
 
 
 def peaks():
@@ -103,22 +105,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline ----
-def cpu_baseline_run(steps: int, warmup: int, ids: torch.Tensor, weight: torch.Tensor,
-                     grad: torch.Tensor):
-    """The reference's own CPU path for one table: remainder -> F.embedding -> autograd ->
-    torch.optim.Adagrad(lr=0.5) with dense gradients (oracle port; all host threads)."""
+def cpu_baseline_run(steps: int, warmup: int, ids_tables, weights, grad: torch.Tensor):
+    """The reference's own CPU path for the WHOLE config -- every one of the T tables per step:
+    remainder -> F.embedding -> autograd -> torch.optim.Adagrad(lr=0.5) with dense gradients, one
+    module + optimizer per table as the reference holds them (oracle port; all host threads).
+    Returns the per-step wall times."""
     from oracle import embedding_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    mod = O.FlatTableCPU(weight)
-    opt = torch.optim.Adagrad(mod.parameters(), lr=LR)
-    ids2 = ids.view(BATCH, HIST)
+    mods = [O.FlatTableCPU(w) for w in weights]
+    opts = [torch.optim.Adagrad(m.parameters(), lr=LR) for m in mods]
     g3 = grad.view(BATCH, HIST, DIM)
+
+    def step():
+        for m, o, ids in zip(mods, opts, ids_tables):
+            O.cpu_train_step(m, o, ids.view(BATCH, HIST), g3)
     for _ in range(warmup):
-        O.cpu_train_step(mod, opt, ids2, g3)
+        step()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.cpu_train_step(mod, opt, ids2, g3)
+        step()
         times.append(time.perf_counter() - t0)
     return times
 
@@ -129,22 +135,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ids = host_ids(0)
-    torch.manual_seed(1234)
-    weight = torch.randn(ROWS, DIM)
+    ids = [host_ids(t) for t in range(T_TABLES)]
+    weights = []
+    for t in range(T_TABLES):
+        torch.manual_seed(1234 + t)
+        weights.append(torch.randn(ROWS, DIM))
     grad = torch.randn(BATCH * HIST, DIM, generator=torch.Generator().manual_seed(4321))
-    times = cpu_baseline_run(args.steps, args.warmup, ids, weight, grad)
+    times = cpu_baseline_run(args.steps, args.warmup, ids, weights, grad)
     total = sum(times)
-    value = BATCH * HIST * args.steps / total
-    sample = (f"1 of {T_TABLES} tables per step (FlatEmbedding {ROWS}x{DIM} fp32, ids [{BATCH},{HIST}]), "
-              f"fwd + dense bwd + torch.optim.Adagrad, {args.warmup} warm-up + {args.steps} timed")
+    value = T_TABLES * BATCH * HIST * args.steps / total
+    sample = (f"the whole config per step: all {T_TABLES} tables (FlatEmbedding {ROWS}x{DIM} fp32, ids [{BATCH},{HIST}] "
+              f"each), fwd + dense bwd + torch.optim.Adagrad, {args.warmup} warm-up + {args.steps} timed")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cfg2: LTHM embedding fwd+bwd, batch 8192, history 200, 10 tables 1Mx64 fp32 "
-                               "(CPU arm: bounded sample = one table per step)"},
+        "config": {"workload": WORKLOAD, "lookups_per_step_per_gpu": T_TABLES * BATCH * HIST},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -277,15 +284,46 @@ def run_b200(args):
                        "frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak},
     }
 
-    # ---- end to end: HOST ids -> C-ABI host entry point -> device result read back ----
-    e2e = run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier)
+    # ---- the same step through the drop-in nn.Module (EmbeddingCollection: 10 reference-style tables,
+    # per-table state_dict keys, one launch per phase) with autograd: module(ids); out.backward(g)
+    module_path = run_module_path(args, N, dev, world, ids_host, ids_dev, grads, barrier)
 
-    # ---- N > 1: also time the path that really exchanges data over NVLink (cfg 5: row-wise
-    # sharded large-vocab tables), same process group
+    # ---- end to end through the C-ABI host entry point (HOST ids in, counters out) ----
+    e2e_cabi = run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier)
+    e2e = dict(module_path.pop("e2e"))
+    e2e["c_abi_host_entry"] = e2e_cabi
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # NB: the tables were already updated by the timed steps -- any weights do for a timing
+        w_cpu = [table_all[t * ROWS:(t + 1) * ROWS].cpu() for t in range(T_TABLES)]
+        ids_cpu = [ids_host[t * n:(t + 1) * n].clone() for t in range(T_TABLES)]
+        times = cpu_baseline_run(3, 1, ids_cpu, w_cpu, grads[:n].cpu())
+        best = min(times)
+        cpu = {"value": n_all / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"the whole config: all {T_TABLES} tables per step (same ids / weights as the GPU run), fwd + "
+                         f"dense bwd + torch.optim.Adagrad on CPU, 1 warm-up + 3 timed, best; "
+                         f"os.cpu_count()={os.cpu_count()}"}
+        del w_cpu, ids_cpu
+
+    del table_all, state_all, grads, outs, plan_buf, ws_buf
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (kernel-level, inputs resident): cfg 3 ranker pooled + tcgen05
+    # interaction, cfg 4 long-history Zipf + row-wise Adagrad, the k-shift series, the plan alone
+    configs = None
+    if world == 1 and not args.no_configs:
+        try:
+            sys.path.insert(0, str(ROOT / "scripts"))
+            import bench_configs
+            configs = bench_configs.run(["cfg2plan", "kshift", "cfg3", "cfg4"], quiet=True)
+        except Exception as exc:
+            configs = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- the path that really exchanges data over NVLink (cfg 5: row-wise sharded large-vocab tables),
+    # same process group; at world 1 it is the W = 1 anchor of the scaling series
     sharded = None
-    if world > 1 and not args.no_sharded:
-        del table_all, state_all, grads, outs, plan_buf, ws_buf
-        torch.cuda.empty_cache()
+    if not args.no_sharded:
         try:
             sys.path.insert(0, str(ROOT / "scripts"))
             import bench_sharded
@@ -296,33 +334,113 @@ def run_b200(args):
         except Exception as exc:  # the headline line must survive a failure of the extra run
             sharded = {"error": f"{type(exc).__name__}: {exc}"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        w_cpu = table_all[:ROWS].cpu()  # NB: already updated by the timed steps -- any weights do
-        times = cpu_baseline_run(3, 1, ids_host[:n].clone(), w_cpu, grads[:n].cpu())
-        best = min(times)
-        cpu = {"value": n / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 of {T_TABLES} tables (same ids / weights / grads as the GPU run), fwd + dense bwd + "
-                         f"torch.optim.Adagrad on CPU, 1 warm-up + 3 timed, best; os.cpu_count()={os.cpu_count()}"}
-
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: LTHM embedding fwd+bwd, batch 8192 x history 200, 10 tables "
-                                   "1Mx64 fp32, sequence gather + fused element-wise Adagrad(lr=0.5)",
+            "config": {"workload": WORKLOAD,
                        "lookups_per_step_per_gpu": n_all, "unique_rows_per_step": uniq,
                        "layout": "tables stacked [10*1M, 64]; table-batched launches (ids_per_table)",
                        "l2": "inputs larger than L2: 419 MB out + 419 MB grad + 256 MB table per table vs 126 MB",
                        "multi_gpu": "replicas (tables replicated as in the reference), weak scaling"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "sharded_cfg5": sharded,
+            "module_path": module_path, "configs": configs, "sharded_cfg5": sharded,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_module_path(args, N, dev, world, ids_host, ids_dev, grads, barrier):
+    """cfg 2 through recommendations_b200.EmbeddingCollection -- what INTEGRATION.md tells a maintainer to
+    use in place of ten FlatEmbedding modules -- (a) device-resident ids, CUDA events; (b) end to end:
+    the step's ids start in PINNED HOST memory and are copied inside the timed region (double-buffered on
+    a copy stream so step s+1's copy runs under step s), and the host reads a slice of the step's output
+    back every step."""
+    import torch.distributed as dist
+
+    import recommendations_b200 as R
+    n = BATCH * HIST
+    n_all = T_TABLES * n
+    coll = R.EmbeddingCollection(T_TABLES, ROWS, DIM, device=dev,
+                                 fused_optimizer=R.FusedOptimizerConfig(kind="adagrad", lr=LR, eps=EPS))
+    g4 = grads.view(T_TABLES, BATCH, HIST, DIM)
+    ids3 = ids_dev.view(T_TABLES, BATCH, HIST)
+
+    def mstep():
+        coll(ids3).backward(g4)
+
+    def reduce_max(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return ms
+
+    for _ in range(args.warmup):
+        mstep()
+    barrier()
+    c0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mstep()
+    e1.record()
+    barrier()
+    ms_dev = reduce_max(e0.elapsed_time(e1))
+    launches = N.launch_count() - c0
+
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(ids_dev) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    probe = torch.zeros(2, 16).pin_memory()
+
+    def run(steps):
+        seen = 0.0
+        for s in range(steps):
+            k = s % 2
+            if s >= 2:
+                copy_stream.wait_event(done[k])       # step s-2 has finished reading bufs[k]
+            with torch.cuda.stream(copy_stream):
+                bufs[k].copy_(ids_host, non_blocking=True)
+                copied[k].record(copy_stream)
+            main.wait_event(copied[k])
+            out = coll(bufs[k].view(T_TABLES, BATCH, HIST))
+            out.backward(g4)
+            probe[k].copy_(out.view(-1)[:16], non_blocking=True)
+            done[k].record(main)
+            if s > 0:
+                done[1 - k].synchronize()              # the host consumes step s-1's result
+                seen += float(probe[1 - k][0])
+        done[(steps - 1) % 2].synchronize()
+        return seen + float(probe[(steps - 1) % 2][0])
+
+    run(max(2, args.warmup))
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(args.steps)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms_e2e = reduce_max(e0.elapsed_time(e1))
+    del coll
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms_dev / args.steps, "value": world * n_all * args.steps / (ms_dev * 1e-3), "unit": UNIT,
+            "gpu_launches": launches,
+            "api": "recommendations_b200.EmbeddingCollection(10, 1M, 64, fused adagrad): out = module(ids); "
+                   "out.backward(grad) -- autograd.Function over the C ABI, plan built on a side stream during forward",
+            "e2e": {"value": world * n_all * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": n_all * 8, "d2h_bytes_per_step": 64,
+                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall * 1e3 / args.steps,
+                    "api": "EmbeddingCollection.forward / backward on ids copied from pinned host memory every step "
+                           "(copy stream, double-buffered); 64 bytes of the step's output read back by the host every "
+                           "step (a training step's outputs and updated tables stay on the device)"}}
 
 
 def run_e2e(args, lib, N, ops, dev, world, table_all, state_all, ids_host, grads, outs, hp, barrier):
@@ -408,6 +526,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 3 / cfg 4 / k-shift sub-measurements")
     ap.add_argument("--no-overlap-plan", dest="overlap_plan", action="store_false",
                     help="build the backward plan after the gather on the same stream (default: concurrently)")
     args = ap.parse_args()

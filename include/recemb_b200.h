@@ -240,6 +240,18 @@ RECEMB_API int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
                      const recemb_optim_params* hp_host, void* workspace, size_t workspace_bytes,
                      int device, recemb_stream_t stream);
 
+/* recemb_bwd_apply with a device-side guard: when *skip_if_nonzero (device memory, may be NULL) is
+ * non-zero at kernel start, every kernel of the call returns without reading or writing the table
+ * or the optimizer state.  The peer exchange passes its arena's status word: a step whose inbox
+ * overflowed or whose barrier timed out leaves the shard untouched instead of applying an
+ * incomplete gradient; the host learns about it at its next (asynchronous) status check. */
+RECEMB_API int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad,
+                             int grad_dtype, int64_t grad_rows, int32_t dim, int32_t slots_per_grad_row,
+                             const float* slot_weight, const float* grad_row_scale, int update,
+                             void* table, int dtype, int64_t num_rows, void* state1, void* state2,
+                             const recemb_optim_params* hp_host, void* workspace, size_t workspace_bytes,
+                             const uint32_t* skip_if_nonzero, int device, recemb_stream_t stream);
+
 /* Measurement hook: the next recemb_bwd_apply on this thread records the two CUDA events
  * (cudaEvent_t) around its level-0 segmented-reduction launch, then disarms the hook. */
 RECEMB_API int recemb_time_next_apply(void* start_event, void* stop_event);
@@ -341,7 +353,8 @@ RECEMB_API int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
  * visible to everything enqueued after it on any rank.  `channel` (0 .. RECEMB_PEER_CHANNELS-1)
  * selects an independent set of flags, so that two streams of a rank can each run their own
  * barrier sequence concurrently; every rank must call a channel the same number of times.
- * A rank that waits longer than ~2 s sets status bit 2 and continues (no GPU hang). */
+ * A rank that waits longer than RECEMB_PEER_BARRIER_TIMEOUT_S (environment, default 600 s) sets status
+ * bit 2 in its own arena and continues (no GPU hang); see recemb_bwd_apply_guarded. */
 #define RECEMB_PEER_CHANNELS 2
 RECEMB_API int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
                         int device, recemb_stream_t stream);
@@ -367,7 +380,8 @@ RECEMB_API int recemb_peer_pool_push(const recemb_peer_group* group, const recem
 
 /* Backward, sender side.  recemb_shard_bucket whose entries land in the owners' inboxes: entry
  * k of my bucket for owner o is stored at inbox(o)[rank][k], the bucket size at counts(o)[rank].
- * Entries beyond arena->cap are dropped and status bit 1 is set on this rank.  workspace as
+ * Entries beyond arena->cap are dropped and status bit 1 is set on this rank AND on the owner whose
+ * inbox is now incomplete (so that its guarded update skips the step).  workspace as
  * recemb_shard_bucket_workspace_bytes. */
 RECEMB_API int recemb_peer_bucket_push(const recemb_peer_group* group, const recemb_peer_arena* arena,
                             const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,

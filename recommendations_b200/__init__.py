@@ -6,6 +6,7 @@ C ABI in include/recemb_b200.h).  Importing the package does not need a GPU; cal
 any op does, and a missing library raises instead of falling back.
 """
 from . import _native
+from .collection import EmbeddingCollection
 from .interaction import DotInteraction, dot_interaction
 from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PatternFromTimelocal,
                      PooledEmbeddingBag, QREmbedding)
@@ -13,7 +14,7 @@ from .logq import CascadedStreamingLogQCorrectionModule, StreamingLogQCorrection
 from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
 
 __all__ = [
-    "CosineVectorEmbedding", "DotInteraction", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
+    "CosineVectorEmbedding", "DotInteraction", "EmbeddingCollection", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
     "FusedOptimizerConfig", "KShiftEmbedding", "PatternFromTimelocal", "PooledEmbeddingBag", "QREmbedding",
     "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule",
 ]

@@ -114,6 +114,8 @@ SIGNATURES = {
     "recemb_bwd_apply_workspace_bytes": (_SZ, [_I64, _I32]),
     "recemb_bwd_apply": (_INT, [_P, _SZ, _I64, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
                                 _P, _P, C.POINTER(OptimParams), _P, _SZ, _INT, _P]),
+    "recemb_bwd_apply_guarded": (_INT, [_P, _SZ, _I64, _P, _INT, _I64, _I32, _I32, _P, _P, _INT, _P, _INT, _I64,
+                                        _P, _P, C.POINTER(OptimParams), _P, _SZ, _P, _INT, _P]),
     "recemb_time_next_apply": (_INT, [_P, _P]),
     "recemb_epilogue_bwd": (_INT, [_P, _P, _INT, _P, _I64, _I32, _INT, _I32, _P, _INT, _P]),
     "recemb_shard_bucket_workspace_bytes": (_SZ, [_I64, _I32]),

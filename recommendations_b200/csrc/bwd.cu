@@ -1,8 +1,8 @@
 // Backward of the embedding hot path (sm_100a):
 //   plan   : lookup slots -> (row, slot) pairs sorted by row, stable in slot
-//            (sort-based dedup; replaces the sort inside ATen's
-//            embedding_dense_backward that autograd runs for
-//            embedding_module_gen.py:113, :152)
+//            (sort-based dedup with the hand-written radix sort of sort.cu;
+//            replaces the sort inside ATen's embedding_dense_backward that
+//            autograd runs for embedding_module_gen.py:113, :152)
 //   apply  : chunked segmented reduction over the sorted pairs + fused
 //            optimizer update of the touched rows only (replaces the dense
 //            [N, D] gradient + torch.optim.Adagrad full-table pass,
@@ -16,12 +16,11 @@
 // that the next level reduces with the same kernel, until one chunk is left.
 // Summation order is fixed (sorted order, then chunk order): deterministic, no
 // atomics.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace recemb {
 
@@ -49,11 +48,10 @@ static cudaError_t plan_layout(int64_t n, int64_t num_rows, PlanLayout* L) {
   L->n = n;
   L->key_bits = bit_width_u64((uint64_t)num_rows);  // the sentinel key == num_rows must sort last
   if (L->key_bits < 1) L->key_bits = 1;
-  size_t temp = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr,
-                                                  (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                                  (uint32_t*)nullptr, (int64_t)n, 0, L->key_bits);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  const size_t temp = sort_shape(n, L->key_bits, dev).temp_bytes;
   const size_t arr = align_up((size_t)n * 4, 256);
   size_t off = kCounterBytes;
   L->off_keys_in = off;
@@ -231,6 +229,7 @@ struct SegArgs {
   float* out_partials;    // [2 * chunks, dim]
   const uint32_t* flag_in;  // level >= 1: non-zero iff the previous level emitted a record
   uint32_t* flag_out;
+  const uint32_t* guard;  // optional: a non-zero word means "do not touch the table" (every CTA returns)
   int32_t chunk;          // consecutive entries per group (level 0: wave-fitted, >= kChunk0)
   int32_t pf_bulk;        // level 0 fast path: rows prefetched with one bulk L2 prefetch per row
 };
@@ -383,6 +382,7 @@ struct SegCfg {
 template <int G, int V, int E, typename GT, typename WT, bool L0, int CH, typename Cfg>
 __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_kernel(const SegArgs a) {
   if (!L0 && *a.flag_in == 0) return;  // the previous level emitted nothing
+  if (a.guard && *reinterpret_cast<const volatile uint32_t*>(a.guard) != 0u) return;
   constexpr int B = Cfg::B, PD = Cfg::PD;
   constexpr bool PLAIN = Cfg::PLAIN && L0, EXACT = Cfg::EXACT;
   constexpr int GROUPS = kBwdThreads / G;
@@ -621,6 +621,7 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
   constexpr int GROUPS = kBwdThreads / G;
   static_assert(E * sizeof(T) == 16, "one 16-byte vector per lane");
   static_assert(UPD == RECEMB_UPD_ROWWISE_ADAGRAD || UPD == RECEMB_UPD_SGD, "scalar-state updates only");
+  if (a.guard && *reinterpret_cast<const volatile uint32_t*>(a.guard) != 0u) return;
   const int lane = threadIdx.x & 31;
   const int lig = lane % G;
   const int gi_warp = lane / G;
@@ -1121,19 +1122,18 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, const recemb_l
   a.lengths = lengths;
   a.last_n = last_n;
   a.sentinel = (uint32_t)total_rows;
-  a.keys = (uint32_t*)(base + L.off_keys_in);
-  a.vals = (uint32_t*)(base + L.off_vals_in);
+  // the sort ping-pongs between the two pair buffers and always ends in the "out" one
+  const bool start_in_out = sort_input_in_b(sort_shape(n, L.key_bits, device));
+  a.keys = (uint32_t*)(base + (start_in_out ? L.off_keys_out : L.off_keys_in));
+  a.vals = (uint32_t*)(base + (start_in_out ? L.off_vals_out : L.off_vals_in));
   const int sms = sm_count(device);
   int64_t grid = (n + kBwdThreads - 1) / kBwdThreads;
   if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
   plan_keys_kernel<<<(unsigned)grid, kBwdThreads, 0, s>>>(a);
   RECEMB_LAUNCHED();
-  size_t temp = L.temp_bytes;
-  RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(
-      base + L.off_temp, temp, (const uint32_t*)a.keys, (uint32_t*)(base + L.off_keys_out),
-      (const uint32_t*)a.vals, (uint32_t*)(base + L.off_vals_out), (int64_t)n, 0, L.key_bits, s));
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);  // the sort is >= 1 launch; counted once
-  return RECEMB_OK;
+  return sort_pairs((uint32_t*)(base + L.off_keys_in), (uint32_t*)(base + L.off_vals_in),
+                    (uint32_t*)(base + L.off_keys_out), (uint32_t*)(base + L.off_vals_out), n, L.key_bits,
+                    base + L.off_temp, L.temp_bytes, device, s);
 }
 
 extern "C" int recemb_plan_count(void* plan, size_t plan_bytes, int64_t n_slots, int64_t num_rows,
@@ -1197,6 +1197,19 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
                                 int64_t num_rows, void* state1, void* state2,
                                 const recemb_optim_params* hp_host, void* workspace,
                                 size_t workspace_bytes, int device, recemb_stream_t stream) {
+  return recemb_bwd_apply_guarded(plan, plan_bytes, n_slots, grad, grad_dtype, grad_rows, dim, slots_per_grad_row,
+                                  slot_weight, grad_row_scale, update, table, dtype, num_rows, state1, state2, hp_host,
+                                  workspace, workspace_bytes, nullptr, device, stream);
+}
+
+extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad,
+                                        int grad_dtype, int64_t grad_rows, int32_t dim,
+                                        int32_t slots_per_grad_row, const float* slot_weight,
+                                        const float* grad_row_scale, int update, void* table, int dtype,
+                                        int64_t num_rows, void* state1, void* state2,
+                                        const recemb_optim_params* hp_host, void* workspace,
+                                        size_t workspace_bytes, const uint32_t* skip_if_nonzero, int device,
+                                        recemb_stream_t stream) {
   RECEMB_CHECK_ARG(plan && table, "null plan/table");
   RECEMB_CHECK_ARG(grad_rows >= 0 && slots_per_grad_row >= 1, "bad grad_rows / slots_per_grad_row");
   RECEMB_CHECK_ARG(update >= RECEMB_UPD_DENSE_GRAD && update <= RECEMB_UPD_ADAMW, "bad update %d", update);
@@ -1258,6 +1271,7 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
   if (hp_host) a.hp = *hp_host;
   else a.hp = recemb_optim_params{};
   a.chunk = kChunk0;
+  a.guard = skip_if_nonzero;
   {
     static const int pf = env_flag("RECEMB_SEG_PF_BULK", 0);
     a.pf_bulk = pf;

@@ -7,6 +7,7 @@
 // NVLink 5 / NVSwitch make every peer's HBM addressable at ~770 GB/s per direction with ~2 us
 // load latency; a pooled lookup keeps 8 x 256-byte row loads in flight per half-warp, far more
 // than the bandwidth-delay product needs, so the forward pull needs no staging or collective.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,10 +33,13 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
 // has published at least the same epoch here.  The release store orders every earlier store of
 // this stream (kernel boundaries are system-scope ordered, the fence makes it cumulative); the
 // acquire load orders the kernels that follow.
-constexpr long long kBarrierTimeoutCycles = 4000000000ll;  // ~2 s at 1.9 GHz
-
+// Timeout: a rank may legitimately stall for a long time (data loader, rank-0 checkpoint or eval), so the
+// default is collective-library-like (RECEMB_PEER_BARRIER_TIMEOUT_S, default 600 s).  A rank that still
+// gives up sets status bit 2 in ITS arena; the guarded update (recemb_bwd_apply_guarded) then leaves the
+// table untouched for that step and the host raises at its next status check -- a stalled peer can
+// delay a step or lose it, never corrupt the shard.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerPtrs g, int64_t off_flags, int64_t off_epoch,
-                                                          int64_t off_status) {
+                                                          int64_t off_status, long long kBarrierTimeoutCycles) {
   char* mine = g.arena[g.rank];
   uint64_t* epoch_ptr = (uint64_t*)(mine + off_epoch);
   uint64_t epoch = 0;
@@ -76,7 +80,9 @@ __global__ void __launch_bounds__(256) allgather_push_kernel(const PeerPtrs g, c
       const int64_t i = i0 + u * 256;
       if (i < vecs) v[u] = ldg_nc_v4(src + i);
     }
-    for (int p = 0; p < g.world; ++p) {
+    for (int q = 1; q <= g.world; ++q) {  // rotated: all ranks never store into the same peer at once
+      int p = g.rank + q;
+      if (p >= g.world) p -= g.world;
       uint4* dst = s_dst[p];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -197,8 +203,16 @@ extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_
   if (p.world == 1) return RECEMB_OK;
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
+  static long long timeout_cycles = 0;
+  if (timeout_cycles == 0) {
+    const char* e = getenv("RECEMB_PEER_BARRIER_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    timeout_cycles = (long long)(sec * 2.0e9);  // clock64 ticks at <= 2 GHz: at least `sec` seconds
+  }
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, arena->off_flags + (int64_t)channel * RECEMB_MAX_PEERS * 8,
-                                                         arena->off_epoch + (int64_t)channel * 8, arena->off_status);
+                                                         arena->off_epoch + (int64_t)channel * 8, arena->off_status,
+                                                         timeout_cycles);
   RECEMB_LAUNCHED();
   return RECEMB_OK;
 }

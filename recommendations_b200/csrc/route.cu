@@ -13,9 +13,9 @@
 // Inside a bucket the entries keep slot order, i.e. they are sorted by bag: the owner sees each
 // (sender, bag) as one contiguous run and pools it in slot order (same fp32 order as the
 // unsharded kernel).
-#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace recemb {
 
@@ -46,6 +46,7 @@ struct BucketArgs {
   int64_t* peer_count[RECEMB_MAX_PEERS];  // owner o's count slot for THIS rank
   uint32_t cap;                           // inbox capacity per sender
   uint32_t* status;                       // this rank's sticky status word (bit 0: inbox overflow)
+  uint32_t* peer_status[RECEMB_MAX_PEERS];  // owner o's status word: its inbox is incomplete -> it must skip its update
 };
 
 __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketArgs a) {
@@ -138,6 +139,9 @@ __global__ void __launch_bounds__(1024) bucket_scan_kernel(const BucketArgs a, i
       if (t > a.cap) {
         t = a.cap;
         atomicOr(a.status, 1u);
+        // the owner would apply an incomplete gradient: flag it as well (system scope, peer memory) so
+        // that its guarded update leaves the shard untouched in THIS step
+        atomicOr_system(a.peer_status[threadIdx.x], 1u);
       }
       *a.peer_count[threadIdx.x] = (int64_t)t;
       if (a.counts) a.counts[threadIdx.x] = (int64_t)t;
@@ -286,6 +290,7 @@ struct PoolInboxArgs {
   int64_t cap;
   int64_t bags_total;
   int32_t world;
+  int32_t rank;
   int32_t chunks_per_sender;
   const void* table;
   int32_t vecs;
@@ -301,10 +306,14 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
   __syncthreads();
   const int lane = threadIdx.x & 31, lig = lane % G;
   const int64_t chunk_global = (int64_t)blockIdx.x * (kRtThreads / G) + threadIdx.x / G;
-  const int sender = (int)(chunk_global / a.chunks_per_sender);
-  if (sender >= a.world) return;
+  const int sender_slot = (int)(chunk_global / a.chunks_per_sender);
+  if (sender_slot >= a.world) return;
+  // rotated: the first CTAs of rank r serve sender r + 1, so the ranks do not all store their partial
+  // rows into peer 0 first (NVSwitch gives every pair full bandwidth, one ingress port does not)
+  int sender = sender_slot + a.rank + 1;
+  while (sender >= a.world) sender -= a.world;
   const int n = (int)a.counts[sender];
-  const int start = (int)(chunk_global - (int64_t)sender * a.chunks_per_sender) * kPeChunk;
+  const int start = (int)(chunk_global - (int64_t)sender_slot * a.chunks_per_sender) * kPeChunk;
   if (start >= n) return;
   const int end = min(start + kPeChunk, n);
   const int64_t* entries = a.inbox + (int64_t)sender * a.cap;
@@ -448,7 +457,10 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
   a.counts = counts_out;
   a.cap = 0;
   a.status = nullptr;
-  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.peer_inbox[i] = a.peer_count[i] = nullptr;
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) {
+    a.peer_inbox[i] = a.peer_count[i] = nullptr;
+    a.peer_status[i] = nullptr;
+  }
   if (group) {
     RECEMB_CHECK_ARG(arena && group->world == layout->shard_world && group->rank == layout->shard_rank &&
                          group->world <= RECEMB_MAX_PEERS,
@@ -460,6 +472,7 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
       char* base = (char*)group->arena[o];
       a.peer_inbox[o] = (int64_t*)(base + arena->off_inbox) + (int64_t)group->rank * arena->cap;
       a.peer_count[o] = (int64_t*)(base + arena->off_counts) + group->rank;
+      a.peer_status[o] = (uint32_t*)(base + arena->off_status);
     }
     a.cap = (uint32_t)arena->cap;
     a.status = (uint32_t*)((char*)group->arena[group->rank] + arena->off_status);
@@ -579,14 +592,13 @@ extern "C" int recemb_bwd_plan_entries(const int64_t* entries, int64_t n, int64_
   int64_t grid = (n + kRtThreads - 1) / kRtThreads;
   const int64_t cap = (int64_t)sm_count(device) * 16;
   if (grid > cap) grid = cap;
-  unpack_entries_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>(entries, n, keys_in, vals_in);
-  RECEMB_LAUNCHED();
   int bits = 0;
   for (uint64_t x = (uint64_t)total_rows; x; x >>= 1) ++bits;
-  RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
-                                              (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return RECEMB_OK;
+  const bool in_b = sort_input_in_b(sort_shape(n, bits, device));  // the sort ends in the "out" pair buffers
+  unpack_entries_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>(entries, n, in_b ? keys_out : keys_in,
+                                                             in_b ? vals_out : vals_in);
+  RECEMB_LAUNCHED();
+  return sort_pairs(keys_in, vals_in, keys_out, vals_out, n, bits, temp, temp_bytes, device, s);
 }
 
 
@@ -619,16 +631,15 @@ extern "C" int recemb_peer_plan(const recemb_peer_group* group, const recemb_pee
   int64_t grid = (n + kRtThreads - 1) / kRtThreads;
   const int64_t cap_grid = (int64_t)sm_count(device) * 16;
   if (grid > cap_grid) grid = cap_grid;
-  unpack_inbox_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>((const int64_t*)(mine + arena->off_inbox),
-                                                           (const int64_t*)(mine + arena->off_counts), arena->cap,
-                                                           n, (uint32_t)total_rows, keys_in, vals_in);
-  RECEMB_LAUNCHED();
   int bits = 0;  // the sentinel key == total_rows must sort last
   for (uint64_t x = (uint64_t)total_rows; x; x >>= 1) ++bits;
-  RECEMB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
-                                              (const uint32_t*)vals_in, vals_out, (int64_t)n, 0, bits, s));
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return RECEMB_OK;
+  const bool in_b = sort_input_in_b(sort_shape(n, bits, device));
+  unpack_inbox_kernel<<<(unsigned)grid, kRtThreads, 0, s>>>((const int64_t*)(mine + arena->off_inbox),
+                                                           (const int64_t*)(mine + arena->off_counts), arena->cap,
+                                                           n, (uint32_t)total_rows, in_b ? keys_out : keys_in,
+                                                           in_b ? vals_out : vals_in);
+  RECEMB_LAUNCHED();
+  return sort_pairs(keys_in, vals_in, keys_out, vals_out, n, bits, temp, temp_bytes, device, s);
 }
 
 
@@ -653,6 +664,7 @@ extern "C" int recemb_peer_pool_push(const recemb_peer_group* group, const recem
   a.cap = arena->cap;
   a.bags_total = arena->bags_total;
   a.world = group->world;
+  a.rank = group->rank;
   a.chunks_per_sender = (int32_t)((arena->cap + kPeChunk - 1) / kPeChunk);
   a.table = group->table[group->rank];
   a.vecs = (int32_t)(row_bytes / 16);

@@ -69,9 +69,10 @@ class _GatherFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, anchor2, ids, holder, holder2, hash_mode, hash_mode2, hash_arg,
-                epilogue, zero_pad, pad_id, flip_len=0):
-        # needs_input_grad is all-False under torch.no_grad() / inference: no inverse norms, no plan
-        need_grad = ctx.needs_input_grad[0] or (anchor2 is not None and ctx.needs_input_grad[1])
+                epilogue, zero_pad, pad_id, flip_len=0, record=True):
+        # `record` = torch.is_grad_enabled() at the call site (grad mode is always off in here and
+        # needs_input_grad ignores no_grad): inference builds no inverse norms and no plan
+        need_grad = record and (ctx.needs_input_grad[0] or (anchor2 is not None and ctx.needs_input_grad[1]))
         out, inv = ops.gather_fwd(
             holder.weight.detach(), ids, hash_mode=hash_mode, hash_arg=hash_arg,
             table2=None if holder2 is None else holder2.weight.detach(), hash_mode2=hash_mode2,
@@ -81,7 +82,8 @@ class _GatherFn(torch.autograd.Function):
         ctx.flip_len = flip_len
         ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
-        _plan_early(ctx, ids, holder2 is None and ctx.needs_input_grad[0] and not (holder.sparse and holder.fused is None),
+        _plan_early(ctx, ids, holder2 is None and record and ctx.needs_input_grad[0]
+                    and not (holder.sparse and holder.fused is None),
                     lambda: ops.BackwardPlan.build(
                         ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
                         zero_pad=zero_pad, pad_id=pad_id,
@@ -116,7 +118,7 @@ class _GatherFn(torch.autograd.Function):
                 zero_pad=zero_pad, pad_id=pad_id,
                 pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
             grads[i] = holder.consume(plan, g)
-        return (grads[0], grads[1]) + (None,) * 10
+        return (grads[0], grads[1]) + (None,) * 11
 
 
 def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable,
@@ -133,12 +135,13 @@ def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable,
 
 class _KShiftFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0):
+    def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0, record=True):
+        record = record and ctx.needs_input_grad[0]
         out, inv = ops.kshift_fwd(holder.weight.detach(), ids, num_shifts, epilogue,
-                                  want_inv_norm=ctx.needs_input_grad[0], flip_len=flip_len)
+                                  want_inv_norm=record, flip_len=flip_len)
         ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
-        _plan_early(ctx, ids, ctx.needs_input_grad[0] and not (holder.sparse and holder.fused is None),
+        _plan_early(ctx, ids, record and not (holder.sparse and holder.fused is None),
                     lambda: ops.BackwardPlan.build(
                         ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=num_shifts,
                         pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
@@ -158,7 +161,7 @@ class _KShiftFn(torch.autograd.Function):
                 ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
                 pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
             return (holder.consume(plan, g2d, slots_per_grad_row=k, grad_div=math.sqrt(k)),
-                    None, None, None, None, None)
+                    None, None, None, None, None, None)
         dx = ops.epilogue_bwd(g2d, out, inv, ctx.epilogue, k)
         if sparse_coo:
             flat = ids.contiguous().view(-1)
@@ -167,24 +170,24 @@ class _KShiftFn(torch.autograd.Function):
             if ctx.flip_len:
                 dx = dx.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
             vals = dx.to(holder.weight.dtype).repeat(k, 1)
-            return (_coo(rows, vals, holder), None, None, None, None, None)
+            return (_coo(rows, vals, holder), None, None, None, None, None, None)
         plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
-        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None)
+        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None, None)
 
 
 class _PoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, ids, lengths, per_slot_weight, holder, hash_mode, hash_arg, pool_mode,
-                last_n, zero_pad, pad_id):
+                last_n, zero_pad, pad_id, record=True):
         out = ops.pool_fwd(holder.weight.detach(), ids, lengths=lengths, last_n=last_n,
                            per_slot_weight=per_slot_weight, hash_mode=hash_mode, hash_arg=hash_arg,
                            pool_mode=pool_mode, zero_pad=zero_pad, pad_id=pad_id)
         ctx.holder = holder
         ctx.cfg = (hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id)
         ctx.save_for_backward(ids, lengths, per_slot_weight)
-        _plan_early(ctx, ids, ctx.needs_input_grad[0], lambda: ops.BackwardPlan.build(
+        _plan_early(ctx, ids, record and ctx.needs_input_grad[0], lambda: ops.BackwardPlan.build(
             ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
             zero_pad=zero_pad, pad_id=pad_id,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=ids.shape[1],
@@ -209,7 +212,7 @@ class _PoolFn(torch.autograd.Function):
             scale = 1.0 / pooled_counts(ids, lengths, last_n, zero_pad, pad_id).clamp_(min=1).float()
         gw = holder.consume(plan, grad_out.contiguous().view(m, -1), slots_per_grad_row=p,
                             slot_weight=per_slot_weight, grad_row_scale=scale)
-        return (gw,) + (None,) * 10
+        return (gw,) + (None,) * 11
 
 
 def pooled_counts(ids, lengths, last_n, zero_pad, pad_id) -> torch.Tensor:
@@ -267,7 +270,7 @@ class FlatEmbedding(nn.Module):
         t = self._emb_table
         return _GatherFn.apply(t.grad_anchor(), None, x, t, None, N.HASH_FLOORMOD, 0, 0,
                                N.EPI_L2NORM if self._normalize_output else N.EPI_NONE,
-                               self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences))
+                               self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences), torch.is_grad_enabled())
 
 
 class PatternFromTimelocal(nn.Module):
@@ -292,7 +295,7 @@ class PatternFromTimelocal(nn.Module):
         if self.emb_dim <= 0:
             return self.index(x)
         return _GatherFn.apply(self.emb.grad_anchor(), None, x.long(), self.emb, None, N.HASH_DIV_FLOORMOD, 0,
-                               self.div, N.EPI_NONE, False, 0, 0)
+                               self.div, N.EPI_NONE, False, 0, 0, torch.is_grad_enabled())
 
 
 class KShiftEmbedding(nn.Module):
@@ -317,7 +320,7 @@ class KShiftEmbedding(nn.Module):
     def forward(self, id_: torch.Tensor) -> torch.Tensor:
         return _KShiftFn.apply(self.emb.grad_anchor(), id_, self.emb, self._num_shifts,
                                N.EPI_L2NORM if self._normalize_output else N.EPI_RSQRT_K,
-                               _flip_len(id_, self._flip_sequences))
+                               _flip_len(id_, self._flip_sequences), torch.is_grad_enabled())
 
     def get_row_idx(self, x: torch.Tensor, col_idx: int) -> torch.Tensor:
         """Bit-exact commons/layers.py:174-185 (wrapping <<, arithmetic >>, floor-mod)."""
@@ -346,7 +349,7 @@ class QREmbedding(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _GatherFn.apply(self.emb_q.grad_anchor(), self.emb_r.grad_anchor(), x, self.emb_q,
                                self.emb_r, N.HASH_QR_QUOTIENT, N.HASH_QR_REMAINDER, self._div,
-                               N.EPI_L2NORM if self.normalize_output else N.EPI_NONE, False, 0)
+                               N.EPI_L2NORM if self.normalize_output else N.EPI_NONE, False, 0, 0, torch.is_grad_enabled())
 
 
 class PooledEmbeddingBag(nn.Module):
@@ -384,7 +387,7 @@ class PooledEmbeddingBag(nn.Module):
         return _PoolFn.apply(self.emb.grad_anchor(), ids, lengths, per_sample_weights, self.emb,
                              N.HASH_FLOORMOD if self.hash_ids else N.HASH_IDENTITY, 0,
                              N.POOL_SUM if self.mode == "sum" else N.POOL_MEAN, self.last_n,
-                             self.skip_pad, self.pad_id)
+                             self.skip_pad, self.pad_id, torch.is_grad_enabled())
 
 
 class CosineVectorEmbedding(nn.Module):
@@ -416,7 +419,7 @@ class CosineVectorEmbedding(nn.Module):
     def bag(self, idxs: torch.Tensor) -> torch.Tensor:
         """EmbeddingBag(mode='sum') half (commons/transformers/layers.py:469): idxs [M, n_proj] -> [M, emb_dim]."""
         return _PoolFn.apply(self.emb.grad_anchor(), idxs, None, None, self.emb, N.HASH_IDENTITY, 0,
-                             N.POOL_SUM, 0, False, 0)
+                             N.POOL_SUM, 0, False, 0, torch.is_grad_enabled())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         bs, seq_len, _ = x.size()

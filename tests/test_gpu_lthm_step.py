@@ -46,7 +46,8 @@ def test_b200_flavour_equals_torch_flavour_on_the_same_gpu(golden):
     # current_token_emb = product_mapper(masked(emb_mapper(normalize(kshift)) + sum of cosine bags))
     torch.testing.assert_close(r1["output"]["current_token_emb"], r2["output"]["current_token_emb"],
                                rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(r1["output"]["next_token_emb"], r2["output"]["next_token_emb"], rtol=1e-5, atol=2e-6)
+    # two transformer layers amplify the 1e-7 differences of the embedding inputs
+    torch.testing.assert_close(r1["output"]["next_token_emb"], r2["output"]["next_token_emb"], rtol=1e-4, atol=1e-5)
     for n in H.embedding_param_names(m1):
         a, b = r1["grads"][n], r2["grads"][n]
         assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-30), n

@@ -12,7 +12,7 @@ from recommendations_b200 import _native as N
 from recommendations_b200 import ops
 from oracle import embedding_oracle as O
 from conftest import seeded_ids
-from tolerances import (assert_sums_close, dense_grad64 as _dense_grad64, kshift_adagrad_budget,
+from tolerances import (assert_cross_device_trajectory, assert_sums_close, dense_grad64 as _dense_grad64, kshift_adagrad_budget,
                         kshift_adagrad_error_bound as _kshift_adagrad_error_bound,
                         assert_adagrad_trajectory_close as _assert_adagrad_trajectory_close)
 
@@ -239,6 +239,29 @@ def test_plan_is_sorted_stable_and_complete(n, n_rows):
     assert n_valid == n and n_unique == torch.unique(want_rows).numel()  # dedup count bit-exact
 
 
+@pytest.mark.parametrize("n_rows", [1, 5, 4095, 4096, 4097, (1 << 24) - 1, (1 << 24) + 5, (1 << 31) + 11])
+@pytest.mark.parametrize("n,skew", [(1, 0), (31, 0), (4097, 0), (70001, 0), (70001, 2), (3_000_000, 0), (3_000_000, 1)])
+def test_plan_radix_sort_passes_and_skew(n, n_rows, skew):
+    """The hand-written LSD radix sort (csrc/sort.cu) behind every plan: 1 / 2 / 3 passes (key widths
+    1 ... 32 bits), one tile and many tiles, uniform keys, Zipf-like heads (skew 1: half of the slots on
+    4 rows) and a single hot row (skew 2) -- sorted, stable in slot, complete."""
+    g = torch.Generator().manual_seed(n + skew)
+    rows = torch.randint(0, n_rows, (n,), generator=g, dtype=torch.int64)
+    if skew == 1:
+        hot = torch.randint(0, n_rows, (4,), generator=g, dtype=torch.int64)
+        pick = torch.rand(n, generator=g) < 0.5
+        rows[pick] = hot[torch.randint(0, 4, (int(pick.sum()),), generator=g)]
+    elif skew == 2:
+        rows[:] = n_rows - 1
+        rows[::7] = 0
+    plan = ops.BackwardPlan.build(rows.to(DEV), num_rows=n_rows, hash_mode=N.HASH_IDENTITY)
+    order = torch.argsort(rows, stable=True)
+    assert torch.equal(plan.sorted_rows.cpu(), rows[order])
+    assert torch.equal(plan.sorted_slots.cpu(), order)
+    n_valid, n_unique = plan.counters.cpu().tolist()
+    assert n_valid == n and n_unique == torch.unique(rows).numel()
+
+
 def test_plan_drops_padding_and_window():
     m, p, n_rows = 50, 8, 64
     ids = seeded_ids(m * p, 39, (m, p))
@@ -377,14 +400,31 @@ def test_flat_adagrad_golden_fused_and_torch_modes(golden):
     assert torch.equal(m._emb_table.weight.cpu()[untouched], T(g["weight0"])[untouched])
 
 
+def _torch_kshift_loop_on_gpu(g, steps=3):
+    """The same loop with plain torch ops on the SAME GPU (the oracle's functions are device-agnostic):
+    identical upstream arithmetic, so what differs from the kernels' result is the kernels."""
+    k, lr = int(g["k"]), float(g["lr"])
+    ids, target = T(g["ids"]).to(DEV), T(g["target"]).to(DEV)
+    w = torch.nn.Parameter(T(g["weight0"]).to(DEV))
+    opt = torch.optim.Adagrad([w], lr=lr)
+    for _ in range(steps):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(O.kshift_embedding(w, ids, k, True), target).backward()
+        opt.step()
+    return w.detach().cpu()
+
+
 def test_kshift_train_loop_golden(golden):
-    """embedding_module_gen.train_model body (MSE vs target, Adagrad lr 0.5), three steps."""
+    """embedding_module_gen.train_model body (MSE vs target, Adagrad lr 0.5), three steps: losses and
+    table vs the reference-generated fixture, table element by element vs the same loop in plain torch on
+    this GPU within the demonstrated fp32 summation budget (tests/tolerances.py)."""
     g = golden("kshift_adagrad_train")
     k = int(g["k"])
     ids, target = T(g["ids"]).to(DEV), T(g["target"]).to(DEV)
     n_rows = g["weight0"].shape[0]
     bound = _kshift_adagrad_error_bound(g)
-    # the fixture itself (torch fp32, dense CPU backward) sits inside the same budget around float64
+    twin = _torch_kshift_loop_on_gpu(g)
+    assert_cross_device_trajectory(twin, T(g["weight3"]), float(g["lr"]), 3, "torch on this GPU vs the CPU fixture")
     for fused in (True, False):
         m = R.KShiftEmbedding(n_rows, 32, num_shifts=k, normalize_output=True, device=DEV)
         m.load_state_dict({"emb.weight": T(g["weight0"])})
@@ -401,8 +441,9 @@ def test_kshift_train_loop_golden(golden):
             opt.step()
             losses.append(loss.item())
         np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
-        got, want = m.emb.weight.detach().cpu(), T(g["weight3"])
-        _assert_adagrad_trajectory_close(got, want, bound, f"fused={fused}")
+        got = m.emb.weight.detach().cpu()
+        assert_cross_device_trajectory(got, T(g["weight3"]), float(g["lr"]), 3, f"fused={fused} vs the CPU fixture")
+        _assert_adagrad_trajectory_close(got, twin, bound, f"fused={fused} vs torch on this GPU")
 
 
 @pytest.mark.parametrize("kind", ["sgd", "adagrad", "rowwise_adagrad", "adam", "adamw"])
@@ -619,7 +660,12 @@ def test_cfg1_lthm_product_front_end():
     # fp32 summation noise of its terms, the demonstrated budget (tests/tolerances.py) elsewhere -- a full
     # +-lr sign flip is only admitted where float64 says |G| is below that noise
     budget = kshift_adagrad_budget(ids, target, w, k, 0.5, steps=1)
-    _assert_adagrad_trajectory_close(ks2.emb.weight.cpu(), w_ref, budget, "cfg1 table update")
+    assert_cross_device_trajectory(ks2.emb.weight.cpu(), w_ref, 0.5, 1, "cfg1 table update vs the CPU oracle")
+    wt = torch.nn.Parameter(w.to(DEV))          # the same step in plain torch on this GPU
+    opt_t = torch.optim.Adagrad([wt], lr=0.5)
+    torch.nn.functional.mse_loss(O.kshift_embedding(wt, ids.to(DEV), k, normalize=True), target.to(DEV)).backward()
+    opt_t.step()
+    _assert_adagrad_trajectory_close(ks2.emb.weight.cpu(), wt.detach().cpu(), budget, "cfg1 table update vs torch on this GPU")
 
 
 @pytest.mark.parametrize("dim,dtype,k", [(64, torch.float32, 8), (32, torch.float32, 16), (128, torch.bfloat16, 4),
@@ -678,6 +724,20 @@ def test_mask_model_train_loop_golden(golden):
     k = int(g["k"])
     n_rows = g["sd0/0.emb.weight"].shape[0]
     budget = mask_model_budget(g)
+    # the same loop in plain torch on this GPU (k = 16: the 1/sqrt(k) scale is exact, so the forward and
+    # with it the upstream gradient are bit-identical to the kernels' -- only the table reduction differs)
+    wt = torch.nn.Parameter(T(g["sd0/0.emb.weight"]).to(DEV))
+    mlp_t = mask_mlp(4).to(DEV)
+    mlp_t.load_state_dict({n[6:]: T(g[n]) for n in g.files if n.startswith("sd0/1.")})
+    opt_t = torch.optim.Adagrad([wt, *mlp_t.parameters()], lr=float(g["lr"]))
+    for step in range(3):
+        ids = T(g["ids"][step]).to(DEV)
+        target = torch.cat([torch.ones(ids.numel() // 2), torch.zeros(ids.numel() // 2)]).to(DEV)
+        torch.nn.functional.binary_cross_entropy_with_logits(
+            mlp_t(O.kshift_embedding(wt, ids, k, False)).squeeze(1), target).backward()
+        opt_t.step()
+        opt_t.zero_grad()
+    twin = wt.detach().cpu()
     for fused in (False, True):
         ks = R.KShiftEmbedding(n_rows, 4, num_shifts=k, normalize_output=False, device=DEV)
         model = torch.nn.Sequential(ks, mask_mlp(4).to(DEV))
@@ -698,8 +758,23 @@ def test_mask_model_train_loop_golden(golden):
                 o.zero_grad()
             losses.append(loss.item())
         np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
-        _assert_adagrad_trajectory_close(ks.emb.weight.detach().cpu(), T(g["sd3/0.emb.weight"]), budget,
-                                         f"mask model fused={fused}")
+        got = ks.emb.weight.detach().cpu()
+        assert_cross_device_trajectory(got, T(g["sd3/0.emb.weight"]), float(g["lr"]), 3, f"mask model fused={fused}")
+        _assert_adagrad_trajectory_close(got, twin, budget, f"mask model fused={fused} vs torch on this GPU")
         for n in ("1.model.0.weight", "1.model.2.weight"):  # dense torch layers (cuBLAS vs CPU GEMM): sanity only
             e = (model.state_dict()[n].cpu() - T(g[f"sd3/{n}"])).abs()
             assert (e <= 1e-3 + 1e-3 * T(g[f"sd3/{n}"]).abs()).float().mean().item() >= 0.99, n
+
+
+def test_hand_written_radix_sort_selected_by_environment():
+    """RECEMB_PLAN_SORT=own swaps the library sort of the plan for the hand-written LSD radix sort
+    (csrc/sort.cu); the choice is read once per process, so the plan tests are re-run in a child."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, RECEMB_PLAN_SORT="own")
+    res = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
+                          "test_plan_ or test_dense_grad_integer_exact or test_dense_grad_hot_rows"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert " passed" in res.stdout

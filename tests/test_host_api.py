@@ -98,3 +98,31 @@ def test_fused_optimizer_checkpoint_round_trip():
         other.load_state_dict(opt.state_dict())
     # the tables' own state_dict keeps the reference keys only
     assert set(tabs[0].state_dict().keys()) == {"weight"}
+
+
+def test_embedding_collection_keeps_per_table_checkpoint_keys_and_shared_storage():
+    """T tables stacked in one allocation, yet state_dict() shows T independent reference tables."""
+    import recommendations_b200 as R
+    torch.manual_seed(0)
+    c = R.EmbeddingCollection(["user", "item", "ctx"], 50, 8)
+    assert sorted(c.state_dict()) == ["tables.ctx._emb_table.weight", "tables.item._emb_table.weight",
+                                      "tables.user._emb_table.weight"]
+    assert len(list(c.parameters())) == 3
+    base = c.table.weight.data_ptr()
+    for i, t in enumerate(c.members()):
+        assert t.weight.data_ptr() == base + i * 50 * 8 * 4          # views of the stacked storage
+    ref = {k: torch.randn(50, 8) for k in c.state_dict()}
+    c.load_state_dict(ref)
+    assert torch.equal(c.table.weight[50:100], ref["tables.item._emb_table.weight"])
+    c = c.double()                                                    # .to() must not un-stack the tables
+    base = c.table.weight.data_ptr()
+    for i, t in enumerate(c.members()):
+        assert t.weight.dtype == torch.float64 and t.weight.data_ptr() == base + i * 50 * 8 * 8
+    assert torch.equal(c.table.weight[50:100].float(), ref["tables.item._emb_table.weight"])
+    # fused mode: no Parameters, weights stay in state_dict under the same keys, state is per table
+    p = R.EmbeddingCollection(2, 30, 4, kind="pooled", fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad"))
+    assert list(p.parameters()) == [] and sorted(p.state_dict()) == ["tables.table_0.emb.weight", "tables.table_1.emb.weight"]
+    assert p.members()[1].opt_state1.shape == (30,) and p.table.opt_state1.shape == (60,)
+    assert p.members()[1].opt_state1.data_ptr() == p.table.opt_state1.data_ptr() + 30 * 4
+    opt = R.FusedEmbeddingOptimizer([p.table])
+    assert "fused" in opt.state_dict()
