@@ -333,8 +333,8 @@ typedef struct recemb_peer_arena {
   int64_t off_grads;   /* [world][bags_total][dim] pooled gradients, slice s written by rank s */
   int64_t cap;         /* inbox capacity per sender (entries) */
   int64_t bags_total;
-  int64_t off_parts;   /* [world][bags_total][dim] partial pools of MY bags, slice o written by owner o
-                          (push forward; the requester zero-fills it before the owners write) */
+  int64_t off_parts;   /* [world][bags_total][dim] partial pools of MY bags, slice o written completely by
+                          owner o (push forward) */
 } recemb_peer_arena;
 
 /* handle_out identifies the whole allocation that contains ptr; *offset_out = ptr - its base. */
@@ -355,9 +355,19 @@ RECEMB_API int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
  * barrier sequence concurrently; every rank must call a channel the same number of times.
  * A rank that waits longer than RECEMB_PEER_BARRIER_TIMEOUT_S (environment, default 600 s) sets status
  * bit 2 in its own arena and continues (no GPU hang); see recemb_bwd_apply_guarded. */
-#define RECEMB_PEER_CHANNELS 2
+#define RECEMB_PEER_CHANNELS 4
 RECEMB_API int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
                         int device, recemb_stream_t stream);
+/* The two halves of the barrier as separate launches (pipelined steps: producer and consumer on different
+ * streams).  recemb_peer_signal publishes this rank's next epoch of `channel` to every rank and never
+ * blocks: enqueue it right after the kernel whose peer stores it announces.  recemb_peer_wait blocks `stream`
+ * until every rank has published the epoch this rank is at: enqueue it right before the consumer, AFTER
+ * this rank's own signal of the same round in stream / event order.  On a channel, rounds of
+ * (signal, wait) and full barriers may be mixed as long as every rank issues the same sequence. */
+RECEMB_API int recemb_peer_signal(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                       int device, recemb_stream_t stream);
+RECEMB_API int recemb_peer_wait(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                     int device, recemb_stream_t stream);
 
 /* Forward.  As recemb_pool_fwd on the unsharded table of num_rows (GLOBAL) rows per table, except
  * that global row r is read from group->table[r % world] at local row r / world (+ the table
@@ -373,8 +383,10 @@ RECEMB_API int recemb_peer_pool_fwd(const recemb_peer_group* group, int64_t num_
  * instead of one row per lookup).  Owner side, after recemb_peer_bucket_push + barrier: every run
  * of equal (sender, bag) in MY inbox is pooled from MY shard (fp32 accumulation in slot order) and
  * the partial row is stored straight into the sender's arena at parts[rank][bag] over NVLink.
- * Pairs without an entry are not written: the requester zero-fills its parts region before the
- * barrier and sums the world slices afterwards (recemb_sum_partials, fixed owner order). */
+ * Pairs without an entry get a zero row from the same kernel (the run that follows a gap of bag numbers in
+ * a sender's region fills it; the last run fills the tail), so every row of parts[rank] is written exactly
+ * once per step and the requester needs no zero fill; it sums the world slices after the barrier
+ * (recemb_sum_partials, fixed owner order). */
 RECEMB_API int recemb_peer_pool_push(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
                           int dtype, int device, recemb_stream_t stream);
 

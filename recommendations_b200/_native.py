@@ -129,6 +129,8 @@ SIGNATURES = {
     "recemb_peer_close": (_INT, [_P, _INT]),
     "recemb_peer_arena_layout": (_INT, [_I32, _I64, _I64, _I32, _INT, C.POINTER(PeerArena)]),
     "recemb_peer_barrier": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _INT, _P]),
+    "recemb_peer_signal": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _INT, _P]),
+    "recemb_peer_wait": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _INT, _P]),
     "recemb_peer_pool_fwd": (_INT, [C.POINTER(PeerGroupStruct), _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P,
                                     _INT, _I64, _INT, _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
     "recemb_peer_pool_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _INT, _P]),

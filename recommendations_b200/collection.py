@@ -36,7 +36,7 @@ class _CollectionFn(torch.autograd.Function):
             flip_len = int(ids.shape[-1]) if coll.flip_sequences else 0
             out, _ = ops.gather_fwd(stacked, ids, zero_pad=coll.fused_pad_mask, pad_id=0, ids_per_table=per_table,
                                     flip_len=flip_len)
-            build = lambda: ops.BackwardPlan.build(  # noqa: E731
+            build = lambda: coll._all.build_plan(  # noqa: E731
                 ids, num_rows=n_rows, zero_pad=coll.fused_pad_mask, pad_id=0, ids_per_table=per_table,
                 flip_len=flip_len)
         else:
@@ -45,7 +45,7 @@ class _CollectionFn(torch.autograd.Function):
             out = ops.pool_fwd(stacked, ids.reshape(t * b, p), lengths=flat_len, last_n=coll.last_n,
                                hash_mode=coll.hash_mode, pool_mode=coll.pool_mode, zero_pad=coll.skip_pad,
                                pad_id=coll.pad_id, num_rows=n_rows, bags_per_table=b).view(t, b, -1)
-            build = lambda: ops.BackwardPlan.build(  # noqa: E731
+            build = lambda: coll._all.build_plan(  # noqa: E731
                 ids.reshape(t * b, p), num_rows=n_rows, hash_mode=coll.hash_mode, zero_pad=coll.skip_pad,
                 pad_id=coll.pad_id, bag_size=p, lengths=flat_len, last_n=coll.last_n, ids_per_table=b * p)
         ctx.coll, ctx.build = coll, build

@@ -65,6 +65,45 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerPtrs g, int6
   __threadfence_system();
 }
 
+// The two halves of the barrier as separate launches, for pipelined steps where producer and consumer
+// live on different streams: `signal` (enqueued right after the producer, never blocks) publishes this
+// rank's next epoch of the channel to every rank; `wait` (enqueued right before the consumer, after the
+// local signal in stream / event order) spins until every rank has published the epoch this rank is at.
+// A stream is then only ever blocked in front of a kernel that really needs the peers' data.
+__global__ void __launch_bounds__(32) peer_signal_kernel(const PeerPtrs g, int64_t off_flags, int64_t off_epoch) {
+  char* mine = g.arena[g.rank];
+  uint64_t* epoch_ptr = (uint64_t*)(mine + off_epoch);
+  uint64_t epoch = 0;
+  if (threadIdx.x == 0) {
+    epoch = *epoch_ptr + 1;
+    *epoch_ptr = epoch;
+  }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  if ((int)threadIdx.x < g.world) {
+    __threadfence_system();
+    st_release_sys_u64((uint64_t*)(g.arena[threadIdx.x] + off_flags) + g.rank, epoch);
+  }
+}
+
+__global__ void __launch_bounds__(32) peer_wait_kernel(const PeerPtrs g, int64_t off_flags, int64_t off_epoch,
+                                                       int64_t off_status, long long kBarrierTimeoutCycles) {
+  char* mine = g.arena[g.rank];
+  const uint64_t epoch = *(const volatile uint64_t*)(mine + off_epoch);
+  if ((int)threadIdx.x < g.world) {
+    const uint64_t* flag = (const uint64_t*)(mine + off_flags) + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(flag) < epoch) {
+      if (clock64() - t0 > kBarrierTimeoutCycles) {
+        atomicOr((uint32_t*)(mine + off_status), 2u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+
 // src -> slice `rank` of the same buffer on every rank: one read, world stores per 16-byte vector
 __global__ void __launch_bounds__(256) allgather_push_kernel(const PeerPtrs g, const uint4* __restrict__ src,
                                                             int64_t vecs, int64_t dst_offset) {
@@ -193,8 +232,16 @@ extern "C" int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
   return RECEMB_OK;
 }
 
-extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
-                                   int device, recemb_stream_t stream) {
+static long long barrier_timeout_cycles() {
+  const char* e = getenv("RECEMB_PEER_BARRIER_TIMEOUT_S");
+  double sec = e ? atof(e) : 600.0;
+  if (!(sec > 0.0)) sec = 600.0;
+  return (long long)(sec * 2.0e9);  // clock64 ticks at <= 2 GHz: at least `sec` seconds
+}
+
+// what: 0 = barrier (signal + wait in one launch), 1 = signal only, 2 = wait only
+static int barrier_launch(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel, int what,
+                          int device, recemb_stream_t stream) {
   RECEMB_CHECK_ARG(arena, "null arena");
   RECEMB_CHECK_ARG(channel >= 0 && channel < RECEMB_PEER_CHANNELS, "barrier channel %d out of range", channel);
   PeerPtrs p;
@@ -203,18 +250,30 @@ extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_
   if (p.world == 1) return RECEMB_OK;
   DeviceGuard g(device);
   RECEMB_CUDA(g.err);
-  static long long timeout_cycles = 0;
-  if (timeout_cycles == 0) {
-    const char* e = getenv("RECEMB_PEER_BARRIER_TIMEOUT_S");
-    double sec = e ? atof(e) : 600.0;
-    if (!(sec > 0.0)) sec = 600.0;
-    timeout_cycles = (long long)(sec * 2.0e9);  // clock64 ticks at <= 2 GHz: at least `sec` seconds
-  }
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, arena->off_flags + (int64_t)channel * RECEMB_MAX_PEERS * 8,
-                                                         arena->off_epoch + (int64_t)channel * 8, arena->off_status,
-                                                         timeout_cycles);
+  const long long timeout_cycles = barrier_timeout_cycles();
+  const int64_t off_flags = arena->off_flags + (int64_t)channel * RECEMB_MAX_PEERS * 8;
+  const int64_t off_epoch = arena->off_epoch + (int64_t)channel * 8;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (what == 0) peer_barrier_kernel<<<1, 32, 0, s>>>(p, off_flags, off_epoch, arena->off_status, timeout_cycles);
+  else if (what == 1) peer_signal_kernel<<<1, 32, 0, s>>>(p, off_flags, off_epoch);
+  else peer_wait_kernel<<<1, 32, 0, s>>>(p, off_flags, off_epoch, arena->off_status, timeout_cycles);
   RECEMB_LAUNCHED();
   return RECEMB_OK;
+}
+
+extern "C" int recemb_peer_barrier(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                                   int device, recemb_stream_t stream) {
+  return barrier_launch(group, arena, channel, 0, device, stream);
+}
+
+extern "C" int recemb_peer_signal(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                                  int device, recemb_stream_t stream) {
+  return barrier_launch(group, arena, channel, 1, device, stream);
+}
+
+extern "C" int recemb_peer_wait(const recemb_peer_group* group, const recemb_peer_arena* arena, int channel,
+                                int device, recemb_stream_t stream) {
+  return barrier_launch(group, arena, channel, 2, device, stream);
 }
 
 extern "C" int recemb_peer_allgather_push(const recemb_peer_group* group, const void* src, int64_t bytes,

@@ -313,24 +313,39 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
   int sender = sender_slot + a.rank + 1;
   while (sender >= a.world) sender -= a.world;
   const int n = (int)a.counts[sender];
-  const int start = (int)(chunk_global - (int64_t)sender_slot * a.chunks_per_sender) * kPeChunk;
+  const int chunk_local = (int)(chunk_global - (int64_t)sender_slot * a.chunks_per_sender);
+  const int start = chunk_local * kPeChunk;
+  uint4* out = s_parts[sender];
+  const uint32_t key_base = (uint32_t)((int64_t)sender * a.bags_total);
+  // Bags of this sender without an entry on this owner get a zero row from here as well (every row of
+  // parts[rank] is written exactly once per step, the requester never zero-fills): the run that follows
+  // a gap of bag numbers fills it, the last run of the region fills the tail.
+  auto zero_rows = [&](uint32_t k0, uint32_t k1) {  // keys [k0, k1)
+    if (lig < a.vecs)
+      for (uint32_t z = k0; z != k1; ++z) stg_v4(out + (size_t)(z - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
+  };
+  if (n == 0) {
+    if (chunk_local == 0) zero_rows(key_base, key_base + (uint32_t)a.bags_total);
+    return;
+  }
   if (start >= n) return;
   const int end = min(start + kPeChunk, n);
   const int64_t* entries = a.inbox + (int64_t)sender * a.cap;
   const uint4* table = reinterpret_cast<const uint4*>(a.table);
-  uint4* out = s_parts[sender];
-  const uint32_t key_base = (uint32_t)((int64_t)sender * a.bags_total);
   auto key_of = [&](int i) { return (uint32_t)((uint64_t)entries[i] & 0xffffffffull); };
 
   int i = start;
+  uint32_t prev_key = key_base - 1u;  // key of the run before the next one that starts in this chunk
   if (start > 0) {  // skip the tail of a run that started in an earlier chunk
-    const uint32_t prev = key_of(start - 1);
-    while (i < n && i < end && key_of(i) == prev) ++i;
-    if (i == end && i < n && key_of(i) == prev) return;
+    prev_key = key_of(start - 1);
+    while (i < n && i < end && key_of(i) == prev_key) ++i;
+    if (i == end) return;  // whole chunk inside an older run: its owner walks on (and fills the tail)
   }
   float acc[E];
   while (i < end) {  // runs starting in [start, end)
     const uint32_t key = key_of(i);
+    zero_rows(prev_key + 1u, key);
+    prev_key = key;
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
     bool more = true;
@@ -365,6 +380,7 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
     }
     if (lig < a.vecs) stg_v4(out + (size_t)(key - key_base) * a.vecs + lig, Vec16<T>::pack(acc));
   }
+  if (i >= n) zero_rows(prev_key + 1u, key_base + (uint32_t)a.bags_total);  // I closed the region's last run
 }
 
 // ------------------------------------------------------------------ plan from entries ----

@@ -84,7 +84,7 @@ class _GatherFn(torch.autograd.Function):
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         _plan_early(ctx, ids, holder2 is None and record and ctx.needs_input_grad[0]
                     and not (holder.sparse and holder.fused is None),
-                    lambda: ops.BackwardPlan.build(
+                    lambda: holder.build_plan(
                         ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
                         zero_pad=zero_pad, pad_id=pad_id,
                         pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
@@ -113,7 +113,7 @@ class _GatherFn(torch.autograd.Function):
                 keep = (ids.reshape(-1) != pad_id) if zero_pad else None
                 grads[i] = _coo(rows, vals, holder, keep)
                 continue
-            plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
+            plan = _plan_take(ctx, lambda: holder.build_plan(
                 ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
                 zero_pad=zero_pad, pad_id=pad_id,
                 pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
@@ -142,7 +142,7 @@ class _KShiftFn(torch.autograd.Function):
         ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
         ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         _plan_early(ctx, ids, record and not (holder.sparse and holder.fused is None),
-                    lambda: ops.BackwardPlan.build(
+                    lambda: holder.build_plan(
                         ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=num_shifts,
                         pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
         return out
@@ -157,7 +157,7 @@ class _KShiftFn(torch.autograd.Function):
         if ctx.epilogue == N.EPI_RSQRT_K and not sparse_coo:
             # x / sqrt(k) (commons/layers.py:170): its backward is a division of every gradient
             # element -- folded into the segmented reduction, dx is never materialised
-            plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
+            plan = _plan_take(ctx, lambda: holder.build_plan(
                 ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
                 pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
             return (holder.consume(plan, g2d, slots_per_grad_row=k, grad_div=math.sqrt(k)),
@@ -171,7 +171,7 @@ class _KShiftFn(torch.autograd.Function):
                 dx = dx.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
             vals = dx.to(holder.weight.dtype).repeat(k, 1)
             return (_coo(rows, vals, holder), None, None, None, None, None, None)
-        plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
+        plan = _plan_take(ctx, lambda: holder.build_plan(
             ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
         return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None, None)
@@ -187,7 +187,7 @@ class _PoolFn(torch.autograd.Function):
         ctx.holder = holder
         ctx.cfg = (hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id)
         ctx.save_for_backward(ids, lengths, per_slot_weight)
-        _plan_early(ctx, ids, record and ctx.needs_input_grad[0], lambda: ops.BackwardPlan.build(
+        _plan_early(ctx, ids, record and ctx.needs_input_grad[0], lambda: holder.build_plan(
             ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
             zero_pad=zero_pad, pad_id=pad_id,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=ids.shape[1],
@@ -202,7 +202,7 @@ class _PoolFn(torch.autograd.Function):
         holder = ctx.holder
         hash_mode, hash_arg, pool_mode, last_n, zero_pad, pad_id = ctx.cfg
         m, p = ids.shape
-        plan = _plan_take(ctx, lambda: ops.BackwardPlan.build(
+        plan = _plan_take(ctx, lambda: holder.build_plan(
             ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
             zero_pad=zero_pad, pad_id=pad_id,
             pad_row=-1 if holder.padding_idx is None else holder.padding_idx, bag_size=p,

@@ -194,15 +194,18 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
               state2: Optional[torch.Tensor] = None, hp: Optional[N.OptimParams] = None,
               slot_weight: Optional[torch.Tensor] = None,
               grad_row_scale: Optional[torch.Tensor] = None,
-              workspace: Optional[torch.Tensor] = None, grad_div: float = 0.0) -> None:
+              workspace: Optional[torch.Tensor] = None, grad_div: float = 0.0,
+              guard: Optional[torch.Tensor] = None) -> None:
     """Segmented reduction of `grad` rows over the plan + `update` on `table` (in place).
-    grad_div > 0: gradient elements are divided by it on the fly (k-shift 1/sqrt(k) backward)."""
+    grad_div > 0: gradient elements are divided by it on the fly (k-shift 1/sqrt(k) backward).
+    guard (int32 / uint32 device word): the update is skipped entirely when it is non-zero at kernel start
+    (the peer exchange's status word: overflowed inbox / timed-out barrier -> the shard stays untouched)."""
     dim = table.shape[1]
     grad2d = grad.contiguous().view(-1, dim)
     if plan.slots_cover_grad and grad2d.shape[0] * slots_per_grad_row != plan.n_slots:
         raise N.NativeError(
             f"grad has {grad2d.shape[0]} rows x {slots_per_grad_row} slots, plan has {plan.n_slots}")
-    dev = N.require_cuda(plan.buf, grad2d, table, state1, state2, slot_weight, grad_row_scale)
+    dev = N.require_cuda(plan.buf, grad2d, table, state1, state2, slot_weight, grad_row_scale, guard)
     lib = N.load()
     need = int(lib.recemb_bwd_apply_workspace_bytes(plan.n_slots, dim))
     if workspace is None or workspace.numel() < need:
@@ -213,11 +216,11 @@ def bwd_apply(plan: BackwardPlan, grad: torch.Tensor, *, table: torch.Tensor, up
             raise N.NativeError("grad_div cannot be combined with slot_weight / grad_row_scale")
         hp = N.OptimParams.from_buffer_copy(hp)
         hp.grad_div = grad_div
-    N.check(lib.recemb_bwd_apply(
+    N.check(lib.recemb_bwd_apply_guarded(
         N.ptr(plan.buf), plan.buf.numel(), plan.n_slots, N.ptr(grad2d), N.dtype_code(grad2d.dtype),
         grad2d.shape[0], dim, slots_per_grad_row, N.ptr(slot_weight), N.ptr(grad_row_scale), update,
         N.ptr(table), N.dtype_code(table.dtype), table.shape[0], N.ptr(state1), N.ptr(state2),
-        C.byref(hp), N.ptr(workspace), workspace.numel(), dev, N.stream_ptr(dev)),
+        C.byref(hp), N.ptr(workspace), workspace.numel(), N.ptr(guard), dev, N.stream_ptr(dev)),
         "recemb_bwd_apply")
 
 
@@ -285,12 +288,16 @@ def plan_from_entries(entries: torch.Tensor, total_rows: int) -> "BackwardPlan":
     return BackwardPlan(buf=buf, n_slots=n, num_rows=total_rows, slots_per_id=1, slots_cover_grad=False)
 
 
-def sum_partials(parts: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+def sum_partials(parts: torch.Tensor, row_scale: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[world, rows, dim] per-owner partial pools -> [rows, dim], fixed owner order, fp32 accumulate."""
     parts = parts.contiguous()
-    dev = N.require_cuda(parts, row_scale)
+    dev = N.require_cuda(parts, row_scale, out)
     w, rows, dim = parts.shape
-    out = torch.empty((rows, dim), dtype=parts.dtype, device=parts.device)
+    if out is None:
+        out = torch.empty((rows, dim), dtype=parts.dtype, device=parts.device)
+    elif tuple(out.shape) != (rows, dim) or out.dtype != parts.dtype:
+        raise N.NativeError("preallocated `out` has the wrong shape / dtype")
     N.check(N.load().recemb_sum_partials(N.ptr(parts), w, rows, dim, N.dtype_code(parts.dtype),
                                          N.ptr(row_scale), N.ptr(out), dev, N.stream_ptr(dev)),
             "recemb_sum_partials")
@@ -365,14 +372,28 @@ def peer_barrier(group, channel: int = 0) -> None:
                                          N.stream_ptr(group.device)), "recemb_peer_barrier")
 
 
-def peer_plan(group, total_rows: int) -> "BackwardPlan":
-    """Owner side (after the barrier): plan over my inbox, world * cap pairs, unused ones = sentinel."""
+def peer_signal(group, channel: int) -> None:
+    """First half of a barrier round on the current stream (never blocks): see recemb_peer_signal."""
+    N.check(N.load().recemb_peer_signal(C.byref(group.struct), C.byref(group.layout), channel, group.device,
+                                        N.stream_ptr(group.device)), "recemb_peer_signal")
+
+
+def peer_wait(group, channel: int) -> None:
+    """Second half: the current stream blocks until every rank has signalled this round of `channel`."""
+    N.check(N.load().recemb_peer_wait(C.byref(group.struct), C.byref(group.layout), channel, group.device,
+                                      N.stream_ptr(group.device)), "recemb_peer_wait")
+
+
+def peer_plan(group, total_rows: int, buf: Optional[torch.Tensor] = None) -> "BackwardPlan":
+    """Owner side (after the barrier): plan over my inbox, world * cap pairs, unused ones = sentinel.
+    `buf`: plan memory kept by the caller from step to step (reallocated when too small)."""
     lib = N.load()
     n = group.world * int(group.layout.cap)
     need = int(lib.recemb_bwd_plan_bytes(n, total_rows))
     if need == 0:
         N.check(-2, "recemb_bwd_plan_bytes")
-    buf = torch.empty((need,), dtype=torch.uint8, device=group.arena.device)
+    if buf is None or buf.numel() < need or buf.device != group.arena.device:
+        buf = torch.empty((need,), dtype=torch.uint8, device=group.arena.device)
     N.check(lib.recemb_peer_plan(C.byref(group.struct), C.byref(group.layout), total_rows, N.ptr(buf), buf.numel(),
                                  group.device, N.stream_ptr(group.device)), "recemb_peer_plan")
     return BackwardPlan(buf=buf, n_slots=n, num_rows=total_rows, slots_per_id=1, slots_cover_grad=False)

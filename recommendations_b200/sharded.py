@@ -43,6 +43,8 @@ NVLink bytes per GPU per step (W = 8, b = 8192, P = 20, T tables, R = row bytes)
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Optional
 
 import torch
@@ -297,14 +299,14 @@ class _PeerPoolFn(torch.autograd.Function):
     def _forward_push(ctx, ids, lengths, module, pg, main):
         """Owner-side partial pooling: entries to the owners, one partial row per (bag, owner)
         pair back -- (W-1) b T R bytes over NVLink at most instead of (W-1)/W n R.
-          main: zero my parts -> bucket + push entries -> barrier -> pool my inbox, STORE the
-                partial rows into the requesters' parts -> [join side] -> barrier -> sum parts
+          main: bucket + push entries -> barrier -> pool my inbox, STORE the partial rows into
+                the requesters' parts (zero rows for pairs without an entry) -> [join side] ->
+                barrier -> sum parts
           side: (after the first barrier) unpack + sort of my inbox = the backward plan
         The owners only read their own shard, so no barrier guards the table rows; inbox, parts
         and gradient buffers are protected by the three barriers of the step."""
         dt = module.emb.weight.dtype
         parts = pg.parts_view(module.emb_dim, dt)
-        parts.zero_()
         ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths, last_n=module.last_n,
                              zero_pad=module.skip_pad, pad_id=module.pad_id, **module._own_batching(ids))
         ops.peer_barrier(pg, channel=0)
@@ -354,13 +356,149 @@ class _PeerPoolFn(torch.autograd.Function):
         ops.peer_barrier(pg, channel=0)
         main.wait_event(ctx.plan_ready)
         _mark(module, "barrier+plan")
+        # guard = my arena's status word: an overflowed inbox (flagged by the sender) or a timed-out
+        # barrier leaves the shard untouched in this step; the host raises at its next status check
         res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype),
-                                 slots_per_grad_row=1)
+                                 slots_per_grad_row=1, guard=pg.status_word())
         _mark(module, "apply")
         ctx.plan = None
         pg.snapshot_status()
         module._peer_dirty = True
         return res, None, None, None
+
+
+CH_ENTRIES, CH_PARTS, CH_GRADS, CH_REPEAT = 0, 1, 2, 3   # barrier channels of a pipelined group's arena
+
+
+class _PeerPipelinedFn(torch.autograd.Function):
+    """exchange="peer", push forward, T >= 2 tables: the step is cut into table groups, each with its own
+    exchange arena, and the kernels are issued by ROLE, not by group: everything bound by the local HBM
+    stays on the caller's stream, everything bound by NVLink goes to a second stream, the sort of the
+    inboxes to a third.  The groups are staggered by construction (the NVLink stream works on group g while
+    the HBM stream buckets group g + 1 / sums group g - 1 / updates group g - 1), and no stream ever sits in
+    a full barrier: a producer SIGNALS its peers right after its kernel, a consumer WAITS right before its
+    own (recemb_peer_signal / recemb_peer_wait, one flag set per group and phase).
+
+      forward   main: bucket + push entries_g, signal E_g        (all g)  ...  wait P_g, sum parts_g  (all g)
+                nv:   wait E_g, pool my inbox_g + STORE partial rows to the requesters, signal P_g     (all g)
+                side: (after wait E_g) unpack + sort inbox_g = the backward plan of group g            (all g)
+      backward  nv:   push gradients_g to every owner, [join sort_g], signal G_g                      (all g)
+                main: wait G_g, segmented reduction + update of group g's rows of my shard            (all g)
+
+    Hazards: my inbox_g is refilled by a peer's bucket of the NEXT step, which that peer enqueues after its
+    update_g, i.e. after it waited for my G_g -- which I only signal once my pooling and my sort of inbox_g
+    are done.  parts_g / gradient buffer_g are refilled after the peer waited for my next E_g, which I signal
+    after sum_g / update_g (stream order on main).  Owners read only their own shard; the nv stream's pooling
+    of the next step starts after main's bucket of that step, i.e. after the update.
+    Same kernels and per-group arithmetic as _PeerPoolFn's push path: the forward is bit-identical."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, module):
+        groups = module._pipe
+        dev = ids.device
+        main = torch.cuda.current_stream(dev)
+        nv, side = module._pipe_streams(dev)
+        t, dim, dt = module.num_tables, module.emb_dim, module.emb.weight.dtype
+        b = ids.shape[0] // t
+        for grp in groups:
+            grp.pg.raise_on_status()
+        need = bool(ctx.needs_input_grad[0])
+        out = torch.empty((ids.shape[0], dim), dtype=dt, device=dev)
+        scale = None
+        if module.mode == "mean":
+            scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad, module.pad_id).clamp_(min=1).float()
+        pooled = []
+        for grp in groups:
+            pg, rows = grp.pg, slice(grp.t0 * b, grp.t1 * b)
+            tg = grp.t1 - grp.t0
+            batching = dict(bags_per_table=b, num_tables=tg) if tg > 1 else dict(bags_per_table=0, num_tables=0)
+            ops.peer_bucket_push(pg, ids[rows], num_rows=module.num_embeddings,
+                                 lengths=None if lengths is None else lengths[rows], last_n=module.last_n,
+                                 zero_pad=module.skip_pad, pad_id=module.pad_id, **batching)
+            ops.peer_signal(pg, CH_ENTRIES)
+            bucketed = torch.cuda.Event()
+            bucketed.record(main)
+            with torch.cuda.stream(nv):
+                nv.wait_event(bucketed)
+                ops.peer_wait(pg, CH_ENTRIES)
+                arrived = torch.cuda.Event()
+                arrived.record(nv)
+                ops.peer_pool_push(pg, dim, dt)
+                ops.peer_signal(pg, CH_PARTS)
+                ev = torch.cuda.Event()
+                ev.record(nv)
+                pooled.append(ev)
+            grp.plan, grp.plan_ready = None, None
+            if need:
+                with torch.cuda.stream(side):
+                    side.wait_event(arrived)
+                    grp.plan = ops.peer_plan(pg, tg * module.local_rows, buf=grp.plan_buf)
+                    grp.plan_buf = grp.plan.buf
+                    grp.plan_ready = torch.cuda.Event()
+                    grp.plan_ready.record(side)
+        for grp, ev in zip(groups, pooled):
+            pg, rows = grp.pg, slice(grp.t0 * b, grp.t1 * b)
+            main.wait_event(ev)
+            ops.peer_wait(pg, CH_PARTS)
+            ops.sum_partials(pg.parts_view(dim, dt), None if scale is None else scale[rows], out=out[rows])
+        module._peer_dirty = False
+        ctx.module, ctx.b = module, b
+        ctx.save_for_backward(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (scale,) = ctx.saved_tensors
+        module, b = ctx.module, ctx.b
+        groups = module._pipe
+        dim, dt = module.emb_dim, module.emb.weight.dtype
+        g = grad_out.contiguous()
+        if scale is not None:
+            g = g * scale.unsqueeze(1).to(g.dtype)
+        if g.dtype != dt:
+            g = g.to(dt)
+        dev = g.device
+        main = torch.cuda.current_stream(dev)
+        nv, _ = module._pipe_streams(dev)
+        nv.wait_stream(main)
+        g.record_stream(nv)
+        pushed = []
+        with torch.cuda.stream(nv):
+            for grp in groups:
+                pg, rows = grp.pg, slice(grp.t0 * b, grp.t1 * b)
+                if grp.plan is None:
+                    raise N.NativeError("pipelined peer step: backward without a recorded forward")
+                if module._peer_dirty:
+                    # two backward passes without a forward in between: the peers' previous update may still be
+                    # reading the gradient buffer this pass overwrites
+                    ops.peer_barrier(pg, channel=CH_REPEAT)
+                ops.peer_allgather_push(pg, g[rows], int(pg.layout.off_grads))
+                nv.wait_event(grp.plan_ready)   # my G_g also tells the peers that inbox_g may be refilled
+                ops.peer_signal(pg, CH_GRADS)
+                ev = torch.cuda.Event()
+                ev.record(nv)
+                pushed.append(ev)
+        module.emb.begin_update()
+        for grp, ev in zip(groups, pushed):
+            pg = grp.pg
+            main.wait_event(ev)
+            ops.peer_wait(pg, CH_GRADS)
+            module.emb._apply_fused(grp.plan, pg.grads_view(dim, dt), 1, None, None, 0.0,
+                                    rows=(grp.t0 * module.local_rows, grp.t1 * module.local_rows),
+                                    guard=pg.status_word())
+            pg.snapshot_status()
+            grp.plan = None
+        module.emb.end_update()
+        module._peer_dirty = True
+        return None, None, None, None
+
+
+class _PipeGroup:
+    """Tables [t0, t1) of the stacked shard with their own exchange arena."""
+
+    def __init__(self, t0: int, t1: int, pg: PeerGroup):
+        self.t0, self.t1, self.pg = t0, t1, pg
+        self.plan, self.plan_ready, self.plan_buf = None, None, None
 
 
 class RowWiseShardedEmbeddingBag(nn.Module):
@@ -382,7 +520,7 @@ class RowWiseShardedEmbeddingBag(nn.Module):
                  reduce_partials: Optional[Callable] = None, exchange: Optional[str] = None,
                  bucket: Optional[Callable] = None, pool_entries: Optional[Callable] = None,
                  entries_backward: Optional[Callable] = None, capacity_factor: Optional[float] = None,
-                 peer_forward: Optional[str] = None):
+                 peer_forward: Optional[str] = None, pipeline_groups: Optional[int] = None):
         super().__init__()
         if mode not in ("sum", "mean"):
             raise ValueError("mode must be 'sum' or 'mean'")
@@ -416,6 +554,14 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         if peer_forward not in ("pull", "push"):
             raise ValueError("peer_forward must be 'pull' or 'push'")
         self.peer_forward = peer_forward
+        # peer + push + several tables: the step is pipelined over table groups (_PeerPipelinedFn); needs the
+        # fused optimizer (each group's rows are updated in place).  RECEMB_PEER_GROUPS overrides the default
+        # (4 groups, or one per table when there are fewer); 1 = the unpipelined step.
+        if pipeline_groups is None:
+            pipeline_groups = int(os.environ.get("RECEMB_PEER_GROUPS", "4"))
+        self.pipeline_groups = max(1, min(int(pipeline_groups), self.num_tables))
+        self._pipe = None
+        self._pipe_key = None
         self._peer: Optional[PeerGroup] = None
         self._peer_key = None
         self._peer_dirty = True
@@ -465,6 +611,8 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         return max(2, cap + (cap & 1))
 
     def peer_group(self) -> PeerGroup:
+        if self._peer is None and self._pipe:
+            return self._pipe[0].pg
         if self._peer is None:
             raise N.NativeError("peer exchange: call forward first (the group is built for its batch shape)")
         return self._peer
@@ -495,6 +643,43 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         self._peer, self._peer_key = cache[key], key
         self._peer_dirty = True
 
+    # ------------------------------------------------------ pipelined groups ----
+    def _pipelined(self) -> bool:
+        return (self.exchange == "peer" and self.peer_forward == "push" and self.pipeline_groups > 1
+                and self.emb.fused is not None and not self.emb.fused.accumulate)
+
+    def _pipe_streams(self, device):
+        if getattr(self, "_pstreams", None) is None:
+            # [NVLink-bound kernels, inbox sorts]; the NVLink stream gets priority so that its (short) kernels
+            # are not queued behind a full-grid HBM-bound kernel of the caller's stream
+            self._pstreams = [torch.cuda.Stream(device=device, priority=-1), torch.cuda.Stream(device=device)]
+        return self._pstreams
+
+    def _ensure_pipeline(self, ids: torch.Tensor) -> None:
+        """(Re)builds one peer group (arena + mapped shard pointers) per table group for this batch shape.
+        Collective over the module's process group."""
+        w = self.emb.weight
+        key = (w.data_ptr(), tuple(ids.shape))
+        if self._pipe is not None and self._pipe_key == key:
+            return
+        self.close_peer()
+        t, g = self.num_tables, self.pipeline_groups
+        b, p = ids.shape[0] // t, ids.shape[1]
+        bounds = [round(i * t / g) for i in range(g + 1)]
+        groups = []
+        for t0, t1 in zip(bounds[:-1], bounds[1:]):
+            view = w.detach()[t0 * self.local_rows:t1 * self.local_rows]
+            bags = (t1 - t0) * b
+            cap = self.peer_capacity(bags * p)
+            if self.comm.world == 1:
+                layout = arena_layout(1, cap, bags, self.emb_dim, w.dtype)
+                pg = PeerGroup.local(1, 0, [PeerGroup.new_arena(layout, w.device)], [view], layout)
+            else:
+                pg = PeerGroup.connect(view, cap=cap, bags_total=bags, group=self.comm.group)
+            groups.append(_PipeGroup(t0, t1, pg))
+        self._pipe, self._pipe_key = groups, key
+        self._peer_dirty = True
+
     def _side_stream(self, device) -> "torch.cuda.Stream":
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=device)
@@ -503,16 +688,20 @@ class RowWiseShardedEmbeddingBag(nn.Module):
     def close_peer(self) -> None:
         """Collective: unmap the peers' memory (before this rank's shard / arena may be freed)."""
         cache = self.__dict__.get("_peer_cache") or {}
-        if self._peer is None and not cache:
+        pipe = self.__dict__.get("_pipe") or []
+        if self._peer is None and not cache and not pipe:
             return
         torch.cuda.synchronize(self.emb.weight.device)
         if self.comm.world > 1:
             dist.barrier(group=self.comm.group)
         for pg in cache.values():
             pg.close()
+        for grp in pipe:
+            grp.pg.close()
         if self.comm.world > 1:
             dist.barrier(group=self.comm.group)
         self._peer, self._peer_key, self._peer_cache = None, None, {}
+        self._pipe, self._pipe_key = None, None
 
     def _batching(self, ids_all):
         """gathered bags are [W, T, b]: bag g belongs to table (g // b) % T."""
@@ -534,7 +723,10 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         if t != self.num_tables:
             raise N.NativeError(f"expected ids for {self.num_tables} tables, got {t}")
         flat = ids.contiguous().view(t * b, p)
-        if self.exchange == "peer":
+        if self._pipelined():
+            self._ensure_pipeline(flat)
+            fn = _PeerPipelinedFn
+        elif self.exchange == "peer":
             self._ensure_peer_group(flat)
         out = fn.apply(self.emb.grad_anchor(), flat,
                        None if lengths is None else lengths.contiguous().view(t * b), self)

@@ -130,13 +130,12 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
         remote = (world - 1) / world
         nv_in = int(remote * T * B_LOCAL * P * (row_bytes + 8) + (world - 1) * T * B_LOCAL * row_bytes)
         if mod.peer_forward == "push":
-            # entries in + one partial row per non-empty (bag, remote owner) pair + gathered gradients
-            pairs = (world - 1) * (1.0 - (1.0 - 1.0 / world) ** P)
-            nv_in = int(remote * T * B_LOCAL * P * 8 + pairs * T * B_LOCAL * row_bytes
-                        + (world - 1) * T * B_LOCAL * row_bytes)
+            # entries in + one partial row per (bag, remote owner) pair (zero rows included) + gathered gradients
+            nv_in = int(remote * T * B_LOCAL * P * 8 + 2 * (world - 1) * T * B_LOCAL * row_bytes)
     t_step = ms / args.steps * 1e-3
     mod_exchange = mod.exchange
     mod_peer_forward = mod.peer_forward
+    mod_groups = mod.pipeline_groups if mod._pipelined() else 1
     phases = None
     if graph:
         step = eager_step
@@ -167,7 +166,8 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 row-wise sharded over {world} GPU(s), "
                                    f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange,
-                       "peer_forward": mod_peer_forward if mod_exchange == "peer" else None},
+                       "peer_forward": mod_peer_forward if mod_exchange == "peer" else None,
+                       "pipeline_groups": mod_groups},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
             "gpu_launches": (launches_per_step * args.steps if graph else N.launch_count() - launches0),
@@ -180,6 +180,7 @@ def phase_bench(world, rank, dev, rows_per_gpu=25_000_000, reps=10):
     from recommendations_b200 import ops
     n_rows = rows_per_gpu * world
     mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange="peer",
+                                     pipeline_groups=1,
                                      fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
     ids = ids_for(rank, T, B_LOCAL, P).to(dev)
     grad = torch.randn(T, B_LOCAL, DIM, device=dev, dtype=torch.bfloat16)
@@ -215,7 +216,6 @@ def phase_bench(world, rank, dev, rows_per_gpu=25_000_000, reps=10):
     timed("bucket_push", lambda: ops.peer_bucket_push(pg, flat, num_rows=n_rows, **batching))
     timed("grads_push", lambda: ops.peer_allgather_push(pg, grad, int(pg.layout.off_grads)))
     parts = pg.parts_view(DIM, torch.bfloat16)
-    timed("zero_parts", lambda: parts.zero_())
     ops.peer_bucket_push(pg, flat, num_rows=n_rows, **batching)
     timed("pool_push(owner pools inbox, stores partial rows)", lambda: ops.peer_pool_push(pg, DIM, torch.bfloat16))
     timed("sum_partials", lambda: ops.sum_partials(parts))

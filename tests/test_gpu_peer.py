@@ -149,7 +149,13 @@ def test_peer_push_forward(world, tables, dtype):
     for r in range(world):
         ids = seeded_ids(m * p, 60 + r, (m, p))
         lengths = torch.randint(0, p + 1, (m,), generator=torch.Generator().manual_seed(40 + r))
-        groups[r].parts_view(dim, dtype).zero_()
+        if r == 1:
+            lengths[: m // 2] = 0                # a long gap of bags without entries
+        if r == 2:
+            lengths[:] = 0                       # a sender that sends nothing at all
+        # the owners write EVERY row of parts (zero rows for (bag, owner) pairs without an entry):
+        # nothing of this fill may survive
+        groups[r].parts_view(dim, dtype).fill_(float("nan"))
         ops.peer_bucket_push(groups[r], ids.to(DEV), num_rows=n_rows, lengths=lengths.to(DEV), **batching)
         inputs.append((ids, lengths))
     for o in range(world):                      # (barrier) owners pool and push
@@ -303,3 +309,95 @@ def test_peer_module_fused_step_in_cuda_graph():
     assert torch.equal(out_static, out_eager)
     assert torch.equal(graphed.emb.weight, eager.emb.weight)
     graphed.peer_group().raise_on_status(synchronize=True)
+
+
+@pytest.mark.parametrize("tables,groups", [(5, 2), (8, 4), (3, 3)])
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_peer_pipelined_groups_equal_the_unpipelined_step(tables, groups, mode):
+    """Table groups with one arena each, kernels issued by role on three streams (_PeerPipelinedFn): same
+    kernels, so the forward on equal tables is bit-identical to the one-arena push step; the fused update
+    agrees to fp32 re-association (the segmented reduction cuts its chunks per group), and so do the
+    forwards of the following steps."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    import recommendations_b200 as R
+    n_rows, dim, b, p = 9973, 64, 257, 20
+    ids = seeded_ids(tables * b * p, 81, (tables, b, p)).to(DEV)
+    lengths = torch.randint(0, p + 1, (tables, b), generator=torch.Generator().manual_seed(8)).to(DEV)
+    go = torch.randn(tables, b, dim, device=DEV)
+    mods = []
+    for g in (groups, 1):
+        m = RowWiseShardedEmbeddingBag(n_rows, dim, mode=mode, exchange="peer", peer_forward="push", num_tables=tables,
+                                       device=DEV, pipeline_groups=g,
+                                       fused_optimizer=R.FusedOptimizerConfig(kind="adagrad", lr=0.1,
+                                                                              initial_accumulator_value=0.1))
+        if mods:
+            m.load_state_dict(mods[0].state_dict())
+        mods.append(m)
+    assert mods[0]._pipelined() and not mods[1]._pipelined()
+    for it in range(3):
+        outs = [m(ids, lengths) for m in mods]
+        if it == 0:
+            assert torch.equal(outs[0], outs[1])
+        else:
+            torch.testing.assert_close(outs[0], outs[1], rtol=1e-5, atol=1e-5)
+        for o in outs:
+            o.backward(go)
+        torch.testing.assert_close(mods[0].emb.weight, mods[1].emb.weight, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(mods[0].emb.opt_state1, mods[1].emb.opt_state1, rtol=1e-5, atol=1e-5)
+    assert mods[0].emb.fused_step == mods[1].emb.fused_step == 3
+    assert len(mods[0]._pipe) == groups
+    for m in mods:
+        m.peer_group().raise_on_status(synchronize=True)
+        m.close_peer()
+
+
+def test_peer_pipelined_step_in_cuda_graph():
+    """The pipelined step forks onto two streams and joins again: capturable, replays match eager steps."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    import recommendations_b200 as R
+    n_rows, dim, b, p, tables = 50021, 128, 512, 20, 4
+    ids = seeded_ids(tables * b * p, 12, (tables, b, p)).to(DEV)
+    go = torch.randn(tables, b, dim, device=DEV, dtype=torch.bfloat16)
+    mk = lambda: RowWiseShardedEmbeddingBag(n_rows, dim, exchange="peer", peer_forward="push", num_tables=tables,  # noqa: E731
+                                            dtype=torch.bfloat16, device=DEV, pipeline_groups=2,
+                                            fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
+    eager, graphed = mk(), mk()
+    graphed.load_state_dict(eager.state_dict())
+
+    def step(mod):
+        out = mod(ids)
+        out.backward(go)
+        return out
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(graphed)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_static = step(graphed)
+    for _ in range(3):
+        graph.replay()
+    for _ in range(4):
+        out_eager = step(eager)
+    torch.cuda.synchronize()
+    assert torch.equal(out_static, out_eager)
+    assert torch.equal(graphed.emb.weight, eager.emb.weight)
+    graphed.peer_group().raise_on_status(synchronize=True)
+
+
+def test_guarded_update_leaves_the_table_untouched():
+    """recemb_bwd_apply_guarded: a non-zero guard word (the peer arena's status: overflowed inbox, timed-out
+    barrier) skips the whole update -- an incomplete gradient is never applied."""
+    w = torch.randn(500, 64, device=DEV)
+    state = torch.zeros(500, device=DEV)
+    ids = seeded_ids(4000, 13).to(DEV)
+    grad = torch.randn(4000, 64, device=DEV)
+    plan = ops.BackwardPlan.build(ids, num_rows=500)
+    hp = ops.make_optim_params(lr=0.1, eps=1e-10)
+    for flag, changed in ((1, False), (0, True)):
+        w0, s0 = w.clone(), state.clone()
+        guard = torch.full((1,), flag, dtype=torch.int32, device=DEV)
+        ops.bwd_apply(plan, grad, table=w, update=N.UPD_ROWWISE_ADAGRAD, state1=state, hp=hp, guard=guard)
+        assert torch.equal(w, w0) != changed and torch.equal(state, s0) != changed

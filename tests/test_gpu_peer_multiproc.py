@@ -76,6 +76,23 @@ def _worker(rank, world, port, peer_forward, result):
         mod.close_peer()
         from recommendations_b200 import peer
         assert not peer._OPENED, "every mapped IPC handle must be closed again"
+        if peer_forward == "push":
+            # the pipelined step (table groups on two streams, one arena per group, fused update guarded by the
+            # arena status): SGD with lr 1 leaves w0 - (gradient of the GLOBAL batch) on the rows this rank owns
+            import recommendations_b200 as R
+            pm = RowWiseShardedEmbeddingBag(N_ROWS, DIM, num_tables=T, device=dev, exchange="peer", peer_forward="push",
+                                            pipeline_groups=2, fused_optimizer=R.FusedOptimizerConfig(kind="sgd", lr=1.0))
+            pm.load_full_weight(full)
+            assert pm._pipelined()
+            w0 = pm.emb.weight.detach().cpu().clone()
+            out_p = pm(ids.to(dev), lengths.to(dev))
+            torch.testing.assert_close(out_p.cpu(), out.cpu(), rtol=1e-6, atol=1e-6)
+            out_p.backward(go.to(dev))
+            torch.cuda.synchronize()
+            torch.testing.assert_close(pm.emb.weight.cpu(), w0 - mine, rtol=1e-4, atol=1e-5)
+            pm.peer_group().raise_on_status(synchronize=True)
+            pm.close_peer()
+            assert not peer._OPENED
         result[rank] = 1
     finally:
         dist.destroy_process_group()

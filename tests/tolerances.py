@@ -48,21 +48,31 @@ def kshift_adagrad_error_bound(g, steps=3, c=8.0):
     return kshift_adagrad_budget(T(g["ids"]), T(g["target"]), T(g["weight0"]), int(g["k"]), float(g["lr"]), steps, c)
 
 
-def kshift_adagrad_budget(ids, target, w0, k, lr, steps, c=8.0):
-    """See kshift_adagrad_error_bound: the same replay for any ids / target / initial table."""
+def kshift_adagrad_budget(ids, target, w0, k, lr, steps, c=8.0, s0=None):
+    """See kshift_adagrad_error_bound: the same replay for any ids / target / initial table (and initial
+    Adagrad accumulator s0: a single-step budget from a mid-training state)."""
     target, w = target.double(), w0.double()
     n_rows = w.shape[0]
     rows = [O.row_index(ids, n_rows, c_) for c_ in range(k)]
-    s = torch.zeros_like(w)
+    s = torch.zeros_like(w) if s0 is None else s0.double().clone()
     budget = torch.zeros_like(w)
     for _ in range(steps):
-        x = sum(w[r] for r in rows).requires_grad_(True)
-        loss = torch.nn.functional.mse_loss(torch.nn.functional.normalize(x, p=2.0, dim=-1), target)
-        (dx,) = torch.autograd.grad(loss, x)
+        x = sum(w[r] for r in rows)
+        nrm = x.norm(p=2.0, dim=-1, keepdim=True).clamp_min(1e-12)
+        y = x / nrm
+        n_el = float(y.numel())
+        # gradient of MSE(normalize(x), target) w.r.t. x, and the magnitude of the terms it is made of: an
+        # fp32 implementation carries ~eps32 of THOSE (g = 2 (y - t) / n cancels when y ~ t, dx = (g - y (y.g)) / |x|
+        # cancels when g is parallel to y), not of the possibly tiny result
+        g_ = 2.0 * (y - target) / n_el
+        dot = (y * g_).sum(-1, keepdim=True)
+        dx = (g_ - y * dot) / nrm
+        g_abs = 2.0 * (y.abs() + target.abs()) / n_el
+        dx_abs = (g_abs + y.abs() * (y.abs() * g_abs).sum(-1, keepdim=True)) / nrm
         G, A = torch.zeros_like(w), torch.zeros_like(w)
         for r in rows:
             G.index_add_(0, r.reshape(-1), dx.reshape(-1, dx.shape[-1]))
-            A.index_add_(0, r.reshape(-1), dx.reshape(-1, dx.shape[-1]).abs())
+            A.index_add_(0, r.reshape(-1), dx_abs.reshape(-1, dx.shape[-1]))
         s = s + G * G
         budget += torch.minimum(lr * c * EPS32 * A / (s.sqrt() + 1e-10), torch.full_like(A, 2 * lr))
         w = w - lr * G / (s.sqrt() + 1e-10)
@@ -72,18 +82,17 @@ def kshift_adagrad_budget(ids, target, w0, k, lr, steps, c=8.0):
 def assert_adagrad_trajectory_close(got, want, budget, tag):
     """1e-5 (north star) + the fp32 summation budget, element by element.  `budget` is the c = 8 model
     (8 eps32 * sum |g_i| mapped through the update): >= 99.99 % of the elements must sit inside it, every
-    element inside 4x of it (the model ignores that the upstream rows themselves carry a few ulps and that
-    errors of step t feed step t + 1).  The elements whose budget exceeds 1e-5 are the ill-conditioned ones
-    (|G| << sum |g_i|) and must be few; all others hold the plain 1e-5 statement."""
+    element inside 4x of it.  Independently of the budget, >= 99.9 % of ALL elements hold the plain 1e-5 statement,
+    and so does every element whose budget is below 1e-5 (|G| well above the noise of its terms)."""
     err = (got.double() - want.double()).abs()
     base = 1e-5 + 1e-5 * want.double().abs()
     inside = (err <= base + budget).float().mean().item()
     assert inside >= 0.9999, (tag, inside, float((err / (base + budget)).max()))
     assert (err <= base + 4 * budget).all(), (tag, float((err / (base + 4 * budget)).max()), int((err > base + 4 * budget).sum()))
-    ill = budget > 1e-5
-    assert ill.float().mean().item() < 0.10, (tag, ill.float().mean().item())
+    # the plain north-star statement, statistically over all elements and strictly over the well-conditioned
+    # ones (budget below 1e-5: |G| well above the noise of the terms it is summed from)
     assert (err <= base).float().mean().item() >= 0.999, tag
-    well = ~ill
+    well = budget <= 1e-5
     assert (err[well] <= base[well] + 4e-5).all(), tag
 
 
@@ -94,13 +103,20 @@ class QuickGELU(torch.nn.Module):
         return x * torch.sigmoid(1.702 * x)
 
 
+class MaskMLP(torch.nn.Module):
+    """MLP(mask_emb_dim, 1, [mask_emb_dim * 16]) of embedding_module_gen.py:86 (commons/layers.py:65-82), same
+    parameter names under `model.`; scriptable."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.model = torch.nn.Sequential(torch.nn.Linear(dim, dim * 16), QuickGELU(), torch.nn.Linear(dim * 16, 1))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.model(x)
+
+
 def mask_mlp(dim, dtype=torch.float32):
-    """MLP(mask_emb_dim, 1, [mask_emb_dim * 16]) of embedding_module_gen.py:86 (commons/layers.py:65-82),
-    same parameter names under `model.`."""
-    m = torch.nn.Module()
-    m.model = torch.nn.Sequential(torch.nn.Linear(dim, dim * 16), QuickGELU(), torch.nn.Linear(dim * 16, 1))
-    m.forward = lambda x: m.model(x)
-    return m.to(dtype)
+    return MaskMLP(dim).to(dtype)
 
 
 def mask_model_budget(g, steps=3, c=8.0):
@@ -123,10 +139,13 @@ def mask_model_budget(g, steps=3, c=8.0):
         loss = torch.nn.functional.binary_cross_entropy_with_logits(mlp(x / (k ** 0.5)).squeeze(1), target)
         loss.backward()
         dx = x.grad
+        with torch.no_grad():
+            dx_chk, dx_abs = _mask_dx(mlp, x.detach(), k, target)
+        assert torch.allclose(dx_chk, dx, rtol=1e-9, atol=1e-15)
         G, A = torch.zeros_like(w), torch.zeros_like(w)
         for r in rows:
             G.index_add_(0, r, dx)
-            A.index_add_(0, r, dx.abs())
+            A.index_add_(0, r, dx_abs)
         s = s + G * G
         budget += torch.minimum(lr * c * EPS32 * A / (s.sqrt() + 1e-10), torch.full_like(A, 2 * lr))
         w = w - lr * G / (s.sqrt() + 1e-10)
@@ -144,3 +163,39 @@ def assert_cross_device_trajectory(got, want, lr, steps, tag):
     inside = (err <= 1e-5 + 1e-5 * want.double().abs()).float().mean().item()
     assert inside >= 0.99, (tag, inside)
     assert err.max().item() <= 2 * lr * steps, (tag, err.max().item())
+
+
+def _mask_dx(head, x, k, target):
+    """dL/dx of BCE(head(x / sqrt(k)), target) and the magnitude of the terms it is summed from
+    (|W1|^T (|gelu'| * |W2| * (sigmoid + target) / M)): the upstream rows are matmul sums that cancel."""
+    w1, b1 = head.model[0].weight, head.model[0].bias
+    w2 = head.model[2].weight
+    a = (x / (k ** 0.5)) @ w1.t() + b1
+    sg = torch.sigmoid(1.702 * a)
+    z = (a * sg) @ w2.t() + head.model[2].bias
+    dgelu = sg + 1.702 * a * sg * (1 - sg)
+    m = float(x.shape[0])
+    dlogit = (torch.sigmoid(z) - target.unsqueeze(1)) / m
+    dlogit_abs = (torch.sigmoid(z) + target.unsqueeze(1)) / m
+    dx = ((dlogit * w2) * dgelu) @ w1 / (k ** 0.5)
+    dx_abs = ((dlogit_abs * w2.abs()) * dgelu.abs()) @ w1.abs() / (k ** 0.5)
+    return dx, dx_abs
+
+
+def mask_step_budget(ids, w_before, s_before, mlp, k, lr, c=8.0):
+    """Single-step budget of the mask model's table update from a given state (fp64; `mlp` = the dense head
+    at that state, left untouched)."""
+    import copy
+    w = w_before.double()
+    head = copy.deepcopy(mlp).double().cpu()
+    n_rows = w.shape[0]
+    target = torch.cat([torch.ones(ids.numel() // 2), torch.zeros(ids.numel() // 2)]).double()
+    rows = [O.row_index(ids, n_rows, c_) for c_ in range(k)]
+    with torch.no_grad():
+        dx, dx_abs = _mask_dx(head, sum(w[r] for r in rows), k, target)
+    G, A = torch.zeros_like(w), torch.zeros_like(w)
+    for r in rows:
+        G.index_add_(0, r, dx)
+        A.index_add_(0, r, dx_abs)
+    s = s_before.double() + G * G
+    return torch.minimum(lr * c * EPS32 * A / (s.sqrt() + 1e-10), torch.full_like(A, 2 * lr))
