@@ -104,13 +104,24 @@ enum recemb_update {
  *     written at the mirrored position inside its sequence, (i / L) * L + (L - 1 - i % L), and the
  *     plan maps every slot to that mirrored gradient row -- Encoder.flip_all
  *     (models/lthm/sequence/encoder.py:52-54, :60-61: right-padded -> left-padded) folded into the
- *     gather's addressing instead of a torch.flip copy of [B, L, D]. */
+ *     gather's addressing instead of a torch.flip copy of [B, L, D].
+ *   window_keep != NULL (sequence gather / k-shift / their plan): the lookups form sequences of seq_len = L;
+ *     K = *window_keep (a DEVICE int32, 0 <= K <= L, typically written by recemb_sequence_window on the same
+ *     stream) positions of every sequence are kept -- the first K (window_side 0) or the last K
+ *     (window_side 1) -- the others are neither read nor written, and the kept ones are stored compactly:
+ *     output row (i / L) * K + q, q = position inside the window (mirrored when flip_len == L).  `out`
+ *     must hold n rows (K = L); the first (n / L) * K are written.  The plan drops the slots outside the
+ *     window and maps the others to the compact gradient rows.  This is QueryTower's batch-wide trim
+ *     (models/lthm/sequence/query_tower.py:73-86) applied BEFORE the rows are moved instead of after. */
 typedef struct recemb_layout {
   int64_t ids_per_table;
   int32_t num_tables;
   int32_t shard_world;
   int32_t shard_rank;
   int32_t flip_len;
+  int32_t seq_len;
+  int32_t window_side;
+  const int32_t* window_keep;
 } recemb_layout;
 
 typedef struct recemb_optim_params {
@@ -165,6 +176,25 @@ RECEMB_API int recemb_gather_fwd(const void* table, int64_t num_rows, const void
 RECEMB_API int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t dim, int dtype,
                       const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue, int32_t flip_len,
                       void* out, float* inv_norm_out, int device, recemb_stream_t stream);
+/* Same with a recemb_layout (flip_len and the sequence window; one unsharded table). */
+RECEMB_API int recemb_kshift_fwd_layout(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                             const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue,
+                             const recemb_layout* layout, void* out, float* inv_norm_out, int device,
+                             recemb_stream_t stream);
+
+/* ---- sequence window: the batch-wide trim (a7) ---------------------------- */
+/* QueryTower.forward's trim (models/lthm/sequence/query_tower.py:73-79) as one kernel, result left on the
+ * device: a column is all-pad when every row of the batch is padded there -- data[b, l] == pad_id for
+ * kind 0 (int64 ids [batch, seq_len]) or data[b, l] != 0 for kind 1 (uint8 / bool mask, QueryTower's
+ * mask_inp).  trim = seq_len - min_keep when MORE than that many columns are all-pad, else the length of
+ * the all-pad run at the padded end: the START of the sequences for window_side 1 (left-padded, what
+ * QueryTower sees after Encoder.flip_all), the END for window_side 0 (right-padded, before the flip).
+ * out[0] = keep = seq_len - trim, out[1] = trim (device int32[2]); pass out as recemb_layout.window_keep
+ * with the same window_side.  seq_len <= 8192; workspace as recemb_sequence_window_workspace_bytes. */
+RECEMB_API size_t recemb_sequence_window_workspace_bytes(int32_t seq_len);
+RECEMB_API int recemb_sequence_window(const void* data, int kind, int64_t batch, int32_t seq_len, int64_t pad_id,
+                           int32_t min_keep, int window_side, void* workspace, size_t workspace_bytes,
+                           int32_t* out, int device, recemb_stream_t stream);
 
 /* ---- forward: pooled multi-hot bag (a5, a11) ------------------------------ */
 /* ids [num_bags, bag_size]; out[b, :] = pool_{p in window(b)} w[b,p] * table[transform(ids[b,p]), :]
@@ -400,6 +430,24 @@ RECEMB_API int recemb_peer_bucket_push(const recemb_peer_group* group, const rec
                             int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id, int32_t bag_size,
                             const int32_t* lengths, int32_t last_n, void* workspace, size_t workspace_bytes,
                             int device, recemb_stream_t stream);
+/* Sequence mode (every lookup is its own output / gradient row; forward = recemb_peer_pool_fwd with
+ * bag_size 1, i.e. each row pulled from its owner).  Backward, sender side, two halves:
+ *   recemb_peer_bucket_push_rows   (needs only the ids: issue it in the forward's shadow) as
+ *     recemb_peer_bucket_push with bag_size 1, except that entry k of my bucket for owner o names the slot
+ *     rank * cap + k of the owner's gradient buffer, and dest_out[i] (int64 [n_ids]) = (o << 32 | k) for
+ *     lookup i, -1 if it was dropped (pad id / out-of-range identity id / inbox overflow);
+ *   recemb_peer_rows_scatter_push  stores gradient row i (rows [n, dim]) into that slot of its owner's
+ *     buffer over NVLink: every row crosses the link at most once (an all-gather would send it W - 1 times).
+ * The arena must be laid out with bags_total == cap (gradient buffer [world][cap][dim]); the owner then
+ * continues as in the pooled case: barrier, recemb_peer_plan, recemb_bwd_apply(grad = arena + off_grads). */
+RECEMB_API int recemb_peer_bucket_push_rows(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                 const int64_t* ids, int64_t n_ids, const recemb_layout* layout, int hash_mode,
+                                 int64_t num_rows, int64_t hash_arg, int zero_pad, int64_t pad_id,
+                                 int64_t* dest_out, void* workspace, size_t workspace_bytes, int device,
+                                 recemb_stream_t stream);
+RECEMB_API int recemb_peer_rows_scatter_push(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                  const void* rows, int64_t n, int32_t dim, int dtype, const int64_t* dest,
+                                  int device, recemb_stream_t stream);
 /* Backward, sender side.  Push all-gather: src (bytes, 16-byte multiple) is stored at
  * arena(p) + dst_offset + rank * bytes of EVERY rank p (its own included). */
 RECEMB_API int recemb_peer_allgather_push(const recemb_peer_group* group, const void* src, int64_t bytes,

@@ -11,10 +11,11 @@ from .interaction import DotInteraction, dot_interaction
 from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PatternFromTimelocal,
                      PooledEmbeddingBag, QREmbedding)
 from .logq import CascadedStreamingLogQCorrectionModule, StreamingLogQCorrectionModule
+from .sequence import SequenceWindow, sequence_trim
 from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
 
 __all__ = [
     "CosineVectorEmbedding", "DotInteraction", "EmbeddingCollection", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
     "FusedOptimizerConfig", "KShiftEmbedding", "PatternFromTimelocal", "PooledEmbeddingBag", "QREmbedding",
-    "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule",
+    "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule", "SequenceWindow", "sequence_trim",
 ]

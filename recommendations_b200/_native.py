@@ -50,6 +50,9 @@ class Layout(C.Structure):
         ("shard_world", C.c_int32),
         ("shard_rank", C.c_int32),
         ("flip_len", C.c_int32),
+        ("seq_len", C.c_int32),
+        ("window_side", C.c_int32),
+        ("window_keep", C.c_void_p),
     ]
 
 
@@ -75,12 +78,18 @@ class PeerArena(C.Structure):
 
 
 def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
-                flip_len: int = 0):
-    """None when nothing is batched / sharded / flipped (the C side treats NULL as one plain table)."""
-    if not ids_per_table and shard_world <= 1 and not flip_len:
+                flip_len: int = 0, window=None):
+    """None when nothing is batched / sharded / flipped / windowed (the C side treats NULL as one plain table).
+    window: a sequence.SequenceWindow (device-resident number of kept columns)."""
+    if not ids_per_table and shard_world <= 1 and not flip_len and window is None:
         return None
-    return Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=shard_world,
-                  shard_rank=shard_rank, flip_len=flip_len)
+    lay = Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=shard_world,
+                 shard_rank=shard_rank, flip_len=flip_len)
+    if window is not None:
+        if flip_len not in (0, window.seq_len):
+            raise NativeError("a windowed lookup flips whole sequences: flip_len must be 0 or the window's seq_len")
+        lay.seq_len, lay.window_side, lay.window_keep = window.seq_len, window.side, window.keep_ptr()
+    return lay
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -103,6 +112,10 @@ SIGNATURES = {
     "recemb_gather_fwd": (_INT, [_P, _I64, _P, _I64, _I32, _INT, _P, _I64, C.POINTER(Layout), _INT, _INT, _I64,
                                  _INT, _INT, _I64, _P, _P, _INT, _P]),
     "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _I32, _P, _P, _INT, _P]),
+    "recemb_kshift_fwd_layout": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, C.POINTER(Layout), _P, _P, _INT,
+                                        _P]),
+    "recemb_sequence_window_workspace_bytes": (_SZ, [_I32]),
+    "recemb_sequence_window": (_INT, [_P, _INT, _I64, _I32, _I64, _I32, _INT, _P, _SZ, _P, _INT, _P]),
     "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,
                                _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
     "recemb_bwd_plan_bytes": (_SZ, [_I64, _I64]),
@@ -133,6 +146,10 @@ SIGNATURES = {
     "recemb_peer_wait": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _INT, _INT, _P]),
     "recemb_peer_pool_fwd": (_INT, [C.POINTER(PeerGroupStruct), _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P,
                                     _INT, _I64, _INT, _INT, _I64, C.POINTER(Layout), _P, _INT, _P]),
+    "recemb_peer_bucket_push_rows": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
+                                            C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _P, _P, _SZ, _INT, _P]),
+    "recemb_peer_rows_scatter_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64, _I32, _INT,
+                                             _P, _INT, _P]),
     "recemb_peer_pool_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _INT, _P]),
     "recemb_peer_bucket_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
                                        C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32, _P, _SZ,

@@ -87,6 +87,7 @@ struct PlanKeyArgs {
 };
 
 __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArgs a) {
+  const uint32_t keep = window_keep(a.h);
   int64_t s = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * kBwdThreads;
   for (; s < a.n_slots; s += stride) {
@@ -106,6 +107,10 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
       const int lo = a.last_n > 0 ? max(0, hi - a.last_n) : 0;
       ok = p >= lo && p < hi;
     }
+    // the slot's gradient row: mirrored inside its sequence when the forward wrote flipped outputs, compacted
+    // to the sequence window (slots outside it carry nothing)
+    const int64_t orow = (a.h.flip_len | a.h.win_len) ? out_row(id_idx, a.h, keep) : id_idx;
+    ok = ok && orow >= 0;
     uint32_t key = a.sentinel;
     if (ok) {
       int64_t row = a.slots_per_id > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
@@ -115,8 +120,7 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
       }
     }
     a.keys[s] = key;
-    // the slot's gradient row: mirrored inside its sequence when the forward wrote flipped outputs
-    a.vals[s] = a.h.flip_len ? (uint32_t)(flip_index(id_idx, a.h.flip_len) * a.slots_per_id + c) : (uint32_t)s;
+    a.vals[s] = (a.h.flip_len | a.h.win_len) ? (uint32_t)(max(orow, (int64_t)0) * a.slots_per_id + c) : (uint32_t)s;
   }
 }
 

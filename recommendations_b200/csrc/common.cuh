@@ -120,6 +120,12 @@ struct HashSpec {
   uint32_t shard_rank;
   ModN mod_world;
   uint32_t flip_len;  // > 0: outputs / gradient rows mirrored inside sequences of flip_len lookups
+  // sequence window (query_tower.py:73-86, the batch-wide trim): sequences of win_len lookups of which only
+  // *win_keep (DEVICE scalar, read at kernel start) positions are looked up -- the first (win_side 0) or the
+  // last (win_side 1) ones -- and written compactly as [n / win_len, *win_keep, dim]
+  uint32_t win_len;
+  uint32_t win_side;
+  const int32_t* win_keep;
 };
 
 // position i mirrored inside its sequence of L lookups (L == 0: unchanged)
@@ -127,6 +133,29 @@ __device__ __forceinline__ int64_t flip_index(int64_t i, uint32_t L) {
   if (!L) return i;
   const int64_t b = i / L;
   return b * L + (L - 1 - (i - b * L));
+}
+
+__device__ __forceinline__ uint32_t window_keep(const HashSpec& h) {
+  if (!h.win_len) return 0;
+  const int32_t k = *h.win_keep;
+  return (uint32_t)min(max(k, 0), (int32_t)h.win_len);
+}
+
+// output / gradient row of lookup i: mirrored inside its sequence (flip_len), compacted to the kept
+// window (win_len; keep from window_keep()); -1 = outside the window, neither read nor written
+__device__ __forceinline__ int64_t out_row(int64_t i, const HashSpec& h, uint32_t keep) {
+  if (!h.win_len) return flip_index(i, h.flip_len);
+  const uint32_t L = h.win_len;
+  const int64_t b = i / L;
+  uint32_t p = (uint32_t)(i - b * L);
+  if (h.win_side) {
+    if (p < L - keep) return -1;
+    p -= L - keep;
+  } else if (p >= keep) {
+    return -1;
+  }
+  if (h.flip_len) p = keep - 1 - p;
+  return b * keep + p;
 }
 
 int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* out,

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 
   IdStager st;
   st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
+  const uint32_t keep = window_keep(a.h1);
 
   int64_t tile = blockIdx.x;
   int b = 0;
@@ -116,14 +117,20 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
     const int cnt = tile_count(tile);
     st.acquire(b, a.ids + tile * kTileIds, cnt);
 
-    // hash in place: s_ids[b][i] <- row (or -1 for a zero-filled pad position)
+    // hash in place: s_ids[b][i] <- row (-1 for a zero-filled pad position, -2 for a position outside
+    // the sequence window: not read, not written)
     int64_t* rows = s_ids[b];
     for (int i = threadIdx.x; i < cnt; i += kThreads) {
       const int64_t id = rows[i];
       const bool pad = a.zero_pad && id == a.pad_id;
       if (TWO) s_rows2[i] = pad ? -1 : row_of(id, a.h2);
       const int64_t r1 = pad ? -1 : row_of(id, a.h1);  // -1: pad position or out-of-range identity id
-      rows[i] = r1 < 0 ? -1 : r1 + table_offset(tile * kTileIds + i, a.h1);
+      int64_t r = r1 < 0 ? -1 : r1 + table_offset(tile * kTileIds + i, a.h1);
+      if (a.h1.win_len && out_row(tile * kTileIds + i, a.h1, keep) < 0) {
+        r = -2;
+        if (TWO) s_rows2[i] = -1;
+      }
+      rows[i] = r;
     }
     __syncthreads();
 
@@ -195,21 +202,25 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
             for (int j = 0; j < V; ++j)
 #pragma unroll
               for (int e = 0; e < E; ++e) f[j][e] = f[j][e] / denom;
-            if (a.inv_norm && l[u] < cnt && lig == 0)
-              a.inv_norm[flip_index(tile * kTileIds + l[u], a.h1.flip_len)] = 1.f / denom;
+            if (a.inv_norm && l[u] < cnt && lig == 0) {
+              const int64_t o = out_row(tile * kTileIds + l[u], a.h1, keep);
+              if (o >= 0) a.inv_norm[o] = 1.f / denom;
+            }
           }
 #pragma unroll
           for (int j = 0; j < V; ++j) v[u][j] = Vec16<T>::pack(f[j]);
         }
         if (l[u] < cnt) {
+          uint4* dst = out_tile + (int64_t)l[u] * a.row_vecs;
+          if (a.h1.flip_len | a.h1.win_len) {
+            const int64_t o = out_row(tile * kTileIds + l[u], a.h1, keep);
+            dst = o < 0 ? nullptr : a.out + o * a.row_vecs;
+          }
+          if (dst) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const int vec = j * G + lig;
-            if (vec < a.row_vecs) {
-              uint4* dst = a.h1.flip_len
-                               ? a.out + flip_index(tile * kTileIds + l[u], a.h1.flip_len) * a.row_vecs
-                               : out_tile + (int64_t)l[u] * a.row_vecs;
-              stg_cs_v4(dst + vec, v[u][j]);
+            for (int j = 0; j < V; ++j) {
+              const int vec = j * G + lig;
+              if (vec < a.row_vecs) stg_cs_v4(dst + vec, v[u][j]);
             }
           }
         }
@@ -232,7 +243,7 @@ struct KShiftArgs {
   int epilogue;
   float sqrt_k;
   int bulk_ok;
-  uint32_t flip_len;
+  HashSpec h;  // flip_len / sequence window only (out_row)
   int l1_hot;  // rows of shifts >= 1 may stay in L1
 };
 
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
 
   IdStager st;
   st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
+  const uint32_t keep = window_keep(a.h);
   int64_t tile = blockIdx.x;
   int b = 0;
   auto tile_count = [&](int64_t t) { return (int)min((int64_t)kTileIds, a.n - t * kTileIds); };
@@ -264,7 +276,8 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
 
     for (int base = warp * RPW; base < cnt; base += kWarps * RPW) {
       const int l = base + gi;
-      const bool live = l < cnt;
+      const int64_t orow = l < cnt ? out_row(tile * kTileIds + l, a.h, keep) : -1;
+      const bool live = orow >= 0;  // inside the tile and inside the sequence window
       const int64_t id = live ? ids[l] : 0;
       float acc[V][E];
 #pragma unroll
@@ -324,8 +337,7 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
         for (int j = 0; j < V; ++j)
 #pragma unroll
           for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / denom;
-        if (a.inv_norm && live && lig == 0)
-          a.inv_norm[flip_index(tile * kTileIds + l, a.flip_len)] = 1.f / denom;
+        if (a.inv_norm && live && lig == 0) a.inv_norm[orow] = 1.f / denom;
       } else if (a.epilogue == RECEMB_EPI_RSQRT_K) {
 #pragma unroll
         for (int j = 0; j < V; ++j)
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) kshift_kernel(const KShiftArgs a) {
           for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / a.sqrt_k;
       }
       if (live) {
-        uint4* dst = a.out + flip_index(tile * kTileIds + l, a.flip_len) * (int64_t)a.row_vecs;
+        uint4* dst = a.out + orow * (int64_t)a.row_vecs;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const int vec = j * G + lig;
@@ -671,6 +683,9 @@ extern "C" int recemb_gather_fwd(const void* table, int64_t num_rows, const void
   RECEMB_CHECK_ARG(!layout || layout->flip_len == 0 || n % layout->flip_len == 0,
                    "n is not a multiple of flip_len");
   if (rc) return rc;
+  RECEMB_CHECK_ARG(a.h1.win_len == 0 || n % a.h1.win_len == 0, "n is not a multiple of seq_len");
+  RECEMB_CHECK_ARG(a.h1.win_len == 0 || !batched || layout->ids_per_table % a.h1.win_len == 0,
+                   "ids_per_table is not a multiple of seq_len");
   a.h2 = a.h1;
   if (table2) {
     rc = make_hash_spec(hash_mode2, num_rows2, hash_arg, &a.h2);
@@ -717,7 +732,19 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
                                  const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue,
                                  int32_t flip_len, void* out, float* inv_norm_out, int device,
                                  recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(flip_len >= 0, "flip_len < 0");
+  recemb_layout layout = {0, 0, 1, 0, flip_len, 0, 0, nullptr};
+  return recemb_kshift_fwd_layout(table, num_rows, dim, dtype, ids, n, num_shifts, epilogue, &layout, out,
+                                  inv_norm_out, device, stream);
+}
+
+extern "C" int recemb_kshift_fwd_layout(const void* table, int64_t num_rows, int32_t dim, int dtype,
+                                        const int64_t* ids, int64_t n, int32_t num_shifts, int epilogue,
+                                        const recemb_layout* layout, void* out, float* inv_norm_out, int device,
+                                        recemb_stream_t stream) {
   RECEMB_CHECK_ARG(n >= 0, "n < 0");
+  RECEMB_UNSUPPORTED(!layout || (layout->ids_per_table == 0 && layout->shard_world <= 1),
+                     "the k-shift bag takes one unsharded table (layout: flip_len / sequence window only)");
   if (n == 0) return RECEMB_OK;
   RECEMB_CHECK_ARG(table && ids && out, "null pointer");
   RECEMB_CHECK_ARG(num_shifts >= 1 && num_shifts <= 63, "num_shifts %d out of [1, 63]", num_shifts);
@@ -737,8 +764,10 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
   a.mod_rows = make_modn((uint64_t)num_rows);
   a.epilogue = epilogue;
   a.sqrt_k = (float)sqrt((double)num_shifts);
-  RECEMB_CHECK_ARG(flip_len >= 0 && (flip_len == 0 || n % flip_len == 0), "n is not a multiple of flip_len");
-  a.flip_len = (uint32_t)flip_len;
+  rc = make_hash_spec(RECEMB_HASH_FLOORMOD, num_rows, 0, &a.h, layout);
+  if (rc) return rc;
+  RECEMB_CHECK_ARG(a.h.flip_len == 0 || n % a.h.flip_len == 0, "n is not a multiple of flip_len");
+  RECEMB_CHECK_ARG(a.h.win_len == 0 || n % a.h.win_len == 0, "n is not a multiple of seq_len");
   a.bulk_ok = ((uintptr_t)ids % 16 == 0);
   {
     static int l1 = -1;  // RECEMB_KSHIFT_L1=0 turns the L1 residency of the collapse rows off

@@ -54,9 +54,21 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
   h.shard_rank = 0;
   h.mod_world = make_modn(1);
   h.flip_len = 0;
+  h.win_len = 0;
+  h.win_side = 0;
+  h.win_keep = nullptr;
   if (layout) {
     RECEMB_CHECK_ARG(layout->flip_len >= 0, "flip_len < 0");
     h.flip_len = (uint32_t)layout->flip_len;
+    if (layout->window_keep) {
+      RECEMB_CHECK_ARG(layout->seq_len > 0, "a sequence window needs seq_len > 0");
+      RECEMB_CHECK_ARG(layout->flip_len == 0 || layout->flip_len == layout->seq_len,
+                       "flip_len must equal seq_len when a window is set");
+      RECEMB_CHECK_ARG(layout->window_side == 0 || layout->window_side == 1, "window_side must be 0 or 1");
+      h.win_len = (uint32_t)layout->seq_len;
+      h.win_side = (uint32_t)layout->window_side;
+      h.win_keep = layout->window_keep;
+    }
     RECEMB_CHECK_ARG(layout->ids_per_table >= 0 && layout->ids_per_table < 0xffffffffll,
                      "ids_per_table out of range");
     RECEMB_CHECK_ARG(layout->num_tables >= 0, "num_tables < 0");
@@ -151,7 +163,7 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   // another stream) is still computing; the kernels below must not.
   if (wait_event_after_copy)
     RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
-  recemb_layout layout = {ids_per_table, 0, 1, 0, 0};  // no sharding, no flip
+  recemb_layout layout = {ids_per_table, 0, 1, 0, 0, 0, 0, nullptr};  // no sharding, no flip, no window
   int rc;
   if (fork) {
     // the plan (hash + radix sort) only needs the ids: it runs on plan_stream while the gather

@@ -47,6 +47,11 @@ struct BucketArgs {
   uint32_t cap;                           // inbox capacity per sender
   uint32_t* status;                       // this rank's sticky status word (bit 0: inbox overflow)
   uint32_t* peer_status[RECEMB_MAX_PEERS];  // owner o's status word: its inbox is incomplete -> it must skip its update
+  // sequence mode (every lookup is its own gradient row): the entry names the slot of the owner's gradient
+  // buffer the sender will store the row into, rank * cap + position in the bucket; dest[s] remembers
+  // (owner << 32 | position) for that store, -1 for a dropped lookup
+  int64_t* dest;
+  uint32_t seq_base;  // rank * cap
 };
 
 __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketArgs a) {
@@ -186,17 +191,23 @@ __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const Bucket
     const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     if (valid && rank == 0) s_wc[warp][owner] = __popc(peers);
     __syncthreads();
+    int64_t dest = -1;
     if (valid) {
       uint32_t pos = s_run[owner] + rank;
       for (int w = 0; w < warp; ++w) pos += s_wc[w][owner];
       const uint32_t bag = (uint32_t)(s / a.bag_size);
-      const int64_t entry = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)(a.bag_base + bag));
+      const uint32_t grow = a.dest ? a.seq_base + pos : a.bag_base + bag;  // gradient row at the owner
+      const int64_t entry = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)grow);
       if constexpr (PEER) {
-        if (pos < a.cap) s_dst[owner][pos] = entry;  // store into the owner's HBM over NVLink
+        if (pos < a.cap) {
+          s_dst[owner][pos] = entry;  // store into the owner's HBM over NVLink
+          dest = (int64_t)(((uint64_t)owner << 32) | pos);
+        }
       } else {
         a.entries[pos] = entry;
       }
     }
+    if (PEER && a.dest && s < a.n) a.dest[s] = dest;
     __syncthreads();
     if (threadIdx.x < world) {
       uint32_t add = 0;
@@ -383,6 +394,34 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
   if (i >= n) zero_rows(prev_key + 1u, key_base + (uint32_t)a.bags_total);  // I closed the region's last run
 }
 
+// Sequence mode, backward: every gradient row travels ONCE, to the rank that owns its table row -- stored
+// at (my rank * cap + position in my bucket for that owner) of the owner's gradient buffer, the slot the
+// entry pushed during the forward names.  G lanes per row, 16 bytes each: contiguous row_bytes stores.
+struct RowsPushArgs {
+  const uint4* rows;
+  const int64_t* dest;
+  int64_t n;
+  int32_t vecs;
+  uint32_t seq_base;
+  uint4* grads[RECEMB_MAX_PEERS];
+};
+
+template <int G>
+__global__ void __launch_bounds__(kRtThreads) rows_scatter_push_kernel(const RowsPushArgs a) {
+  __shared__ uint4* s_grads[RECEMB_MAX_PEERS];
+  if (threadIdx.x < RECEMB_MAX_PEERS) s_grads[threadIdx.x] = a.grads[threadIdx.x];
+  __syncthreads();
+  const int lig = threadIdx.x % G;
+  int64_t s = (int64_t)blockIdx.x * (kRtThreads / G) + threadIdx.x / G;
+  const int64_t stride = (int64_t)gridDim.x * (kRtThreads / G);
+  for (; s < a.n; s += stride) {
+    const int64_t d = a.dest[s];
+    if (d < 0 || lig >= a.vecs) continue;
+    const uint4 v = ldg_nc_v4(a.rows + s * a.vecs + lig);
+    stg_v4(s_grads[(uint32_t)(d >> 32)] + (size_t)(a.seq_base + (uint32_t)d) * a.vecs + lig, v);
+  }
+}
+
 // ------------------------------------------------------------------ plan from entries ----
 __global__ void __launch_bounds__(kRtThreads) unpack_entries_kernel(const int64_t* __restrict__ entries, int64_t n,
                                                                    uint32_t* __restrict__ keys,
@@ -430,7 +469,8 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
                          int64_t n_ids, const recemb_layout* layout, int hash_mode, int64_t num_rows,
                          int64_t hash_arg, int zero_pad, int64_t pad_id, int32_t bag_size, const int32_t* lengths,
                          int32_t last_n, int64_t bags_total, int64_t* entries_out, int64_t* counts_out,
-                         void* workspace, size_t workspace_bytes, int device, recemb_stream_t stream) {
+                         void* workspace, size_t workspace_bytes, int device, recemb_stream_t stream,
+                         int64_t* seq_dest = nullptr) {
   RECEMB_CHECK_ARG(layout && layout->shard_world >= 1 && layout->shard_world <= kMaxWorld,
                    "shard_world outside [1, %d]", kMaxWorld);
   RECEMB_CHECK_ARG(bag_size >= 1 && n_ids >= 0 && n_ids % bag_size == 0, "n_ids not a multiple of bag_size");
@@ -473,6 +513,8 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
   a.counts = counts_out;
   a.cap = 0;
   a.status = nullptr;
+  a.dest = seq_dest;
+  a.seq_base = 0;
   for (int i = 0; i < RECEMB_MAX_PEERS; ++i) {
     a.peer_inbox[i] = a.peer_count[i] = nullptr;
     a.peer_status[i] = nullptr;
@@ -481,7 +523,7 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
     RECEMB_CHECK_ARG(arena && group->world == layout->shard_world && group->rank == layout->shard_rank &&
                          group->world <= RECEMB_MAX_PEERS,
                      "peer group does not match the layout (world %d rank %d)", group->world, group->rank);
-    RECEMB_CHECK_ARG(arena->cap >= 1 && arena->cap < 0xffffffffll && arena->bags_total == bags_total,
+    RECEMB_CHECK_ARG(arena->cap >= 1 && arena->cap < 0xffffffffll && (seq_dest || arena->bags_total == bags_total),
                      "arena capacity / bags_total mismatch");
     for (int o = 0; o < group->world; ++o) {
       RECEMB_CHECK_ARG(group->arena[o], "peer arena %d not mapped", o);
@@ -492,6 +534,8 @@ static int bucket_common(const recemb_peer_group* group, const recemb_peer_arena
     }
     a.cap = (uint32_t)arena->cap;
     a.status = (uint32_t*)((char*)group->arena[group->rank] + arena->off_status);
+    RECEMB_UNSUPPORTED(!seq_dest || (int64_t)group->world * arena->cap < 0xffffffffll, "gradient buffer too large");
+    a.seq_base = (uint32_t)((int64_t)group->rank * arena->cap);
   }
   if (n_ids == 0) {
     if (group) {
@@ -542,6 +586,62 @@ extern "C" int recemb_peer_bucket_push(const recemb_peer_group* group, const rec
   return bucket_common(group, arena, ids, n_ids, layout, hash_mode, num_rows, hash_arg, zero_pad, pad_id, bag_size,
                        lengths, last_n, arena->bags_total, nullptr, nullptr, workspace, workspace_bytes, device,
                        stream);
+}
+
+extern "C" int recemb_peer_bucket_push_rows(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                            const int64_t* ids, int64_t n_ids, const recemb_layout* layout,
+                                            int hash_mode, int64_t num_rows, int64_t hash_arg, int zero_pad,
+                                            int64_t pad_id, int64_t* dest_out, void* workspace,
+                                            size_t workspace_bytes, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena && dest_out, "null peer group / arena / dest");
+  RECEMB_CHECK_ARG(arena->bags_total == arena->cap,
+                   "sequence mode needs an arena laid out with bags_total == cap (gradient buffer [world][cap][dim])");
+  return bucket_common(group, arena, ids, n_ids, layout, hash_mode, num_rows, hash_arg, zero_pad, pad_id, 1, nullptr,
+                       0, n_ids, nullptr, nullptr, workspace, workspace_bytes, device, stream, dest_out);
+}
+
+extern "C" int recemb_peer_rows_scatter_push(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                             const void* rows, int64_t n, int32_t dim, int dtype,
+                                             const int64_t* dest, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena, "null peer group / arena");
+  RECEMB_CHECK_ARG(group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
+                       group->rank < group->world, "peer group world / rank out of range");
+  RECEMB_CHECK_ARG(n >= 0 && dim > 0, "bad shape");
+  RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "bad dtype");
+  RECEMB_CHECK_ARG(arena->bags_total == arena->cap, "sequence mode needs an arena laid out with bags_total == cap");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(rows && dest && (uintptr_t)rows % 16 == 0, "rows / dest null or misaligned");
+  const int64_t row_bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED(row_bytes % 16 == 0 && row_bytes <= 512, "row of %lld bytes unsupported (16-byte multiple, <= 512)",
+                     (long long)row_bytes);
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  RowsPushArgs a;
+  a.rows = (const uint4*)rows;
+  a.dest = dest;
+  a.n = n;
+  a.vecs = (int32_t)(row_bytes / 16);
+  a.seq_base = (uint32_t)((int64_t)group->rank * arena->cap);
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.grads[i] = nullptr;
+  for (int o = 0; o < group->world; ++o) {
+    RECEMB_CHECK_ARG(group->arena[o], "peer arena %d not mapped", o);
+    a.grads[o] = (uint4*)((char*)group->arena[o] + arena->off_grads);
+  }
+  int G = 1;
+  while (G < a.vecs) G <<= 1;
+  cudaStream_t s = (cudaStream_t)stream;
+#define RSP(G_)                                                                               \
+  if (G == G_) {                                                                              \
+    const int64_t per = kRtThreads / G_;                                                      \
+    int64_t grid = (n + per - 1) / per;                                                       \
+    const int64_t cap_grid = (int64_t)sm_count(device) * 8;                                   \
+    if (grid > cap_grid) grid = cap_grid;                                                     \
+    rows_scatter_push_kernel<G_><<<(unsigned)grid, kRtThreads, 0, s>>>(a);                    \
+  }
+  RSP(1) RSP(2) RSP(4) RSP(8) RSP(16) RSP(32)
+#undef RSP
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
 }
 
 extern "C" int recemb_pool_entries(const void* table, int32_t dim, int dtype, const int64_t* entries, int64_t n,

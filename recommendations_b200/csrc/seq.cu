@@ -1,0 +1,123 @@
+// Sequence front end of the LTHM query tower (sm_100a):
+//   seq_window_kernel - the batch-wide trim of all-pad columns (models/lthm/sequence/query_tower.py:73-79)
+//                       computed on the device, result left in device memory for the windowed gather /
+//                       k-shift / plan (recemb_layout.window_keep) -- the rows outside the window are then
+//                       never moved at all
+#include "common.cuh"
+
+namespace recemb {
+
+constexpr int kSeqThreads = 256;
+constexpr int kSeqMaxLen = 8192;
+
+struct WinArgs {
+  const void* data;     // kind 0: int64 ids [batch, L] (padded = pad_id); kind 1: uint8 mask [batch, L] (non-zero = padded)
+  int kind;
+  int64_t batch;
+  int32_t L;
+  int64_t pad_id;
+  int32_t min_keep;     // export_span: at least this many columns stay
+  int side;             // 0: all-pad columns are dropped at the END of the sequences, 1: at the START
+  uint32_t* col_live;   // [L] zero-filled: column holds at least one real token
+  uint32_t* done;       // zero-filled ticket counter
+  int32_t* out;         // [0] = keep, [1] = trim
+  int64_t per_cta;      // elements per CTA (multiple of 16)
+};
+
+__global__ void __launch_bounds__(kSeqThreads) seq_window_kernel(const WinArgs a) {
+  __shared__ uint32_t s_live[kSeqMaxLen];
+  __shared__ int s_cnt, s_first, s_last, s_is_last;
+  for (int c = threadIdx.x; c < a.L; c += kSeqThreads) s_live[c] = 0;
+  if (threadIdx.x == 0) {
+    s_cnt = 0;
+    s_first = a.L;
+    s_last = -1;
+  }
+  __syncthreads();
+  const int64_t total = a.batch * (int64_t)a.L;
+  const int64_t i0 = (int64_t)blockIdx.x * a.per_cta;
+  const int64_t i1 = min(total, i0 + a.per_cta);
+  if (a.kind == 0) {
+    const int64_t* ids = (const int64_t*)a.data;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += kSeqThreads)
+      if (ids[i] != a.pad_id) s_live[(uint32_t)(i % a.L)] = 1u;  // racing stores of the same value
+  } else {
+    const uint8_t* m = (const uint8_t*)a.data;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += kSeqThreads)
+      if (m[i] == 0) s_live[(uint32_t)(i % a.L)] = 1u;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.L; c += kSeqThreads)
+    if (s_live[c]) a.col_live[c] = 1u;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_is_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  int cnt = 0, first = a.L, last = -1;  // all-pad columns; first / last column with a token
+  for (int c = threadIdx.x; c < a.L; c += kSeqThreads) {
+    if (__ldcg(a.col_live + c)) {
+      first = min(first, c);
+      last = max(last, c);
+    } else {
+      ++cnt;
+    }
+  }
+  atomicAdd(&s_cnt, cnt);
+  atomicMin(&s_first, first);
+  atomicMax(&s_last, last);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // query_tower.py:75-79: more all-pad columns than L - export_span -> exactly export_span columns stay;
+    // otherwise the run of all-pad columns at the padded end goes
+    const int floor_trim = max(a.L - a.min_keep, 0);
+    const int lead = a.side ? s_first : (a.L - 1 - s_last);
+    const int trim = s_cnt > floor_trim ? floor_trim : lead;
+    a.out[0] = a.L - trim;
+    a.out[1] = trim;
+  }
+}
+
+}  // namespace recemb
+
+using namespace recemb;
+
+extern "C" size_t recemb_sequence_window_workspace_bytes(int32_t seq_len) {
+  return seq_len > 0 ? align_up(((size_t)seq_len + 1) * 4, 256) : 256;
+}
+
+extern "C" int recemb_sequence_window(const void* data, int kind, int64_t batch, int32_t seq_len, int64_t pad_id,
+                                      int32_t min_keep, int window_side, void* workspace, size_t workspace_bytes,
+                                      int32_t* out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(data && workspace && out, "null pointer");
+  RECEMB_CHECK_ARG(kind == 0 || kind == 1, "kind must be 0 (int64 ids) or 1 (uint8 mask)");
+  RECEMB_CHECK_ARG(batch >= 1 && seq_len >= 1 && min_keep >= 0, "bad batch / seq_len / min_keep");
+  RECEMB_CHECK_ARG(window_side == 0 || window_side == 1, "window_side must be 0 or 1");
+  RECEMB_UNSUPPORTED(seq_len <= kSeqMaxLen, "seq_len %d > %d", seq_len, kSeqMaxLen);
+  RECEMB_CHECK_ARG(workspace_bytes >= recemb_sequence_window_workspace_bytes(seq_len), "workspace too small");
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  cudaStream_t s = (cudaStream_t)stream;
+  RECEMB_CUDA(cudaMemsetAsync(workspace, 0, ((size_t)seq_len + 1) * 4, s));
+  WinArgs a;
+  a.data = data;
+  a.kind = kind;
+  a.batch = batch;
+  a.L = seq_len;
+  a.pad_id = pad_id;
+  a.min_keep = min_keep;
+  a.side = window_side;
+  a.col_live = (uint32_t*)workspace;
+  a.done = (uint32_t*)workspace + seq_len;
+  a.out = out;
+  const int64_t total = batch * (int64_t)seq_len;
+  int64_t ctas = (int64_t)sm_count(device) * 4;
+  int64_t per = (total + ctas - 1) / ctas;
+  per = (per + 4095) / 4096 * 4096;  // at least a few loads per thread
+  a.per_cta = per;
+  ctas = (total + per - 1) / per;
+  seq_window_kernel<<<(unsigned)ctas, kSeqThreads, 0, s>>>(a);
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}

@@ -69,25 +69,29 @@ class _GatherFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, anchor2, ids, holder, holder2, hash_mode, hash_mode2, hash_arg,
-                epilogue, zero_pad, pad_id, flip_len=0, record=True):
+                epilogue, zero_pad, pad_id, flip_len=0, record=True, window=None):
         # `record` = torch.is_grad_enabled() at the call site (grad mode is always off in here and
         # needs_input_grad ignores no_grad): inference builds no inverse norms and no plan
         need_grad = record and (ctx.needs_input_grad[0] or (anchor2 is not None and ctx.needs_input_grad[1]))
+        _check_window(window, ids, holder, holder2)
         out, inv = ops.gather_fwd(
             holder.weight.detach(), ids, hash_mode=hash_mode, hash_arg=hash_arg,
             table2=None if holder2 is None else holder2.weight.detach(), hash_mode2=hash_mode2,
             epilogue=epilogue, zero_pad=zero_pad, pad_id=pad_id, want_inv_norm=need_grad,
-            flip_len=flip_len)
+            flip_len=flip_len, window=window)
         ctx.holder, ctx.holder2 = holder, holder2
-        ctx.flip_len = flip_len
+        ctx.flip_len, ctx.window = flip_len, window
         ctx.cfg = (hash_mode, hash_mode2, hash_arg, epilogue, zero_pad, pad_id)
-        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         _plan_early(ctx, ids, holder2 is None and record and ctx.needs_input_grad[0]
                     and not (holder.sparse and holder.fused is None),
                     lambda: holder.build_plan(
                         ids, num_rows=holder.num_embeddings, hash_mode=hash_mode, hash_arg=hash_arg,
                         zero_pad=zero_pad, pad_id=pad_id,
-                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
+                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len,
+                        window=window))
+        if window is not None:  # everything is enqueued: now the host may learn `keep`
+            out, inv = _compact(window, ids, out, inv)
+        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         return out
 
     @staticmethod
@@ -116,9 +120,29 @@ class _GatherFn(torch.autograd.Function):
             plan = _plan_take(ctx, lambda: holder.build_plan(
                 ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=hash_arg,
                 zero_pad=zero_pad, pad_id=pad_id,
-                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len,
+                window=ctx.window))
             grads[i] = holder.consume(plan, g)
-        return (grads[0], grads[1]) + (None,) * 11
+        return (grads[0], grads[1]) + (None,) * 12
+
+
+def _check_window(window, ids, *holders) -> None:
+    if window is None:
+        return
+    if ids.dim() != 2 or ids.shape[1] != window.seq_len:
+        raise N.NativeError(f"windowed lookup: ids must be [batch, {window.seq_len}], got {tuple(ids.shape)}")
+    for h in holders:
+        if h is not None and h.sparse and h.fused is None:
+            raise N.NativeError("windowed lookups do not support the sparse-COO gradient mode")
+
+
+def _compact(window, ids, out, inv):
+    """Full-size kernel outputs -> the compact [batch, keep, dim] prefix the windowed kernels wrote."""
+    b = ids.shape[0]
+    out = window.compact(out, b)
+    if inv is not None:
+        inv = inv[: b * window.keep]
+    return out, inv
 
 
 def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable,
@@ -135,16 +159,20 @@ def _coo(rows: torch.Tensor, vals: torch.Tensor, holder: EmbeddingTable,
 
 class _KShiftFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0, record=True):
+    def forward(ctx, anchor, ids, holder, num_shifts, epilogue, flip_len=0, record=True, window=None):
         record = record and ctx.needs_input_grad[0]
+        _check_window(window, ids, holder)
         out, inv = ops.kshift_fwd(holder.weight.detach(), ids, num_shifts, epilogue,
-                                  want_inv_norm=record, flip_len=flip_len)
-        ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len = holder, num_shifts, epilogue, flip_len
-        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
+                                  want_inv_norm=record, flip_len=flip_len, window=window)
+        ctx.holder, ctx.k, ctx.epilogue, ctx.flip_len, ctx.window = holder, num_shifts, epilogue, flip_len, window
         _plan_early(ctx, ids, record and not (holder.sparse and holder.fused is None),
                     lambda: holder.build_plan(
                         ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=num_shifts,
-                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len))
+                        pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=flip_len,
+                        window=window))
+        if window is not None:
+            out, inv = _compact(window, ids, out, inv)
+        ctx.save_for_backward(ids, inv, out if epilogue == N.EPI_L2NORM else None)
         return out
 
     @staticmethod
@@ -159,9 +187,10 @@ class _KShiftFn(torch.autograd.Function):
             # element -- folded into the segmented reduction, dx is never materialised
             plan = _plan_take(ctx, lambda: holder.build_plan(
                 ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
-                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
+                pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len,
+                window=ctx.window))
             return (holder.consume(plan, g2d, slots_per_grad_row=k, grad_div=math.sqrt(k)),
-                    None, None, None, None, None, None)
+                    None, None, None, None, None, None, None)
         dx = ops.epilogue_bwd(g2d, out, inv, ctx.epilogue, k)
         if sparse_coo:
             flat = ids.contiguous().view(-1)
@@ -170,11 +199,12 @@ class _KShiftFn(torch.autograd.Function):
             if ctx.flip_len:
                 dx = dx.view(-1, ctx.flip_len, dim).flip(1).reshape(-1, dim)
             vals = dx.to(holder.weight.dtype).repeat(k, 1)
-            return (_coo(rows, vals, holder), None, None, None, None, None, None)
+            return (_coo(rows, vals, holder), None, None, None, None, None, None, None)
         plan = _plan_take(ctx, lambda: holder.build_plan(
             ids, num_rows=holder.num_embeddings, hash_mode=N.HASH_ROTL_FLOORMOD, slots_per_id=k,
-            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len))
-        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None, None)
+            pad_row=-1 if holder.padding_idx is None else holder.padding_idx, flip_len=ctx.flip_len,
+            window=ctx.window))
+        return (holder.consume(plan, dx, slots_per_grad_row=k), None, None, None, None, None, None, None)
 
 
 class _PoolFn(torch.autograd.Function):
@@ -266,11 +296,14 @@ class FlatEmbedding(nn.Module):
         if fused_optimizer is not None:
             self._emb_table.enable_fused_optimizer(fused_optimizer)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, window=None) -> torch.Tensor:
+        """window (sequence.SequenceWindow over x's [batch, L]): only the kept columns are looked up and the
+        result is [batch, keep, D] -- QueryTower's trim (query_tower.py:73-86) before the rows are moved."""
         t = self._emb_table
         return _GatherFn.apply(t.grad_anchor(), None, x, t, None, N.HASH_FLOORMOD, 0, 0,
                                N.EPI_L2NORM if self._normalize_output else N.EPI_NONE,
-                               self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences), torch.is_grad_enabled())
+                               self._fused_pad_mask, 0, _flip_len(x, self._flip_sequences), torch.is_grad_enabled(),
+                               window)
 
 
 class PatternFromTimelocal(nn.Module):
@@ -317,10 +350,11 @@ class KShiftEmbedding(nn.Module):
         if fused_optimizer is not None:
             self.emb.enable_fused_optimizer(fused_optimizer)
 
-    def forward(self, id_: torch.Tensor) -> torch.Tensor:
+    def forward(self, id_: torch.Tensor, window=None) -> torch.Tensor:
+        """window: see FlatEmbedding.forward."""
         return _KShiftFn.apply(self.emb.grad_anchor(), id_, self.emb, self._num_shifts,
                                N.EPI_L2NORM if self._normalize_output else N.EPI_RSQRT_K,
-                               _flip_len(id_, self._flip_sequences), torch.is_grad_enabled())
+                               _flip_len(id_, self._flip_sequences), torch.is_grad_enabled(), window)
 
     def get_row_idx(self, x: torch.Tensor, col_idx: int) -> torch.Tensor:
         """Bit-exact commons/layers.py:174-185 (wrapping <<, arithmetic >>, floor-mod)."""

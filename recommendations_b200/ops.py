@@ -40,7 +40,10 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
                hash_mode2: int = N.HASH_FLOORMOD, epilogue: int = N.EPI_NONE,
                zero_pad: bool = False, pad_id: int = 0, want_inv_norm: bool = False,
                out: Optional[torch.Tensor] = None, ids_per_table: int = 0,
-               flip_len: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               flip_len: int = 0, window=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """window (sequence.SequenceWindow): only the kept columns of every sequence are looked up; the result is
+    the FULL-size buffer viewed as [*ids.shape, dim] whose first batch * keep rows hold [batch, keep, dim]
+    (window.compact(out, batch) once the host may know `keep`)."""
     flat = _flat_ids(ids)
     dev = N.require_cuda(table, table2, flat, out)
     n, dim = flat.numel(), table.shape[1]
@@ -52,7 +55,7 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
     rows_per_table = table.shape[0]
-    layout = N.make_layout(ids_per_table=ids_per_table, flip_len=flip_len)
+    layout = N.make_layout(ids_per_table=ids_per_table, flip_len=flip_len, window=window)
     if ids_per_table:
         n_tables = -(-n // ids_per_table)
         if table.shape[0] % n_tables:
@@ -66,7 +69,8 @@ def gather_fwd(table: torch.Tensor, ids: torch.Tensor, *, hash_mode: int = N.HAS
 
 
 def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue: int,
-               want_inv_norm: bool = False, flip_len: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               want_inv_norm: bool = False, flip_len: int = 0,
+               window=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     flat = _flat_ids(ids)
     dev = N.require_cuda(table, flat)
     n, dim = flat.numel(), table.shape[1]
@@ -74,9 +78,10 @@ def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue
     inv = None
     if want_inv_norm and epilogue == N.EPI_L2NORM:
         inv = torch.empty((n,), dtype=torch.float32, device=table.device)
-    N.check(N.load().recemb_kshift_fwd(
+    N.check(N.load().recemb_kshift_fwd_layout(
         N.ptr(table), table.shape[0], dim, N.dtype_code(table.dtype), N.ptr(flat), n, num_shifts,
-        epilogue, flip_len, N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)), "recemb_kshift_fwd")
+        epilogue, N.make_layout(flip_len=flip_len, window=window), N.ptr(out), N.ptr(inv), dev, N.stream_ptr(dev)),
+        "recemb_kshift_fwd")
     return out.view(*ids.shape, dim), inv
 
 
@@ -131,7 +136,7 @@ class BackwardPlan:
               pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
               last_n: int = 0, buf: Optional[torch.Tensor] = None, ids_per_table: int = 0,
               num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
-              flip_len: int = 0) -> "BackwardPlan":
+              flip_len: int = 0, window=None) -> "BackwardPlan":
         """num_rows is rows PER TABLE; with ids_per_table > 0 the plan covers the stacked table
         of ceil(n_ids / ids_per_table) tables and `self.num_rows` is the stacked total."""
         flat = _flat_ids(ids)
@@ -140,7 +145,7 @@ class BackwardPlan:
         dev = N.require_cuda(flat, lengths)
         n_slots = flat.numel() * slots_per_id
         lib = N.load()
-        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank, flip_len)
+        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank, flip_len, window)
         total_rows = int(lib.recemb_layout_total_rows(num_rows, layout, flat.numel()))
         need = int(lib.recemb_bwd_plan_bytes(n_slots, total_rows))
         if need == 0:
@@ -154,9 +159,10 @@ class BackwardPlan:
         recipe = (ids, dict(num_rows=num_rows, hash_mode=hash_mode, hash_arg=hash_arg, slots_per_id=slots_per_id,
                             zero_pad=zero_pad, pad_id=pad_id, pad_row=pad_row, bag_size=bag_size, lengths=lengths,
                             last_n=last_n, ids_per_table=ids_per_table, num_tables=num_tables,
-                            shard_world=shard_world, shard_rank=shard_rank, flip_len=flip_len))
+                            shard_world=shard_world, shard_rank=shard_rank, flip_len=flip_len, window=window))
+        # windowed: the slots map to the compact [batch * keep] gradient rows, fewer than the slots
         return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=total_rows, slots_per_id=slots_per_id,
-                            recipe=recipe)
+                            slots_cover_grad=window is None, recipe=recipe)
 
     def _arr(self, which: int) -> torch.Tensor:
         arr_bytes = (self.n_slots * 4 + 255) // 256 * 256
@@ -349,6 +355,39 @@ def peer_bucket_push(group, ids: torch.Tensor, *, num_rows: int, lengths: Option
                                         hash_mode, num_rows, hash_arg, int(zero_pad), pad_id, p, N.ptr(lengths),
                                         last_n, N.ptr(ws), ws.numel(), dev, N.stream_ptr(dev)),
             "recemb_peer_bucket_push")
+
+
+def peer_bucket_push_rows(group, ids: torch.Tensor, *, num_rows: int, zero_pad: bool = False, pad_id: int = 0,
+                          ids_per_table: int = 0, num_tables: int = 0, hash_mode: int = N.HASH_FLOORMOD,
+                          hash_arg: int = 0) -> torch.Tensor:
+    """Sequence mode, sender side (needs only the ids): my (local row, gradient slot) entries land in the
+    owners' inboxes; returns dest int64 [n] = (owner << 32 | position) per lookup, -1 = dropped."""
+    flat = _flat_ids(ids)
+    dev = N.require_cuda(flat)
+    n = flat.numel()
+    lib = N.load()
+    layout = N.Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=group.world,
+                      shard_rank=group.rank, flip_len=0)
+    ws = torch.empty((int(lib.recemb_shard_bucket_workspace_bytes(n, group.world)),), dtype=torch.uint8,
+                     device=flat.device)
+    dest = torch.empty((n,), dtype=torch.int64, device=flat.device)
+    N.check(lib.recemb_peer_bucket_push_rows(C.byref(group.struct), C.byref(group.layout), N.ptr(flat), n, layout,
+                                             hash_mode, num_rows, hash_arg, int(zero_pad), pad_id, N.ptr(dest),
+                                             N.ptr(ws), ws.numel(), dev, N.stream_ptr(dev)),
+            "recemb_peer_bucket_push_rows")
+    return dest
+
+
+def peer_rows_scatter_push(group, rows: torch.Tensor, dest: torch.Tensor) -> None:
+    """Sequence mode, backward: gradient row i -> the slot of its owner's gradient buffer named by dest[i]."""
+    rows = rows.contiguous()
+    dev = N.require_cuda(rows, dest)
+    if rows.dim() != 2 or rows.shape[0] != dest.numel():
+        raise N.NativeError(f"rows {tuple(rows.shape)} do not match dest [{dest.numel()}]")
+    N.check(N.load().recemb_peer_rows_scatter_push(C.byref(group.struct), C.byref(group.layout), N.ptr(rows),
+                                                   rows.shape[0], rows.shape[1], N.dtype_code(rows.dtype),
+                                                   N.ptr(dest), dev, N.stream_ptr(dev)),
+            "recemb_peer_rows_scatter_push")
 
 
 def peer_pool_push(group, dim: int, dtype: torch.dtype) -> None:

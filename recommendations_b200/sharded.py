@@ -367,6 +367,68 @@ class _PeerPoolFn(torch.autograd.Function):
         return res, None, None, None
 
 
+class _PeerSeqFn(torch.autograd.Function):
+    """exchange="peer", sequence mode (RowWiseShardedEmbedding): every lookup is its own output row.
+
+      forward   main: [barrier ch0 if rows changed] -> pool_kernel<PEER> with one slot per bag: each row LOADED
+                      from its owner's shard over NVLink -- (W-1)/W n R bytes, bit-identical to the unsharded gather
+                side: bucket by owner, entries STORED into the owners' inboxes (entry = local row, slot of the
+                      owner's gradient buffer) -> barrier ch1 -> unpack + sort of my inbox -> barrier ch1
+      backward  main: rows_scatter_push: gradient row i STORED into its owner's buffer, once (an all-gather would
+                      move it W - 1 times) -> barrier ch0 -> wait(side) -> segmented reduction + update of MY rows
+    Hazards as in _PeerPoolFn."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, module):
+        pg = module.peer_group()
+        pg.raise_on_status()
+        main = torch.cuda.current_stream(ids.device)
+        ctx.plan, ctx.plan_ready, ctx.pg, ctx.dest = None, None, pg, None
+        batching = module._own_batching(ids)
+        if module._peer_dirty:
+            ops.peer_barrier(pg, channel=0)
+            module._peer_dirty = False
+        if ctx.needs_input_grad[0]:
+            side = module._side_stream(ids.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx.dest = ops.peer_bucket_push_rows(
+                    pg, ids, num_rows=module.num_embeddings, zero_pad=module.skip_pad, pad_id=module.pad_id,
+                    ids_per_table=batching["bags_per_table"], num_tables=batching["num_tables"])
+                ops.peer_barrier(pg, channel=1)
+                ctx.plan = ops.peer_plan(pg, module.emb.weight.shape[0], buf=module.__dict__.get("_seq_plan_buf"))
+                module._seq_plan_buf = ctx.plan.buf
+                ops.peer_barrier(pg, channel=1)
+                ctx.plan_ready = torch.cuda.Event()
+                ctx.plan_ready.record(side)
+            ids.record_stream(side)
+            ctx.dest.record_stream(main)
+        out = ops.peer_pool_fwd(pg, ids, num_rows=module.num_embeddings, dim=module.emb_dim,
+                                dtype=module.emb.weight.dtype, pool_mode=N.POOL_SUM, zero_pad=module.skip_pad,
+                                pad_id=module.pad_id, **batching)
+        ctx.module = module
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module, pg = ctx.module, ctx.pg
+        g = grad_out.contiguous()
+        if g.dtype != module.emb.weight.dtype:
+            g = g.to(module.emb.weight.dtype)
+        main = torch.cuda.current_stream(g.device)
+        if module._peer_dirty:
+            ops.peer_barrier(pg, channel=0)     # two backward passes without a forward in between
+        main.wait_event(ctx.plan_ready)         # dest is written on the side stream
+        ops.peer_rows_scatter_push(pg, g.view(-1, g.shape[-1]), ctx.dest)
+        ops.peer_barrier(pg, channel=0)
+        res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype),
+                                 slots_per_grad_row=1, guard=pg.status_word())
+        ctx.plan, ctx.dest = None, None
+        pg.snapshot_status()
+        module._peer_dirty = True
+        return res, None, None
+
+
 CH_ENTRIES, CH_PARTS, CH_GRADS, CH_REPEAT = 0, 1, 2, 3   # barrier channels of a pipelined group's arena
 
 
@@ -632,13 +694,15 @@ class RowWiseShardedEmbeddingBag(nn.Module):
             # a new batch shape (e.g. the last, smaller batch of an epoch) needs its own arena; the
             # 51 GB shard stays mapped once
             cap = self.peer_capacity(ids.numel())
+            # sequence mode: the gradient buffer holds one row per inbox entry, [W][cap][D]
+            bags_total = cap if getattr(self, "sequence_mode", False) else ids.shape[0]
             if self.comm.world == 1:
-                layout = arena_layout(1, cap, ids.shape[0], self.emb_dim, w.dtype)
+                layout = arena_layout(1, cap, bags_total, self.emb_dim, w.dtype)
                 arena = PeerGroup.new_arena(layout, w.device)
                 cache[key] = PeerGroup.local(1, 0, [arena], [w.detach()], layout)
             else:
                 first = next(iter(cache.values())) if cache else None
-                cache[key] = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group,
+                cache[key] = PeerGroup.connect(w.detach(), cap=cap, bags_total=bags_total, group=self.comm.group,
                                                table_ptrs=None if first is None else first.table_ptrs())
         self._peer, self._peer_key = cache[key], key
         self._peer_dirty = True
@@ -790,3 +854,33 @@ class RowWiseShardedEmbeddingBag(nn.Module):
             full = state[key]
             full = full.reshape((t, self.num_embeddings) + tuple(full.shape[(1 if t == 1 else 2):]))
             buf.copy_(full[:, r::w].reshape(buf.shape).to(buf.device, buf.dtype))
+
+
+class RowWiseShardedEmbedding(RowWiseShardedEmbeddingBag):
+    """Sequence-mode lookup (FlatEmbedding semantics: one output row per id, `out[..., :] =
+    table[floor_mod(id, N)]`, commons/layers.py:56-61) into a row-wise sharded table.
+
+    forward(ids [...] int64 of THIS rank) -> [..., D]; with num_tables = T > 1: ids [T, ...] -> [T, ..., D].
+    exchange="peer": each row is pulled from its owner over NVLink in the forward and each gradient row is
+    pushed to its owner once in the backward (_PeerSeqFn).  The NCCL exchanges ("route" / "gather") treat a
+    lookup as a bag of one slot (functional, but the gradients are all-gathered)."""
+
+    sequence_mode = True
+
+    def __init__(self, num_embeddings: int, emb_dim: int, **kw):
+        kw.setdefault("pipeline_groups", 1)
+        kw["peer_forward"] = "pull"
+        super().__init__(num_embeddings, emb_dim, mode="sum", **kw)
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        t = self.num_tables
+        if t > 1 and (ids.dim() < 2 or ids.shape[0] != t):
+            raise N.NativeError(f"expected ids [T = {t}, ...], got {tuple(ids.shape)}")
+        shape = tuple(ids.shape)
+        flat = ids.contiguous().view(-1, 1)
+        if self.exchange != "peer":
+            out = super().forward(flat.view(t, -1, 1) if t > 1 else flat)
+            return out.reshape(shape + (self.emb_dim,))
+        self._ensure_peer_group(flat)
+        out = _PeerSeqFn.apply(self.emb.grad_anchor(), flat, self)
+        return out.view(shape + (self.emb_dim,))

@@ -361,9 +361,11 @@ def reference_layers():
                            LogQ=LogQFixed, QueryTower=query_tower)
 
 
-def b200_layers(device="cuda:0", trim_fn=None):
+def b200_layers(device="cuda:0", trim_fn=None, pretrim=False):
     """recommendations_b200 modules swapped in (torch-compatible gradient mode: the reference's AdamW
-    drives every parameter, wrapper.py:255-275)."""
+    drives every parameter, wrapper.py:255-275).  pretrim: the product lookup is windowed BEFORE the rows
+    are moved (recommendations_b200.sequence.SequenceWindow on ids == 0; QueryTower's own trim then acts on
+    the window)."""
     import recommendations_b200 as R
     from functools import partial
     L = SimpleNamespace(name="b200",
@@ -372,7 +374,7 @@ def b200_layers(device="cuda:0", trim_fn=None):
                         KShiftEmbedding=partial(R.KShiftEmbedding, device=device),
                         CosineVectorEmbedding=partial(R.CosineVectorEmbedding, device=device),
                         LogQ=partial(R.CascadedStreamingLogQCorrectionModule, device=device),
-                        trim_fn=trim_fn)
+                        trim_fn=trim_fn, pretrim=pretrim)
     L.QueryTower = lambda mc: QueryTowerH(mc, L)
     return L
 
@@ -401,6 +403,8 @@ class LTHMStep(nn.Module):
                                   alpha=cfg.logq_alpha, p_init=cfg.logq_p_init)
         self.batch_idx = 0
         self.fused_logq_mask = L.name == "b200"
+        self.pretrim = bool(getattr(L, "pretrim", False))
+        self.last_window_keep = None
 
     # product_tower.py:43-62
     def product_tower(self, ids, x):
@@ -419,10 +423,18 @@ class LTHMStep(nn.Module):
     def forward(self, batch):
         ids = batch["product_ids"]
         assert ids.dtype == torch.int64  # wrapper.py:52
-        embs = self._model.product_emb_module(ids)
+        labels, timestamp = batch["labels"], batch["timestamp"]
+        if self.pretrim:
+            from recommendations_b200.sequence import SequenceWindow
+            w = SequenceWindow.from_ids(ids, self.cfg.model_config().export_span)
+            embs = self._model.product_emb_module(ids, window=w)   # [B, keep, D]: trimmed columns never moved
+            ids, labels, timestamp = w.narrow(ids), w.narrow(labels), w.narrow(timestamp)
+            self.last_window_keep = w.keep
+        else:
+            embs = self._model.product_emb_module(ids)
         inp, target, mask = self.product_tower(ids, embs)
         inp, target, mask, labels, timestamp, ids = [torch.flip(t, dims=[1]) for t in
-                                                     (inp, target, mask, batch["labels"], batch["timestamp"], ids)]
+                                                     (inp, target, mask, labels, timestamp, ids)]
         return self._model.query_tower(inp, target, mask, labels, timestamp, ids)
 
     # wrapper.py:114-245 (metrics dropped; loss path line by line)

@@ -401,3 +401,81 @@ def test_guarded_update_leaves_the_table_untouched():
         guard = torch.full((1,), flag, dtype=torch.int32, device=DEV)
         ops.bwd_apply(plan, grad, table=w, update=N.UPD_ROWWISE_ADAGRAD, state1=state, hp=hp, guard=guard)
         assert torch.equal(w, w0) != changed and torch.equal(state, s0) != changed
+
+
+# ---------------------------------------------------------------- sequence mode ----
+@pytest.mark.parametrize("world,tables", [(1, 1), (2, 1), (4, 3), (8, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_peer_sequence_mode_emulated_ranks(world, tables, dtype):
+    """Sequence mode (one output / gradient row per lookup): the forward pulls every row from its owner
+    (bit-identical to the unsharded gather); in the backward every sender buckets its lookups into the owners'
+    inboxes and stores each gradient row ONCE into the slot its entry names; every owner's plan + dense
+    gradient then equals the unsharded scatter-add restricted to the rows it owns."""
+    n_rows, dim, b, length = 20011, 64, 37, 50
+    n = tables * b * length
+    torch.manual_seed(7 + world)
+    full = torch.randn(tables, n_rows, dim).to(dtype)
+    cap = n                                            # room for everything: no overflow in this test
+    shards, arenas, groups = make_groups(world, full.float(), cap, cap, dtype)
+    stacked = full.reshape(-1, dim).contiguous().to(DEV)
+    batching = dict(ids_per_table=b * length if tables > 1 else 0, num_tables=tables if tables > 1 else 0)
+    pool_batching = dict(bags_per_table=b * length if tables > 1 else 0, num_tables=tables if tables > 1 else 0)
+    dense_want = [torch.zeros(tables * n_rows, dim) for _ in range(1)][0]
+    for r in range(world):
+        ids = seeded_ids(n, 300 + r, (n, 1))
+        ids[::7] = 0                                   # pad ids: dropped with zero_pad
+        got = ops.peer_pool_fwd(groups[r], ids.to(DEV), num_rows=n_rows, dim=dim, dtype=dtype, zero_pad=True,
+                                pad_id=0, **pool_batching)
+        want, _ = ops.gather_fwd(stacked, ids.view(-1).to(DEV), zero_pad=True, pad_id=0,
+                                 ids_per_table=batching["ids_per_table"])
+        assert torch.equal(got, want.view(n, dim))
+        # backward, sender side
+        dest = ops.peer_bucket_push_rows(groups[r], ids.to(DEV), num_rows=n_rows, zero_pad=True, pad_id=0, **batching)
+        grad = torch.randn(n, dim, generator=torch.Generator().manual_seed(r)).to(dtype)
+        ops.peer_rows_scatter_push(groups[r], grad.to(DEV), dest)
+        d = dest.cpu()
+        assert bool(((d < 0) == (ids.view(-1) == 0)).all())
+        rows = O.row_index(ids.view(-1), n_rows, 0) + (torch.arange(n) // (b * length)) * n_rows
+        keep = ids.view(-1) != 0
+        assert bool(((d[keep] >> 32) == (rows[keep] % n_rows) % world).all())      # owner = row mod W
+        dense_want.index_add_(0, rows[keep], grad.float()[keep])
+    for o in range(world):                             # (barrier) owner side
+        plan = ops.peer_plan(groups[o], shards[o].shape[0])
+        dense = torch.zeros(shards[o].shape, dtype=torch.float32, device=DEV)
+        ops.bwd_apply(plan, groups[o].grads_view(dim, dtype).float(), table=dense, update=N.UPD_DENSE_GRAD,
+                      slots_per_grad_row=1)
+        want_o = dense_want.view(tables, n_rows, dim)[:, o::world].reshape(-1, dim)
+        torch.testing.assert_close(dense.cpu(), want_o, rtol=1e-5, atol=1e-4 if dtype == torch.float32 else 5e-2)
+        groups[o].snapshot_status()
+    torch.cuda.synchronize()
+    for g in groups:
+        g.raise_on_status()
+
+
+@pytest.mark.parametrize("tables", [1, 3])
+def test_peer_sequence_module_single_rank(tables):
+    """RowWiseShardedEmbedding (exchange="peer", W = 1) == FlatEmbedding on the same table, forward bit-exact,
+    dense gradient and fused update equal."""
+    import recommendations_b200 as R
+    from recommendations_b200.sharded import RowWiseShardedEmbedding
+    n_rows, dim, b, length = 9973, 64, 33, 40
+    shape = (b, length) if tables == 1 else (tables, b, length)
+    ids = seeded_ids(tables * b * length, 91, shape).to(DEV)
+    a = RowWiseShardedEmbedding(n_rows, dim, exchange="peer", num_tables=tables, device=DEV)
+    out = a(ids)
+    assert out.shape == shape + (dim,)
+    w = a.emb.weight.detach().view(tables, n_rows, dim)
+    for t in range(tables):
+        ref = R.FlatEmbedding(n_rows, dim, device=DEV)
+        ref._emb_table.weight.data.copy_(w[t])
+        ids_t = ids if tables == 1 else ids[t]
+        out_t = out if tables == 1 else out[t]
+        want = ref(ids_t)
+        assert torch.equal(out_t, want)
+    go = torch.randn_like(out)
+    out.backward(go)
+    rows = (ids.view(tables, -1) % n_rows) + torch.arange(tables, device=DEV).unsqueeze(1) * n_rows
+    want_g = torch.zeros_like(a.emb.weight).index_add_(0, rows.view(-1), go.view(-1, dim))
+    torch.testing.assert_close(a.emb.weight.grad, want_g, rtol=1e-5, atol=1e-5)
+    a.peer_group().raise_on_status(synchronize=True)
+    a.close_peer()

@@ -93,6 +93,32 @@ def _worker(rank, world, port, peer_forward, result):
             pm.peer_group().raise_on_status(synchronize=True)
             pm.close_peer()
             assert not peer._OPENED
+        if peer_forward == "pull":
+            # sequence mode (one row per lookup): rows pulled from their owners, each gradient row pushed to its
+            # owner once; SGD with lr 1 leaves w0 - (scatter-add of the GLOBAL batch) on the rows this rank owns
+            import recommendations_b200 as R
+            from recommendations_b200.sharded import RowWiseShardedEmbedding
+            sm = RowWiseShardedEmbedding(N_ROWS, DIM, num_tables=T, device=dev, exchange="peer",
+                                         fused_optimizer=R.FusedOptimizerConfig(kind="sgd", lr=1.0))
+            sm.load_full_weight(full)
+            w0 = sm.emb.weight.detach().cpu().clone()
+            gseq = torch.zeros(T, N_ROWS, DIM)
+            for r in range(world):
+                ids_r, _, _ = _ids(r)
+                go_r = torch.randn(T, B, P, DIM, generator=torch.Generator().manual_seed(70 + r))
+                for t in range(T):
+                    gseq[t].index_add_(0, O.row_index(ids_r[t].reshape(-1), N_ROWS, 0), go_r[t].reshape(-1, DIM))
+            go_seq = torch.randn(T, B, P, DIM, generator=torch.Generator().manual_seed(70 + rank))
+            out_q = sm(ids.to(dev))
+            for t in range(T):
+                assert torch.equal(out_q[t].cpu(), full[t][O.row_index(ids[t], N_ROWS, 0)])
+            out_q.backward(go_seq.to(dev))
+            torch.cuda.synchronize()
+            torch.testing.assert_close(sm.emb.weight.cpu(), w0 - gseq[:, rank::world].reshape(-1, DIM),
+                                       rtol=1e-4, atol=1e-5)
+            sm.peer_group().raise_on_status(synchronize=True)
+            sm.close_peer()
+            assert not peer._OPENED
         result[rank] = 1
     finally:
         dist.destroy_process_group()
