@@ -365,6 +365,8 @@ typedef struct recemb_peer_arena {
   int64_t bags_total;
   int64_t off_parts;   /* [world][bags_total][dim] partial pools of MY bags, slice o written completely by
                           owner o (push forward) */
+  int64_t off_gate;    /* gate region of the fused gradient push (recemb_peer_bwd_apply_fused): step counter,
+                          per-table completion counts, per-table flags [64][RECEMB_MAX_PEERS] */
 } recemb_peer_arena;
 
 /* handle_out identifies the whole allocation that contains ptr; *offset_out = ptr - its base. */
@@ -458,6 +460,24 @@ RECEMB_API int recemb_peer_allgather_push(const recemb_peer_group* group, const 
  * plan as in recemb_bwd_plan_bytes(world * cap, total_rows). */
 RECEMB_API int recemb_peer_plan(const recemb_peer_group* group, const recemb_peer_arena* arena, int64_t total_rows,
                      void* plan, size_t plan_bytes, int device, recemb_stream_t stream);
+
+/* Backward, sender AND owner side in ONE launch (the pooled push / pull exchange, update kinds whose
+ * per-row state is a scalar: row-wise Adagrad, SGD; rows of 256 or 512 bytes, gradients in the table dtype).
+ * Replaces recemb_peer_allgather_push + recemb_peer_barrier + recemb_bwd_apply_guarded: the first
+ * `push_ctas` CTAs of the level-0 kernel store this rank's pooled gradients my_grad
+ * [tables][bags_per_table][dim] into every rank's gradient buffer table by table and publish one flag per
+ * table; the remaining CTAs are the segmented reduction + fused update over `plan` (recemb_peer_plan), and a
+ * chunk of sorted entries waits only for the flags of the last table it touches (keys are table-major:
+ * rows_per_table local rows per table) -- the NVLink transfer of table t + 1 overlaps the HBM-bound update
+ * of table t inside one kernel.  The update is skipped when the arena's status word is non-zero; a gate that
+ * times out (RECEMB_PEER_BARRIER_TIMEOUT_S) sets status bit 2 and skips its chunk.  Every rank must call it
+ * once per step.  workspace as recemb_bwd_apply_workspace_bytes(world * cap, dim). */
+RECEMB_API int recemb_peer_bwd_apply_fused(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                const void* plan, size_t plan_bytes, const void* my_grad, int32_t tables,
+                                int64_t bags_per_table, int32_t dim, int dtype, int update, void* table,
+                                int64_t total_rows, int64_t rows_per_table, void* state1,
+                                const recemb_optim_params* hp, void* workspace, size_t workspace_bytes,
+                                int32_t push_ctas, int device, recemb_stream_t stream);
 
 /* ---- ranker pairwise dot interaction (a11) --------------------------------- */
 /* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:

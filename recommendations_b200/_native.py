@@ -74,7 +74,7 @@ class PeerArena(C.Structure):
     """recemb_peer_arena: byte offsets inside one rank's exchange arena."""
     _fields_ = [(name, C.c_int64) for name in
                 ("bytes", "off_flags", "off_epoch", "off_status", "off_counts", "off_inbox", "off_grads",
-                 "cap", "bags_total", "off_parts")]
+                 "cap", "bags_total", "off_parts", "off_gate")]
 
 
 def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
@@ -150,6 +150,9 @@ SIGNATURES = {
                                             C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _P, _P, _SZ, _INT, _P]),
     "recemb_peer_rows_scatter_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64, _I32, _INT,
                                              _P, _INT, _P]),
+    "recemb_peer_bwd_apply_fused": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _SZ, _P, _I32, _I64,
+                                           _I32, _INT, _INT, _P, _I64, _I64, _P, C.POINTER(OptimParams), _P, _SZ,
+                                           _I32, _INT, _P]),
     "recemb_peer_pool_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _INT, _P]),
     "recemb_peer_bucket_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
                                        C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32, _P, _SZ,

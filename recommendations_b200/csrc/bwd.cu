@@ -236,7 +236,95 @@ struct SegArgs {
   const uint32_t* guard;  // optional: a non-zero word means "do not touch the table" (every CTA returns)
   int32_t chunk;          // consecutive entries per group (level 0: wave-fitted, >= kChunk0)
   int32_t pf_bulk;        // level 0 fast path: rows prefetched with one bulk L2 prefetch per row
+  PeerGate gate;          // seg_pre_kernel, sharded backward: fused gradient push + per-table gating
 };
+
+// ---- fused gradient push (sharded backward) ---------------------------------------------------
+// Pusher CTAs (blockIdx.x < gate.push_ctas; dispatched first, they never wait): my pooled gradients go to
+// slice `rank` of every rank's gradient buffer, table by table -- one 16-byte load, `world` stores per
+// vector, peers visited in rotated order so the ranks never all store into the same peer.  When the last
+// pusher CTA is done with table t it adds one to the arrival count of table t on every rank (system
+// scope): the peers' reduction groups that need table t are waiting for exactly that.
+__device__ __forceinline__ void gate_push_role(const PeerGate& g) {
+  __shared__ uint4* s_dst[RECEMB_MAX_PEERS];
+  char* mine = g.arena[g.rank];
+  if ((int)threadIdx.x < g.world)
+    s_dst[threadIdx.x] = (uint4*)(g.arena[threadIdx.x] + g.off_grads) + (int64_t)g.rank * g.sender_vecs;
+  __syncthreads();
+  uint32_t* done = (uint32_t*)(mine + g.off_gate + kGateOffDone);
+  const int64_t stride = (int64_t)g.push_ctas * kBwdThreads * 4;
+  for (int t = 0; t < g.tables; ++t) {
+    const uint4* src = g.src + (int64_t)t * g.vecs_per_table;
+    const int64_t dst0 = (int64_t)t * g.vecs_per_table;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBwdThreads * 4 + threadIdx.x; i0 < g.vecs_per_table && !(g.debug & 2);
+         i0 += stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * kBwdThreads;
+        if (i < g.vecs_per_table) v[u] = ldg_nc_v4(src + i);
+      }
+      for (int q = 1; q <= g.world; ++q) {
+        int p = g.rank + q;
+        if (p >= g.world) p -= g.world;
+        uint4* dst = s_dst[p] + dst0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t i = i0 + u * kBwdThreads;
+          if (i < g.vecs_per_table) stg_v4(dst + i, v[u]);
+        }
+      }
+    }
+    // ONE system-scope fence per CTA and table, by one thread after the CTA barrier (the barrier orders the
+    // other threads' stores before it): a membar.sys costs microseconds on a busy GPU -- with one per thread
+    // plus one by the last CTA, signalling 8 tables took 0.13 ms and the reduction sat waiting for it.  Only
+    // warp 0 signals; the other warps go straight on to the next table.
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int last = 0;
+      if (threadIdx.x == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        // wraps back to 0 with the last pusher CTA of the step: nothing to reset
+        last = atomicInc(done + t, (unsigned)g.push_ctas - 1u) == (unsigned)g.push_ctas - 1u;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      // one more sender's table t has landed at rank threadIdx.x: its arrival count of table t goes up by one
+      // (remote atomic over NVLink); the count only ever grows, step s is complete at s * world.  Every
+      // pusher CTA fenced before its increment of `done`, so all of the table is visible system-wide here.
+      if (last && (int)threadIdx.x < g.world)
+        atomicAdd_system((unsigned long long*)(g.arena[threadIdx.x] + g.off_gate + kGateOffFlags) + t, 1ull);
+    }
+  }
+}
+
+// Reduction side: ONE thread per CTA waits until every rank's gradients of table `t_need` (the last table the
+// CTA's chunks touch) have landed here, i.e. until the table's arrival count reaches step * world; the CTA
+// barrier releases the other groups.  One poller per CTA, relaxed loads, back-off from 0.5 to 8 us: thousands
+// of groups wait at the start of a step, and a spin from all of them on one word saturates its L2 bank -- the
+// pushers' own atomics then queue behind the polls (measured: +0.13 ms on a 0.25 ms update).  False on a
+// timeout: status bit 2 is set and the CTA's chunks are skipped -- a late peer may lose a step, never corrupt it.
+__device__ __forceinline__ bool gate_wait(const PeerGate& g, int t_need) {
+  char* mine = g.arena[g.rank];
+  const uint64_t want = *(const volatile uint64_t*)(mine + g.off_gate) * (uint64_t)g.world;
+  const uint64_t* count = (const uint64_t*)(mine + g.off_gate + kGateOffFlags) + t_need;
+  const long long t0 = clock64();
+  unsigned ns = 500;
+  bool ok = true;
+  while (ld_relaxed_sys_u64(count) < want) {
+    if (clock64() - t0 > g.timeout_cycles) {
+      atomicOr(g.status, 2u);
+      ok = false;
+      break;
+    }
+    __nanosleep(ns);
+    if (ns < 8000) ns *= 2;
+  }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  return ok;
+}
+
+__global__ void gate_advance_kernel(uint64_t* step) { *step += 1; }
+
 
 template <int G>
 __device__ __forceinline__ float masked_group_sum(float v, uint32_t mask) {
@@ -625,12 +713,35 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
   constexpr int GROUPS = kBwdThreads / G;
   static_assert(E * sizeof(T) == 16, "one 16-byte vector per lane");
   static_assert(UPD == RECEMB_UPD_ROWWISE_ADAGRAD || UPD == RECEMB_UPD_SGD, "scalar-state updates only");
+  if (a.gate.push_ctas > 0 && (int)blockIdx.x < a.gate.push_ctas) {  // the peers need my gradients whatever
+    gate_push_role(a.gate);                                           // my own status says
+    return;
+  }
   if (a.guard && *reinterpret_cast<const volatile uint32_t*>(a.guard) != 0u) return;
   const int lane = threadIdx.x & 31;
   const int lig = lane % G;
   const int gi_warp = lane / G;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi_warp * G));
-  const int chunk = blockIdx.x * GROUPS + threadIdx.x / G;
+  const int cta = (int)blockIdx.x - a.gate.push_ctas;
+  if (a.gate.push_ctas > 0) {
+    // sorted keys are table-major: the CTA's chunks need the gradients of the tables up to its last valid key's
+    __shared__ int s_go;
+    if (threadIdx.x == 0) {
+      const int64_t first = (int64_t)cta * GROUPS * a.chunk;
+      const int64_t last = min(first + (int64_t)GROUPS * a.chunk, (int64_t)a.n) - 1;
+      int go = 1;
+      if (first < a.n && a.keys[first] < a.sentinel) {
+        const uint32_t klast = a.keys[last];
+        const int t_need = klast >= a.sentinel ? a.gate.tables - 1
+                                               : min((int)(klast / a.gate.rows_per_table), a.gate.tables - 1);
+        if (!(a.gate.debug & 1)) go = gate_wait(a.gate, t_need);
+      }
+      s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+  }
+  const int chunk = cta * GROUPS + threadIdx.x / G;
   const int num_chunks = (a.n + a.chunk - 1) / a.chunk;
   if (chunk >= num_chunks) return;
   const int start = chunk * a.chunk;
@@ -869,14 +980,17 @@ static void launch_kernel(const SegArgs& a_in, cudaStream_t s) {
     const int64_t resident = (int64_t)occ * sm_count(dev) * groups;
     const int64_t chunks64 = ((int64_t)a.n + CH - 1) / CH;
     if (fit && chunks64 > resident) {
+      // the pusher CTAs of a fused launch hold slots of the first wave: without them in the count the
+      // reduction spills into one more (almost empty) wave, +0.13 ms on cfg 5
       const int64_t waves = chunks64 / resident;
-      const int64_t c = ((int64_t)a.n + waves * resident - 1) / (waves * resident);
+      const int64_t slots = waves * resident - (int64_t)a.gate.push_ctas * groups;
+      const int64_t c = slots > 0 ? ((int64_t)a.n + slots - 1) / slots : 0;
       if (c > CH && c <= 2 * CH) a.chunk = (int32_t)c;
     }
     t_chunk_used = a.chunk;
   }
   const int chunks = (a.n + a.chunk - 1) / a.chunk;
-  kernel<<<(unsigned)((chunks + groups - 1) / groups), kBwdThreads, 0, s>>>(a);
+  kernel<<<(unsigned)((chunks + groups - 1) / groups + a.gate.push_ctas), kBwdThreads, 0, s>>>(a);
 }
 
 template <int G, int V, int E, typename GT, typename WT, bool L0, typename Cfg>
@@ -1206,6 +1320,13 @@ extern "C" int recemb_bwd_apply(const void* plan, size_t plan_bytes, int64_t n_s
                                   workspace, workspace_bytes, nullptr, device, stream);
 }
 
+static int apply_impl(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad, int grad_dtype,
+                      int64_t grad_rows, int32_t dim, int32_t slots_per_grad_row, const float* slot_weight,
+                      const float* grad_row_scale, int update, void* table, int dtype, int64_t num_rows,
+                      void* state1, void* state2, const recemb_optim_params* hp_host, void* workspace,
+                      size_t workspace_bytes, const uint32_t* skip_if_nonzero, int device, recemb_stream_t stream,
+                      const PeerGate* gate);
+
 extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad,
                                         int grad_dtype, int64_t grad_rows, int32_t dim,
                                         int32_t slots_per_grad_row, const float* slot_weight,
@@ -1214,6 +1335,74 @@ extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int
                                         const recemb_optim_params* hp_host, void* workspace,
                                         size_t workspace_bytes, const uint32_t* skip_if_nonzero, int device,
                                         recemb_stream_t stream) {
+  return apply_impl(plan, plan_bytes, n_slots, grad, grad_dtype, grad_rows, dim, slots_per_grad_row, slot_weight,
+                    grad_row_scale, update, table, dtype, num_rows, state1, state2, hp_host, workspace,
+                    workspace_bytes, skip_if_nonzero, device, stream, nullptr);
+}
+
+extern "C" int recemb_peer_bwd_apply_fused(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                           const void* plan, size_t plan_bytes, const void* my_grad, int32_t tables,
+                                           int64_t bags_per_table, int32_t dim, int dtype, int update, void* table,
+                                           int64_t total_rows, int64_t rows_per_table, void* state1,
+                                           const recemb_optim_params* hp, void* workspace, size_t workspace_bytes,
+                                           int32_t push_ctas, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(group && arena && my_grad, "null peer group / arena / gradients");
+  RECEMB_CHECK_ARG(group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
+                       group->rank < group->world, "peer group world / rank out of range");
+  RECEMB_CHECK_ARG(tables >= 1 && tables <= kGateTables, "tables %d outside [1, %d]", tables, kGateTables);
+  RECEMB_CHECK_ARG(bags_per_table >= 1 && (int64_t)tables * bags_per_table == arena->bags_total,
+                   "tables x bags_per_table != arena bags_total");
+  RECEMB_CHECK_ARG(rows_per_table >= 1 && rows_per_table < 0xffffffffll && rows_per_table * tables == total_rows,
+                   "rows_per_table x tables != total_rows");
+  RECEMB_CHECK_ARG(push_ctas >= 1 && push_ctas <= 1024, "push_ctas %d outside [1, 1024]", push_ctas);
+  RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "bad dtype");
+  RECEMB_CHECK_ARG((uintptr_t)my_grad % 16 == 0, "gradients must be 16-byte aligned");
+  const int64_t row_bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED((row_bytes == 256 || row_bytes == 512) &&
+                         (update == RECEMB_UPD_ROWWISE_ADAGRAD || update == RECEMB_UPD_SGD) &&
+                         env_flag("RECEMB_SEG_PRE", 1) != 0,
+                     "fused push: rows of 256 / 512 bytes with row-wise Adagrad or SGD only");
+  PeerGate g;
+  g.push_ctas = push_ctas;
+  g.world = group->world;
+  g.rank = group->rank;
+  g.tables = tables;
+  for (int i = 0; i < RECEMB_MAX_PEERS; ++i) g.arena[i] = nullptr;
+  for (int i = 0; i < group->world; ++i) {
+    RECEMB_CHECK_ARG(group->arena[i], "peer arena %d not mapped", i);
+    g.arena[i] = (char*)group->arena[i];
+  }
+  g.off_grads = arena->off_grads;
+  g.off_gate = arena->off_gate;
+  g.src = (const uint4*)my_grad;
+  g.vecs_per_table = bags_per_table * (row_bytes / 16);
+  g.sender_vecs = arena->bags_total * (row_bytes / 16);
+  g.rows_per_table = (uint32_t)rows_per_table;
+  {
+    const char* e = getenv("RECEMB_PEER_BARRIER_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    g.timeout_cycles = (long long)(sec * 2.0e9);
+  }
+  char* mine = g.arena[g.rank];
+  g.status = (uint32_t*)(mine + arena->off_status);
+  g.debug = env_flag("RECEMB_GATE_DEBUG", 0);
+  DeviceGuard dg(device);
+  RECEMB_CUDA(dg.err);
+  gate_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)(mine + arena->off_gate));
+  RECEMB_LAUNCHED();
+  const int64_t n = (int64_t)group->world * arena->cap;
+  return apply_impl(plan, plan_bytes, n, mine + arena->off_grads, dtype, (int64_t)group->world * arena->bags_total, dim,
+                    1, nullptr, nullptr, update, table, dtype, total_rows, state1, nullptr, hp, workspace,
+                    workspace_bytes, g.status, device, stream, &g);
+}
+
+static int apply_impl(const void* plan, size_t plan_bytes, int64_t n_slots, const void* grad, int grad_dtype,
+                      int64_t grad_rows, int32_t dim, int32_t slots_per_grad_row, const float* slot_weight,
+                      const float* grad_row_scale, int update, void* table, int dtype, int64_t num_rows,
+                      void* state1, void* state2, const recemb_optim_params* hp_host, void* workspace,
+                      size_t workspace_bytes, const uint32_t* skip_if_nonzero, int device, recemb_stream_t stream,
+                      const PeerGate* gate) {
   RECEMB_CHECK_ARG(plan && table, "null plan/table");
   RECEMB_CHECK_ARG(grad_rows >= 0 && slots_per_grad_row >= 1, "bad grad_rows / slots_per_grad_row");
   RECEMB_CHECK_ARG(update >= RECEMB_UPD_DENSE_GRAD && update <= RECEMB_UPD_ADAMW, "bad update %d", update);
@@ -1276,6 +1465,7 @@ extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int
   else a.hp = recemb_optim_params{};
   a.chunk = kChunk0;
   a.guard = skip_if_nonzero;
+  a.gate.push_ctas = 0;
   {
     static const int pf = env_flag("RECEMB_SEG_PF_BULK", 0);
     a.pf_bulk = pf;
@@ -1300,6 +1490,10 @@ extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int
     a.flag_out = (uint32_t*)w + l + 1;
     int rc;
     if (l == 0 && t_ev_start) cudaEventRecord(t_ev_start, s);
+    if (gate) {  // level 0 only: the first CTAs push my gradients, the chunks are gated per table
+      if (l == 0) a.gate = *gate;
+      else a.gate.push_ctas = 0;
+    }
     if (l == 0) {
       if (grad_dtype == RECEMB_F32 && dtype == RECEMB_F32)
         rc = launch_seg<float, float, true>(a, shape, s);

@@ -225,6 +225,47 @@ __device__ __forceinline__ int64_t kshift_row(int64_t id, int c, const ModN& m) 
   return floor_mod(signed_rotl(id, c), m);
 }
 
+// ------------------------------------------------------ peer flag helpers ----
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint64_t ld_relaxed_sys_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused gradient push of the sharded backward (bwd.cu: the first `push_ctas` CTAs of the level-0 launch are
+// the all-gather push, table by table; the others are the segmented reduction, every chunk gated on the
+// arrival count of the last table it touches).  Gate region of an arena: step u64 | done u32[kGateTables] |
+// arrival counts u64[kGateTables] (+ reserve) (recemb_peer_arena.off_gate).
+constexpr int kGateTables = 64;
+constexpr int64_t kGateOffDone = 64;
+constexpr int64_t kGateOffFlags = kGateOffDone + kGateTables * 4;
+constexpr int64_t kGateBytes = kGateOffFlags + (int64_t)kGateTables * RECEMB_MAX_PEERS * 8;
+
+struct PeerGate {
+  int32_t push_ctas;  // 0 = no fused push: plain segmented reduction
+  int32_t world, rank;
+  int32_t tables;
+  char* arena[RECEMB_MAX_PEERS];
+  int64_t off_grads;
+  int64_t off_gate;
+  const uint4* src;          // my pooled gradients [tables][bags_per_table][row]
+  int64_t vecs_per_table;    // bags_per_table * row_vecs
+  int64_t sender_vecs;       // bags_total * row_vecs: stride between two senders' slices
+  uint32_t rows_per_table;   // local rows of one table in my stacked shard
+  long long timeout_cycles;
+  uint32_t* status;
+  int debug;  // RECEMB_GATE_DEBUG (timing experiments only): 1 = reduction does not wait, 2 = pushers do not copy
+};
+
 // ------------------------------------------------------- memory helpers ----
 // 128-bit read-only load that does not allocate in L1 (table rows are touched
 // once per CTA; L2 keeps whatever reuse exists).

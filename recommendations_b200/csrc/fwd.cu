@@ -379,15 +379,22 @@ struct PoolArgs {
   const uint4* peer_table[RECEMB_MAX_PEERS];
   int64_t rows_div;  // num_rows / world: local rows of owner o = rows_div + (o < rows_rem)
   uint32_t rows_rem;
+  int prefetch;      // local tables: rows of this group's NEXT bag are pulled into L2 one iteration ahead
 };
 
 constexpr int kPoolTileIds = 2048;
 
-template <int G, int V, typename T, bool PEER>
+// The walk over a bag is a chain (ids -> hash -> row loads -> accumulate) that a warp repeats bag after
+// bag: with ragged bags only a few row loads are in flight per group and the kernel is bound by DRAM
+// latency, not bandwidth (ncu, cfg 3: issue-active 49 %, 8 long-scoreboard stalls per issue, DRAM 35 %).
+// The ids of the whole tile are already in shared memory, so every group hashes the slots of the bag it
+// will process in its NEXT iteration and requests their rows with prefetch.global.L2 (no registers held):
+// the real loads one iteration later find them in L2.
+template <int G, int V, typename T, bool PEER, int BATCH_ = 0>
 __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const PoolArgs a) {
   constexpr int RPW = 32 / G;
   constexpr int E = Vec16<T>::kElems;
-  constexpr int BATCH = (V == 1) ? 8 : (V == 2 ? 4 : 2);
+  constexpr int BATCH = BATCH_ > 0 ? BATCH_ : ((V == 1) ? 8 : (V == 2 ? 4 : 2));
   __shared__ alignas(16) int64_t s_ids[2][kPoolTileIds];
   __shared__ alignas(8) uint64_t s_bar[2];
   __shared__ const uint4* s_peer[PEER ? RECEMB_MAX_PEERS : 1];
@@ -426,6 +433,25 @@ __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const 
       if (live && a.lengths) hi = min(max(a.lengths[bag], 0), P);
       if (a.last_n > 0) lo = max(0, hi - a.last_n);
       if (!live) hi = lo = 0;
+      if constexpr (!PEER) {
+        const int nlb = lb + kWarps * RPW;  // this group's bag of the next iteration
+        if (a.prefetch && nlb < nb) {
+          const int64_t nbag = tile * a.bags_per_tile + nlb;
+          int nhi = P, nlo = 0;
+          if (a.lengths) nhi = min(max(a.lengths[nbag], 0), P);
+          if (a.last_n > 0) nlo = max(0, nhi - a.last_n);
+          for (int p = nlo + lig; p < nhi; p += G) {
+            const int64_t id = ids[nlb * P + p];
+            int64_t row = (a.zero_pad && id == a.pad_id) ? -1 : row_of(id, a.h);
+            if (row >= 0) row = shard_local_row(row, a.h);
+            if (row >= 0) {
+              const uint4* src = a.table + (row + table_offset(nbag * P + p, a.h)) * a.row_vecs;
+              for (int v8 = 0; v8 < a.row_vecs; v8 += 8)  // one request per 128-byte line of the row
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + v8));
+            }
+          }
+        }
+      }
       // the two groups of a warp may have different windows: iterate to the warp max
       int span = hi - lo;
 #pragma unroll
@@ -613,8 +639,22 @@ static int launch_kshift(const KShiftArgs& a, RowShape shape, int64_t tiles, int
 template <typename T>
 static int launch_pool(const PoolArgs& a, RowShape shape, int64_t tiles, int device, cudaStream_t s, bool peer) {
   bool launched = false;
+  // rows of one 16-byte vector per lane: 4 row loads per lane and batch (no register spills at the 64-register
+  // cap of 4 CTAs per SM; with the L2 prefetch one iteration ahead cfg 3 runs 0.356 instead of 0.446 ms, and
+  // 0.385 without the prefetch).  RECEMB_POOL_BATCH=8 restores the 8-deep batches.
+  static const int batch4 = [] {
+    const char* e = getenv("RECEMB_POOL_BATCH");
+    return !(e && atoi(e) == 8);
+  }();
   if (peer) {
     DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T, true>>(a, tiles, device, s)))
+  } else if (batch4 && shape.V == 1) {
+    DISPATCH_GV(1, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
+    DISPATCH_GV(2, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
+    DISPATCH_GV(4, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
+    DISPATCH_GV(8, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
+    DISPATCH_GV(16, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
+    DISPATCH_GV(32, 1, (launch_persistent<pool_kernel<G, V, T, false, 4>>(a, tiles, device, s)))
   } else {
     DISPATCH_SHAPES((launch_persistent<pool_kernel<G, V, T, false>>(a, tiles, device, s)))
   }
@@ -845,6 +885,13 @@ static int pool_fwd_common(const void* table, const recemb_peer_group* group, in
   a.pool_mode = pool_mode;
   a.zero_pad = zero_pad;
   a.pad_id = pad_id;
+  {
+    static const int pf = [] {  // RECEMB_POOL_PREFETCH=0 turns the one-iteration-ahead L2 prefetch off
+      const char* e = getenv("RECEMB_POOL_PREFETCH");
+      return e ? atoi(e) : 1;
+    }();
+    a.prefetch = pf;
+  }
   // every tile start must be 16-byte aligned and every tile an even id count
   a.bulk_ok = ((uintptr_t)ids % 16 == 0) && (((int64_t)a.bags_per_tile * bag_size) % 2 == 0);
   DeviceGuard g(device);

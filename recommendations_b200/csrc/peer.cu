@@ -20,15 +20,6 @@ struct PeerPtrs {
   int32_t rank;
 };
 
-__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // One warp.  Lane p publishes this rank's new epoch in rank p's flag slot and waits until rank p
 // has published at least the same epoch here.  The release store orders every earlier store of
 // this stream (kernel boundaries are system-scope ordered, the fence makes it cumulative); the
@@ -220,6 +211,8 @@ extern "C" int recemb_peer_arena_layout(int32_t world, int64_t cap, int64_t bags
   off += 128;
   out->off_counts = off;
   off += 256;
+  out->off_gate = off;
+  off += (int64_t)align_up((size_t)kGateBytes, 256);
   out->off_inbox = off;
   off += (int64_t)align_up((size_t)((int64_t)world * cap * 8), 256);
   out->off_grads = off;

@@ -411,6 +411,30 @@ def peer_barrier(group, channel: int = 0) -> None:
                                          N.stream_ptr(group.device)), "recemb_peer_barrier")
 
 
+def peer_bwd_apply_fused(plan: "BackwardPlan", my_grad: torch.Tensor, *, group, table: torch.Tensor, update: int,
+                         state1: Optional[torch.Tensor], hp, tables: int, bags_per_table: int, rows_per_table: int,
+                         push_ctas: int = 32, workspace: Optional[torch.Tensor] = None) -> None:
+    """Sharded backward, sender and owner side in ONE level-0 launch: the first push_ctas CTAs store my pooled
+    gradients into every rank's buffer table by table, the others reduce + update my rows, each chunk gated on
+    the flags of the last table it touches (recemb_peer_bwd_apply_fused)."""
+    dim = table.shape[1]
+    my_grad = my_grad.contiguous().view(-1, dim)
+    if my_grad.dtype != table.dtype:
+        raise N.NativeError("fused push: gradients must have the table's dtype")
+    if my_grad.shape[0] != tables * bags_per_table:
+        raise N.NativeError(f"my_grad has {my_grad.shape[0]} rows, expected {tables} x {bags_per_table}")
+    dev = N.require_cuda(plan.buf, my_grad, table, state1)
+    lib = N.load()
+    need = int(lib.recemb_bwd_apply_workspace_bytes(plan.n_slots, dim))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=table.device)
+    N.check(lib.recemb_peer_bwd_apply_fused(
+        C.byref(group.struct), C.byref(group.layout), N.ptr(plan.buf), plan.buf.numel(), N.ptr(my_grad), tables,
+        bags_per_table, dim, N.dtype_code(table.dtype), update, N.ptr(table), table.shape[0], rows_per_table,
+        N.ptr(state1), C.byref(hp), N.ptr(workspace), workspace.numel(), push_ctas, dev, N.stream_ptr(dev)),
+        "recemb_peer_bwd_apply_fused")
+
+
 def peer_signal(group, channel: int) -> None:
     """First half of a barrier round on the current stream (never blocks): see recemb_peer_signal."""
     N.check(N.load().recemb_peer_signal(C.byref(group.struct), C.byref(group.layout), channel, group.device,

@@ -351,16 +351,31 @@ class _PeerPoolFn(torch.autograd.Function):
             # two backward passes without a forward in between (several outstanding forwards): the
             # peers' previous update may still be reading the gradient buffer this pass overwrites
             ops.peer_barrier(pg, channel=0)
-        ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
-        _mark(module, "grads_push")
-        ops.peer_barrier(pg, channel=0)
-        main.wait_event(ctx.plan_ready)
-        _mark(module, "barrier+plan")
-        # guard = my arena's status word: an overflowed inbox (flagged by the sender) or a timed-out
-        # barrier leaves the shard untouched in this step; the host raises at its next status check
-        res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype),
-                                 slots_per_grad_row=1, guard=pg.status_word())
-        _mark(module, "apply")
+        if module._fused_push_ok(g):
+            # ONE launch: its first CTAs push my gradients to every rank table by table, the others reduce and
+            # update my rows as soon as the tables they touch have arrived from everybody (no barrier, the
+            # NVLink transfer of table t + 1 runs under the HBM-bound update of table t)
+            main.wait_event(ctx.plan_ready)
+            t = module.num_tables
+            module.emb.begin_update()
+            module.emb._apply_fused(ctx.plan, g, 1, None, None, 0.0, peer_push=dict(
+                group=pg, tables=t, bags_per_table=int(pg.layout.bags_total) // t,
+                rows_per_table=module.local_rows, push_ctas=module.push_ctas))
+            module.emb.end_update()
+            module.emb._release_plan(ctx.plan)
+            res = None
+            _mark(module, "push+apply (fused)")
+        else:
+            ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
+            _mark(module, "grads_push")
+            ops.peer_barrier(pg, channel=0)
+            main.wait_event(ctx.plan_ready)
+            _mark(module, "barrier+plan")
+            # guard = my arena's status word: an overflowed inbox (flagged by the sender) or a timed-out
+            # barrier leaves the shard untouched in this step; the host raises at its next status check
+            res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, module.emb.weight.dtype),
+                                     slots_per_grad_row=1, guard=pg.status_word())
+            _mark(module, "apply")
         ctx.plan = None
         pg.snapshot_status()
         module._peer_dirty = True
@@ -618,10 +633,16 @@ class RowWiseShardedEmbeddingBag(nn.Module):
         self.peer_forward = peer_forward
         # peer + push + several tables: the step is pipelined over table groups (_PeerPipelinedFn); needs the
         # fused optimizer (each group's rows are updated in place).  RECEMB_PEER_GROUPS overrides the default
-        # (4 groups, or one per table when there are fewer); 1 = the unpipelined step.
+        # (1 = the unpipelined step: measured on cfg 5 at W = 2 / 4 the extra launches of G = 2 / 4 groups cost as
+        # much as the overlap wins, 0.54 / 0.56 / 0.67 ms and 0.633 / 0.631 / 0.717 ms for G = 1 / 2 / 4).
         if pipeline_groups is None:
-            pipeline_groups = int(os.environ.get("RECEMB_PEER_GROUPS", "4"))
+            pipeline_groups = int(os.environ.get("RECEMB_PEER_GROUPS", "1"))
         self.pipeline_groups = max(1, min(int(pipeline_groups), self.num_tables))
+        # the backward's gradient push fused into the update launch (_fused_push_ok); CTAs that push
+        # (True: whenever rows cross NVLink, i.e. world > 1; "force": also on one rank, for tests; False: never)
+        env = os.environ.get("RECEMB_PEER_FUSED_PUSH", "1")
+        self.fused_push = False if env == "0" else ("force" if env == "force" else True)
+        self.push_ctas = int(os.environ.get("RECEMB_PEER_PUSH_CTAS", "32"))
         self._pipe = None
         self._pipe_key = None
         self._peer: Optional[PeerGroup] = None
@@ -706,6 +727,18 @@ class RowWiseShardedEmbeddingBag(nn.Module):
                                                table_ptrs=None if first is None else first.table_ptrs())
         self._peer, self._peer_key = cache[key], key
         self._peer_dirty = True
+
+    def _fused_push_ok(self, g: torch.Tensor) -> bool:
+        """The pooled backward as one launch (gradient push + gated segmented reduction): fused optimizer with a
+        scalar per-row state, rows of 256 / 512 bytes.  RECEMB_PEER_FUSED_PUSH=0 keeps push -> barrier -> update."""
+        f = self.emb.fused
+        if f is None or f.accumulate or f.kind not in ("rowwise_adagrad", "sgd") or self.fused_push is False:
+            return False
+        row_bytes = self.emb_dim * self.emb.weight.element_size()
+        # one rank: nothing crosses NVLink, the plain copy + update is faster (0.456 vs 0.59 ms on cfg 5)
+        return ((self.comm.world > 1 or self.fused_push == "force") and row_bytes in (256, 512)
+                and g.dtype == self.emb.weight.dtype
+                and self.num_tables <= 64 and not getattr(self, "sequence_mode", False))
 
     # ------------------------------------------------------ pipelined groups ----
     def _pipelined(self) -> bool:

@@ -195,9 +195,12 @@ class EmbeddingTable(nn.Module):
             self.fused_step += 1  # no facade: every backward is one optimizer step
 
     def _apply_fused(self, plan, grad2d, slots_per_grad_row, slot_weight, grad_row_scale, grad_div,
-                     rows: Optional[Tuple[int, int]] = None, guard: Optional[torch.Tensor] = None) -> None:
+                     rows: Optional[Tuple[int, int]] = None, guard: Optional[torch.Tensor] = None,
+                     peer_push: Optional[dict] = None) -> None:
         """`rows` = (r0, r1): the plan's keys are relative to that row range of the table (one table group
-        of a stacked shard); the update touches nothing outside it."""
+        of a stacked shard); the update touches nothing outside it.
+        `peer_push` (dict(group, tables, bags_per_table, rows_per_table, push_ctas)): grad2d are THIS rank's
+        pooled gradients and the launch pushes them to every rank itself (ops.peer_bwd_apply_fused)."""
         cfg = self.fused
         self._ensure_state()
         step = self.fused_step + 1
@@ -213,6 +216,10 @@ class EmbeddingTable(nn.Module):
             s1 = None if s1 is None else s1[r0:r1]
             s2 = None if s2 is None else s2[r0:r1]
         with torch.no_grad():
+            if peer_push is not None:
+                ops.peer_bwd_apply_fused(plan, grad2d, table=w, update=N.UPDATE_BY_NAME[cfg.kind], state1=s1, hp=hp,
+                                         **peer_push)
+                return
             ops.bwd_apply(plan, grad2d, table=w, update=N.UPDATE_BY_NAME[cfg.kind],
                           slots_per_grad_row=slots_per_grad_row, state1=s1, state2=s2, hp=hp,
                           slot_weight=slot_weight, grad_row_scale=grad_row_scale, grad_div=grad_div, guard=guard)

@@ -19,6 +19,8 @@ from pathlib import Path
 import torch
 import torch.distributed as dist
 
+os.environ.setdefault("RECEMB_PEER_BARRIER_TIMEOUT_S", "30")   # a benchmark must never sit in a dead barrier
+
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
@@ -224,6 +226,13 @@ def phase_bench(world, rank, dev, rows_per_gpu=25_000_000, reps=10):
     timed("plan(unpack+sort)", lambda: ops.peer_plan(pg, total_rows))
     gv = pg.grads_view(DIM, torch.bfloat16)
     timed("apply(seg+adagrad)", lambda: mod.emb.consume(plan, gv, slots_per_grad_row=1))
+    if mod.emb.fused is not None:
+        hp = ops.make_optim_params(lr=0.05, eps=1e-10)
+        s1 = mod.emb._buffers.get("opt_state1")
+        for ctas in (8, 32, 128):
+            timed(f"fused push+apply (push_ctas={ctas})", lambda: ops.peer_bwd_apply_fused(
+                plan, grad.view(-1, DIM), group=pg, table=mod.emb.weight.data, update=N.UPD_ROWWISE_ADAGRAD, state1=s1,
+                hp=hp, tables=T, bags_per_table=B_LOCAL, rows_per_table=mod.local_rows, push_ctas=ctas))
     pg.raise_on_status(synchronize=True)
     mod.close_peer()
     return res

@@ -479,3 +479,39 @@ def test_peer_sequence_module_single_rank(tables):
     torch.testing.assert_close(a.emb.weight.grad, want_g, rtol=1e-5, atol=1e-5)
     a.peer_group().raise_on_status(synchronize=True)
     a.close_peer()
+
+
+@pytest.mark.parametrize("kind", ["rowwise_adagrad", "sgd"])
+@pytest.mark.parametrize("forward", ["pull", "push"])
+def test_fused_push_update_equals_push_barrier_update(kind, forward):
+    """recemb_peer_bwd_apply_fused (the first CTAs of the level-0 launch push the gradients table by table, the
+    reduction groups are gated on per-table arrival counts) == allgather push -> barrier -> guarded update:
+    same kernel arithmetic and chunking, so weights and optimizer state are bit-identical over several steps."""
+    from recommendations_b200.sharded import RowWiseShardedEmbeddingBag
+    import recommendations_b200 as R
+    n_rows, dim, b, p, tables = 50021, 128, 300, 20, 5
+    ids = seeded_ids(tables * b * p, 31, (tables, b, p)).to(DEV)
+    lengths = torch.randint(0, p + 1, (tables, b), generator=torch.Generator().manual_seed(4)).to(DEV)
+    go = torch.randn(tables, b, dim, device=DEV, dtype=torch.bfloat16)
+    mods = []
+    for fused in ("force", False):
+        m = RowWiseShardedEmbeddingBag(n_rows, dim, exchange="peer", peer_forward=forward, num_tables=tables,
+                                       dtype=torch.bfloat16, device=DEV, pipeline_groups=1,
+                                       fused_optimizer=R.FusedOptimizerConfig(kind=kind, lr=0.05))
+        m.fused_push = fused
+        if mods:
+            m.load_state_dict(mods[0].state_dict())
+        mods.append(m)
+    for _ in range(3):
+        outs = [m(ids, lengths) for m in mods]
+        assert torch.equal(outs[0], outs[1])
+        for o in outs:
+            o.backward(go)
+    assert mods[0]._fused_push_ok(go.view(-1, dim)) and not mods[1]._fused_push_ok(go.view(-1, dim))
+    assert torch.equal(mods[0].emb.weight, mods[1].emb.weight)
+    if kind == "rowwise_adagrad":
+        assert torch.equal(mods[0].emb.opt_state1, mods[1].emb.opt_state1)
+    assert mods[0].emb.fused_step == mods[1].emb.fused_step == 3
+    for m in mods:
+        m.peer_group().raise_on_status(synchronize=True)
+        m.close_peer()
