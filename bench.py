@@ -331,6 +331,16 @@ def run_b200(args):
             # inside the lookup kernels, whole step replayed from one CUDA graph
             sharded = bench_sharded.run_cfg5(world, rank, dev, args.steps, args.warmup, exchange="peer",
                                              graph=True)
+            if world > 1:
+                # the W = 1 anchor of the weak-scaling series in the SAME run: rank 0 alone times the step on
+                # its 1/W slice of the job (same per-GPU table bytes and batch), the others wait
+                if rank == 0:
+                    from recommendations_b200.sharded import SingleProcess
+                    anchor = bench_sharded.run_cfg5(1, 0, dev, args.steps, args.warmup, exchange="peer",
+                                                    graph=True, comm=SingleProcess())
+                    sharded["w1_anchor_ms_per_step"] = anchor["ms_per_step"]
+                    sharded["efficiency_vs_w1"] = anchor["ms_per_step"] / sharded["ms_per_step"]
+                dist.barrier()
         except Exception as exc:  # the headline line must survive a failure of the extra run
             sharded = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -112,7 +112,13 @@ enum recemb_update {
  *     output row (i / L) * K + q, q = position inside the window (mirrored when flip_len == L).  `out`
  *     must hold n rows (K = L); the first (n / L) * K are written.  The plan drops the slots outside the
  *     window and maps the others to the compact gradient rows.  This is QueryTower's batch-wide trim
- *     (models/lthm/sequence/query_tower.py:73-86) applied BEFORE the rows are moved instead of after. */
+ *     (models/lthm/sequence/query_tower.py:73-86) applied BEFORE the rows are moved instead of after.
+ *   out_features = F > 0 (table-batched pooled lookups and their plan; b = ids_per_table / bag_size bags per
+ *     table): the pooled row of bag g is written at row (g % b) * F + g / b + out_feature_offset of `out`,
+ *     i.e. feature-interleaved into a [b, F, dim] tensor -- the input layout of the ranker's dot interaction
+ *     (recemb_dot_interaction_fwd), so no concatenation copy sits between the lookup and the interaction;
+ *     the plan maps every slot to the same row of the [b, F, dim] gradient the interaction's backward
+ *     produces. */
 typedef struct recemb_layout {
   int64_t ids_per_table;
   int32_t num_tables;
@@ -122,6 +128,8 @@ typedef struct recemb_layout {
   int32_t seq_len;
   int32_t window_side;
   const int32_t* window_keep;
+  int32_t out_features;
+  int32_t out_feature_offset;
 } recemb_layout;
 
 typedef struct recemb_optim_params {

@@ -7,7 +7,7 @@ any op does, and a missing library raises instead of falling back.
 """
 from . import _native
 from .collection import EmbeddingCollection
-from .interaction import DotInteraction, dot_interaction
+from .interaction import DotInteraction, PooledInteraction, dot_interaction
 from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PatternFromTimelocal,
                      PooledEmbeddingBag, QREmbedding)
 from .logq import CascadedStreamingLogQCorrectionModule, StreamingLogQCorrectionModule
@@ -18,4 +18,5 @@ __all__ = [
     "CosineVectorEmbedding", "DotInteraction", "EmbeddingCollection", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
     "FusedOptimizerConfig", "KShiftEmbedding", "PatternFromTimelocal", "PooledEmbeddingBag", "QREmbedding",
     "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule", "SequenceWindow", "sequence_trim",
+    "PooledInteraction",
 ]

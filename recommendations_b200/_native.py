@@ -53,6 +53,8 @@ class Layout(C.Structure):
         ("seq_len", C.c_int32),
         ("window_side", C.c_int32),
         ("window_keep", C.c_void_p),
+        ("out_features", C.c_int32),
+        ("out_feature_offset", C.c_int32),
     ]
 
 
@@ -78,13 +80,14 @@ class PeerArena(C.Structure):
 
 
 def make_layout(ids_per_table: int = 0, num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
-                flip_len: int = 0, window=None):
+                flip_len: int = 0, window=None, out_features: int = 0, out_feature_offset: int = 0):
     """None when nothing is batched / sharded / flipped / windowed (the C side treats NULL as one plain table).
     window: a sequence.SequenceWindow (device-resident number of kept columns)."""
     if not ids_per_table and shard_world <= 1 and not flip_len and window is None:
         return None
     lay = Layout(ids_per_table=ids_per_table, num_tables=num_tables, shard_world=shard_world,
-                 shard_rank=shard_rank, flip_len=flip_len)
+                 shard_rank=shard_rank, flip_len=flip_len, out_features=out_features,
+                 out_feature_offset=out_feature_offset)
     if window is not None:
         if flip_len not in (0, window.seq_len):
             raise NativeError("a windowed lookup flips whole sequences: flip_len must be 0 or the window's seq_len")

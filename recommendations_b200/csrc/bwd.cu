@@ -120,7 +120,14 @@ __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArg
       }
     }
     a.keys[s] = key;
-    a.vals[s] = (a.h.flip_len | a.h.win_len) ? (uint32_t)(max(orow, (int64_t)0) * a.slots_per_id + c) : (uint32_t)s;
+    if (a.h.out_feats && a.bag_size > 0) {
+      // pooled bags whose gradient arrives feature-interleaved ([bags_per_table, F, dim], the interaction's
+      // backward): slot -> (gradient row of its bag) * bag_size + position
+      const int64_t bag = id_idx / a.bag_size;
+      a.vals[s] = (uint32_t)(bag_out_row(bag, a.h) * a.bag_size + (id_idx - bag * a.bag_size));
+    } else {
+      a.vals[s] = (a.h.flip_len | a.h.win_len) ? (uint32_t)(max(orow, (int64_t)0) * a.slots_per_id + c) : (uint32_t)s;
+    }
   }
 }
 
@@ -1240,6 +1247,12 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, const recemb_l
   a.lengths = lengths;
   a.last_n = last_n;
   a.sentinel = (uint32_t)total_rows;
+  if (a.h.out_feats) {
+    RECEMB_CHECK_ARG(bag_size > 0 && slots_per_id == 1 && layout->ids_per_table % bag_size == 0,
+                     "out_features needs pooled bags (bag_size > 0) with ids_per_table a multiple of bag_size");
+    a.h.out_bpt = (uint32_t)(layout->ids_per_table / bag_size);
+    RECEMB_UNSUPPORTED((int64_t)a.h.out_bpt * a.h.out_feats * bag_size < 0xffffffffll, "too many gradient slots");
+  }
   // the sort ping-pongs between the two pair buffers and always ends in the "out" one
   const bool start_in_out = sort_input_in_b(sort_shape(n, L.key_bits, device));
   a.keys = (uint32_t*)(base + (start_in_out ? L.off_keys_out : L.off_keys_in));

@@ -126,7 +126,18 @@ struct HashSpec {
   uint32_t win_len;
   uint32_t win_side;
   const int32_t* win_keep;
+  // pooled bags written feature-interleaved into [bags_per_table, out_feats, dim] (0 = bag order)
+  uint32_t out_feats;
+  uint32_t out_feat_off;
+  uint32_t out_bpt;  // bags per table
 };
+
+// output / gradient row of pooled bag g
+__device__ __forceinline__ int64_t bag_out_row(int64_t g, const HashSpec& h) {
+  if (!h.out_feats) return g;
+  const int64_t t = g / h.out_bpt;
+  return (g - t * h.out_bpt) * h.out_feats + t + h.out_feat_off;
+}
 
 // position i mirrored inside its sequence of L lookups (L == 0: unchanged)
 __device__ __forceinline__ int64_t flip_index(int64_t i, uint32_t L) {

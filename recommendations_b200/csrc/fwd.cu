@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 2) ? 4 : 1) pool_kernel(const 
           for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / cntf;
       }
       if (live) {
-        uint4* dst = a.out + bag * (int64_t)a.row_vecs;
+        uint4* dst = a.out + bag_out_row(bag, a.h) * (int64_t)a.row_vecs;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           const int vec = j * G + lig;
@@ -773,7 +773,7 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
                                  int32_t flip_len, void* out, float* inv_norm_out, int device,
                                  recemb_stream_t stream) {
   RECEMB_CHECK_ARG(flip_len >= 0, "flip_len < 0");
-  recemb_layout layout = {0, 0, 1, 0, flip_len, 0, 0, nullptr};
+  recemb_layout layout = {0, 0, 1, 0, flip_len, 0, 0, nullptr, 0, 0};
   return recemb_kshift_fwd_layout(table, num_rows, dim, dtype, ids, n, num_shifts, epilogue, &layout, out,
                                   inv_norm_out, device, stream);
 }
@@ -848,6 +848,13 @@ static int pool_fwd_common(const void* table, const recemb_peer_group* group, in
   if (rc) return rc;
   RECEMB_UNSUPPORTED(!(layout && layout->ids_per_table > 0) || num_bags * bag_size < 0xffffffffll,
                      "too many slots for table-batched mode");
+  if (a.h.out_feats) {
+    RECEMB_CHECK_ARG(layout->ids_per_table % bag_size == 0, "ids_per_table is not a multiple of bag_size");
+    a.h.out_bpt = (uint32_t)(layout->ids_per_table / bag_size);
+    const int64_t tabs = (num_bags + a.h.out_bpt - 1) / a.h.out_bpt;
+    RECEMB_CHECK_ARG(tabs + a.h.out_feat_off <= a.h.out_feats, "out_features %u < %lld tables + offset %u",
+                     a.h.out_feats, (long long)tabs, a.h.out_feat_off);
+  }
   a.table = (const uint4*)table;
   a.rows_div = num_rows;
   a.rows_rem = 0;

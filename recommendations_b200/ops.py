@@ -90,11 +90,15 @@ def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.
              hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0, pool_mode: int = N.POOL_SUM,
              zero_pad: bool = False, pad_id: int = 0, num_rows: Optional[int] = None,
              shard_world: int = 1, shard_rank: int = 0, bags_per_table: int = 0,
-             num_tables: int = 0) -> torch.Tensor:
+             num_tables: int = 0, out: Optional[torch.Tensor] = None, out_features: int = 0,
+             out_feature_offset: int = 0) -> torch.Tensor:
     """`num_rows` = GLOBAL rows of one table (default: table.shape[0]).  Sharded (shard_world > 1):
     `table` is this rank's row-wise shard and the result is this owner's partial pool.
     Table-batched (bags_per_table > 0): bag g uses table (g // bags_per_table) [% num_tables] of
-    the stacked (local) table."""
+    the stacked (local) table.
+    out_features = F > 0 (table-batched, `out` = a [bags_per_table, F, dim] tensor): the pooled row of bag g is
+    written at out[g % bags_per_table, g // bags_per_table + out_feature_offset] -- the dot interaction's input
+    layout, no concatenation afterwards; returns `out`."""
     if ids.dim() != 2:
         raise N.NativeError("pooled bags take ids of shape [num_bags, bag_size]")
     ids = ids.contiguous()
@@ -107,12 +111,22 @@ def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.
     dev = N.require_cuda(table, ids, lengths, per_slot_weight)
     m, p = ids.shape
     dim = table.shape[1]
-    out = torch.empty((m, dim), dtype=table.dtype, device=table.device)
+    if out_features:
+        if out is None or not out.is_contiguous() or out.dtype != table.dtype or bags_per_table <= 0 or \
+                tuple(out.shape) != (bags_per_table, out_features, dim):
+            raise N.NativeError("out_features needs table-batched bags and a contiguous `out` of shape "
+                                "[bags_per_table, out_features, dim] in the table dtype")
+        N.require_cuda(out)
+    elif out is None:
+        out = torch.empty((m, dim), dtype=table.dtype, device=table.device)
+    elif out.numel() != m * dim or out.dtype != table.dtype or not out.is_contiguous():
+        raise N.NativeError("preallocated `out` has the wrong size / dtype")
     N.check(N.load().recemb_pool_fwd(
         N.ptr(table), table.shape[0] if num_rows is None else num_rows, dim,
         N.dtype_code(table.dtype), N.ptr(ids), m, p, N.ptr(lengths), last_n, N.ptr(per_slot_weight),
         hash_mode, hash_arg, pool_mode, int(zero_pad), pad_id,
-        N.make_layout(bags_per_table * p, num_tables, shard_world, shard_rank), N.ptr(out), dev,
+        N.make_layout(bags_per_table * p, num_tables, shard_world, shard_rank, out_features=out_features,
+                      out_feature_offset=out_feature_offset), N.ptr(out), dev,
         N.stream_ptr(dev)), "recemb_pool_fwd")
     return out
 
@@ -136,7 +150,8 @@ class BackwardPlan:
               pad_row: int = -1, bag_size: int = 0, lengths: Optional[torch.Tensor] = None,
               last_n: int = 0, buf: Optional[torch.Tensor] = None, ids_per_table: int = 0,
               num_tables: int = 0, shard_world: int = 1, shard_rank: int = 0,
-              flip_len: int = 0, window=None) -> "BackwardPlan":
+              flip_len: int = 0, window=None, out_features: int = 0,
+              out_feature_offset: int = 0) -> "BackwardPlan":
         """num_rows is rows PER TABLE; with ids_per_table > 0 the plan covers the stacked table
         of ceil(n_ids / ids_per_table) tables and `self.num_rows` is the stacked total."""
         flat = _flat_ids(ids)
@@ -145,7 +160,8 @@ class BackwardPlan:
         dev = N.require_cuda(flat, lengths)
         n_slots = flat.numel() * slots_per_id
         lib = N.load()
-        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank, flip_len, window)
+        layout = N.make_layout(ids_per_table, num_tables, shard_world, shard_rank, flip_len, window, out_features,
+                               out_feature_offset)
         total_rows = int(lib.recemb_layout_total_rows(num_rows, layout, flat.numel()))
         need = int(lib.recemb_bwd_plan_bytes(n_slots, total_rows))
         if need == 0:
@@ -159,10 +175,11 @@ class BackwardPlan:
         recipe = (ids, dict(num_rows=num_rows, hash_mode=hash_mode, hash_arg=hash_arg, slots_per_id=slots_per_id,
                             zero_pad=zero_pad, pad_id=pad_id, pad_row=pad_row, bag_size=bag_size, lengths=lengths,
                             last_n=last_n, ids_per_table=ids_per_table, num_tables=num_tables,
-                            shard_world=shard_world, shard_rank=shard_rank, flip_len=flip_len, window=window))
-        # windowed: the slots map to the compact [batch * keep] gradient rows, fewer than the slots
+                            shard_world=shard_world, shard_rank=shard_rank, flip_len=flip_len, window=window,
+                            out_features=out_features, out_feature_offset=out_feature_offset))
+        # windowed / feature-interleaved: the slots map into a gradient tensor of another row count
         return BackwardPlan(buf=buf, n_slots=n_slots, num_rows=total_rows, slots_per_id=slots_per_id,
-                            slots_cover_grad=window is None, recipe=recipe)
+                            slots_cover_grad=window is None and not out_features, recipe=recipe)
 
     def _arr(self, which: int) -> torch.Tensor:
         arr_bytes = (self.n_slots * 4 + 255) // 256 * 256

@@ -102,6 +102,24 @@ def cfg3():
     report("cfg3 dot-interaction fwd (tcgen05): [16384,27,128] bf16 -> [16384,351]", ms,
            b * fp * r + b * fp * (fp - 1) // 2 * 2, flops_G=round(2 * b * fp * (fp - 1) // 2 * dim / 1e9, 3),
            tensor_GFLOPs_issued=round(2 * (b / 4) * 128 * 128 * dim / 1e9, 2))
+    # the forward as one pipeline: pooled rows written feature-interleaved straight into the interaction's
+    # input (recemb_layout.out_features), dense row copied into slot 0 -- vs lookup, permute + cat, interaction
+    feats_buf = torch.empty(b, fp, dim, device=DEV, dtype=torch.bfloat16)
+
+    def fwd_pipeline():
+        feats_buf[:, 0].copy_(dense)
+        ops.pool_fwd(w, ids, lengths=lengths, num_rows=n_rows, bags_per_table=b, num_tables=f,
+                     hash_mode=N.HASH_IDENTITY, out=feats_buf, out_features=fp, out_feature_offset=1)
+        return ops.dot_interaction_fwd(feats_buf)
+
+    def fwd_two_step():
+        pooled_ = pool().view(f, b, dim)
+        return ops.dot_interaction_fwd(torch.cat([dense.unsqueeze(1), pooled_.permute(1, 0, 2)], dim=1))
+    ms = timeit(fwd_pipeline)
+    ms2 = timeit(fwd_two_step)
+    report("cfg3 fwd pipeline: pooled lookup -> [B,27,128] in place -> tcgen05 interaction (no cat / permute)", ms,
+           valid * (8 + r) + f * b * 4 + 2 * b * fp * r + b * fp * (fp - 1) // 2 * 2, valid,
+           ms_lookup_cat_interaction=round(ms2, 4))
     go = torch.randn(b, fp * (fp - 1) // 2, device=DEV, dtype=torch.bfloat16)
     ms = timeit(lambda: ops.dot_interaction_bwd(feats, go))
     report("cfg3 dot-interaction bwd (tcgen05)", ms, b * fp * (fp - 1) // 2 * 2 + 2 * b * fp * r)

@@ -49,7 +49,7 @@ def check(world, rank, dev, exchange=None):
 
 
 def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=None, graph=False,
-             full_check=False):
+             full_check=False, comm=None):
     """Times the cfg 5 step on an already initialised process group; returns the result dict
     (every rank computes it, rank 0 prints it)."""
     class A:
@@ -57,8 +57,9 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     args = A()
     args.steps, args.warmup, args.rows_per_gpu = steps, warmup, rows_per_gpu
     n_rows = args.rows_per_gpu * world
+    # comm: sharded.SingleProcess() runs the W = 1 anchor on one rank of a larger job (world = 1 here)
     mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange=exchange,
-                                     peer_forward=PEER_FORWARD,
+                                     peer_forward=PEER_FORWARD, comm=comm,
                                      fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
     ids_host = ids_for(rank, T, B_LOCAL, P).pin_memory()
     ids = ids_host.to(dev)
@@ -138,6 +139,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     mod_exchange = mod.exchange
     mod_peer_forward = mod.peer_forward
     mod_groups = mod.pipeline_groups if mod._pipelined() else 1
+    mod_fused_push = bool(mod._fused_push_ok(grad.view(-1, DIM))) if mod_exchange == "peer" else False
     phases = None
     if graph:
         step = eager_step
@@ -169,7 +171,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
                                    f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange,
                        "peer_forward": mod_peer_forward if mod_exchange == "peer" else None,
-                       "pipeline_groups": mod_groups},
+                       "pipeline_groups": mod_groups, "fused_gradient_push": mod_fused_push},
             "nvlink": {"bytes_in_per_gpu_per_step": nv_in, "achieved_gbs": nv_in / t_step / 1e9,
                        "peak_gbs": NVLINK_GBS, "frac": nv_in / t_step / 1e9 / NVLINK_GBS},
             "gpu_launches": (launches_per_step * args.steps if graph else N.launch_count() - launches0),

@@ -76,3 +76,38 @@ def test_module_forward_backward():
     ref.backward(go.float())
     check(ss.grad, sr.grad)
     check(dd.grad, dr.grad)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_pooled_interaction_pipeline_equals_lookup_permute_cat_interaction(mode, fused):
+    """PooledInteraction (the pooled rows written feature-interleaved straight into the interaction's input,
+    the interaction's gradient read in place by the pooled backward) == EmbeddingCollection -> permute ->
+    DotInteraction (two concatenations): outputs bit-identical, gradients / fused updates equal."""
+    import recommendations_b200 as R
+    t, n_rows, dim, b, p = 5, 3001, 128, 300, 7
+    g = torch.Generator().manual_seed(12)
+    ids = torch.randint(-2 ** 40, 2 ** 40, (t, b, p), generator=g, dtype=torch.int64).to(DEV)
+    lengths = torch.randint(0, p + 1, (t, b), generator=g).to(DEV)
+    dense = torch.randn(b, dim, generator=g).to(torch.bfloat16).to(DEV)
+    go = torch.randn(b, dim + (t + 1) * t // 2, generator=g).to(torch.bfloat16).to(DEV)
+    opt = R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05) if fused else None
+    mk = lambda: R.EmbeddingCollection(t, n_rows, dim, kind="pooled", mode=mode, dtype=torch.bfloat16, device=DEV,  # noqa: E731
+                                       fused_optimizer=opt)
+    c1, c2 = mk(), mk()
+    c2.load_state_dict(c1.state_dict())
+    d1 = dense.clone().requires_grad_(True)
+    d2 = dense.clone().requires_grad_(True)
+    out1 = R.PooledInteraction(c1)(d1, ids, lengths)
+    out2 = R.DotInteraction()(d2, c2(ids, lengths).permute(1, 0, 2))
+    assert out1.shape == out2.shape == (b, dim + (t + 1) * t // 2)
+    assert torch.equal(out1, out2)
+    out1.backward(go)
+    out2.backward(go)
+    torch.testing.assert_close(d1.grad.float(), d2.grad.float(), rtol=1e-2, atol=1e-2)
+    if fused:
+        torch.testing.assert_close(c1.table.weight.float(), c2.table.weight.float(), rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(c1.table.opt_state1, c2.table.opt_state1, rtol=1e-2, atol=1e-4)
+    else:
+        for m1, m2 in zip(c1.members(), c2.members()):
+            torch.testing.assert_close(m1.weight.grad.float(), m2.weight.grad.float(), rtol=1e-2, atol=1e-2)
