@@ -139,7 +139,7 @@ def cfg3():
            f * b * p * 8 + f * b * r + uniq * (2 * r + 8), valid, unique_rows=uniq)
     ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, hash_mode=N.HASH_IDENTITY, bag_size=p,
                                                lengths=lengths, ids_per_table=b * p, num_tables=f, buf=plan_buf))
-    report("cfg3 plan alone (key kernel + hand-written radix sort)", ms, f * b * p * 8 * 2, valid)
+    report("cfg3 plan alone (key kernel + library radix sort)", ms, f * b * p * 8 * 2, valid)
 
 
 def zipf_rows(n, n_rows, alpha, seed):
@@ -180,7 +180,7 @@ def cfg4():
     report("cfg4 fwd+bwd", ms_f + ms_b, t * n * (8 + 2 * r) + t * n * (8 + r) + uniq * (2 * r + 8), t * n)
     ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, hash_mode=N.HASH_IDENTITY, ids_per_table=n,
                                                buf=plan_buf), iters=5)
-    report("cfg4 plan alone (key kernel + hand-written radix sort, Zipf keys)", ms, t * n * 8 * 2, t * n)
+    report("cfg4 plan alone (key kernel + library radix sort, Zipf keys)", ms, t * n * 8 * 2, t * n)
 
 
 def cfg2_plan():
@@ -189,7 +189,7 @@ def cfg2_plan():
     ids = torch.cat([uniform_ids(n, 1000 + i) for i in range(t)])
     plan_buf = torch.empty(int(N.load().recemb_bwd_plan_bytes(t * n, t * n_rows)), dtype=torch.uint8, device=DEV)
     ms = timeit(lambda: ops.BackwardPlan.build(ids, num_rows=n_rows, ids_per_table=n, buf=plan_buf))
-    report("cfg2 plan alone (key kernel + hand-written radix sort: 2 passes of 12 bits)", ms, t * n * 8 * 2, t * n)
+    report("cfg2 plan alone (key kernel + library radix sort (cub onesweep); RECEMB_PLAN_SORT=own: hand-written 2 x 12-bit LSD)", ms, t * n * 8 * 2, t * n)
 
 
 RUNNERS = {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4, "cfg2plan": cfg2_plan}
