@@ -161,6 +161,33 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------- B200 arm ----
+def bind_to_gpu_numa(local_rank: int):
+    """Multi-GPU runs: pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned id buffers
+    are allocated (first touch puts them on that NUMA node), so that 8 ranks x 131 MB of ids per step do not
+    all cross one socket's memory controller / inter-socket link on their way to PCIe.  Best effort: returns
+    the CPU list it bound to, or None (NVML unavailable, mask too narrow, affinity not settable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ent = vis.split(",")[local_rank].strip()
+            if not ent.isdigit():
+                return None
+            idx = int(ent)
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -171,6 +198,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 and os.environ.get("RECEMB_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
@@ -357,6 +385,8 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "module_path": module_path, "configs": configs, "sharded_cfg5": sharded,
             "clocks": clocks,
+            "host": {"cpu_count": os.cpu_count(),
+                     "rank0_bound_to_gpu_local_cpus": None if numa_cpus is None else len(numa_cpus)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
