@@ -190,6 +190,25 @@ RECEMB_API int recemb_kshift_fwd_layout(const void* table, int64_t num_rows, int
                              const recemb_layout* layout, void* out, float* inv_norm_out, int device,
                              recemb_stream_t stream);
 
+/* ---- several small lookups summed into one row (QueryTower's input, f1) ----- */
+/* out[i, :] = mask[i] ? masked_row : base[i, :] + sum_k table_k[transform_k(ids_k[i]), :], the terms added in
+ * order k = 0, 1, ... in fp32 (bf16: rounded after every add, as a chain of torch adds does) -- bit-exact
+ * models/lthm/sequence/query_tower.py:89-104:
+ *   x = inp_proj(input) + action_embedding(labels) + hod(ts) + how(ts) + dow(ts);  x = where(mask, pad, x)
+ * as ONE pass (one read of `base`, one write of `out`; the 4 / 24 / 168 / 7-row tables stay in L1) instead of
+ * four gathers, four adds and a where over [B, L, D].  base may be NULL (zeros); mask (uint8 [n]) optional;
+ * up to 8 terms; rows of at most 512 bytes.  terms_host is a HOST array. */
+typedef struct recemb_gather_term {
+  const void* table;   /* [num_rows, dim] in `dtype` */
+  int64_t num_rows;
+  const int64_t* ids;  /* [n] */
+  int hash_mode;       /* recemb_hash, e.g. RECEMB_HASH_FLOORMOD / RECEMB_HASH_DIV_FLOORMOD */
+  int64_t hash_arg;    /* DIV_FLOORMOD: the divisor (PatternFromTimelocal.div) */
+} recemb_gather_term;
+RECEMB_API int recemb_multi_gather_add_fwd(const void* base, const recemb_gather_term* terms_host, int32_t num_terms,
+                                int64_t n, int32_t dim, int dtype, const uint8_t* mask, const void* masked_row,
+                                void* out, int device, recemb_stream_t stream);
+
 /* ---- sequence window: the batch-wide trim (a7) ---------------------------- */
 /* QueryTower.forward's trim (models/lthm/sequence/query_tower.py:73-79) as one kernel, result left on the
  * device: a column is all-pad when every row of the batch is padded there -- data[b, l] == pad_id for

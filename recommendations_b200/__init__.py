@@ -11,12 +11,12 @@ from .interaction import DotInteraction, PooledInteraction, dot_interaction
 from .layers import (CosineVectorEmbedding, FlatEmbedding, KShiftEmbedding, PatternFromTimelocal,
                      PooledEmbeddingBag, QREmbedding)
 from .logq import CascadedStreamingLogQCorrectionModule, StreamingLogQCorrectionModule
-from .sequence import SequenceWindow, sequence_trim
+from .sequence import SequenceWindow, fused_lookup_sum, sequence_trim
 from .table import EmbeddingTable, FusedEmbeddingOptimizer, FusedOptimizerConfig
 
 __all__ = [
     "CosineVectorEmbedding", "DotInteraction", "EmbeddingCollection", "EmbeddingTable", "dot_interaction", "FlatEmbedding", "FusedEmbeddingOptimizer",
     "FusedOptimizerConfig", "KShiftEmbedding", "PatternFromTimelocal", "PooledEmbeddingBag", "QREmbedding",
     "CascadedStreamingLogQCorrectionModule", "StreamingLogQCorrectionModule", "SequenceWindow", "sequence_trim",
-    "PooledInteraction",
+    "PooledInteraction", "fused_lookup_sum",
 ]

@@ -58,6 +58,17 @@ class Layout(C.Structure):
     ]
 
 
+class GatherTerm(C.Structure):
+    """recemb_gather_term: one (table, ids, row transform) summand of recemb_multi_gather_add_fwd."""
+    _fields_ = [
+        ("table", C.c_void_p),
+        ("num_rows", C.c_int64),
+        ("ids", C.c_void_p),
+        ("hash_mode", C.c_int),
+        ("hash_arg", C.c_int64),
+    ]
+
+
 PEER_HANDLE_BYTES = 64
 MAX_PEERS = 16
 
@@ -117,6 +128,7 @@ SIGNATURES = {
     "recemb_kshift_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, _I32, _P, _P, _INT, _P]),
     "recemb_kshift_fwd_layout": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _INT, C.POINTER(Layout), _P, _P, _INT,
                                         _P]),
+    "recemb_multi_gather_add_fwd": (_INT, [_P, C.POINTER(GatherTerm), _I32, _I64, _I32, _INT, _P, _P, _P, _INT, _P]),
     "recemb_sequence_window_workspace_bytes": (_SZ, [_I32]),
     "recemb_sequence_window": (_INT, [_P, _INT, _I64, _I32, _I64, _I32, _INT, _P, _SZ, _P, _INT, _P]),
     "recemb_pool_fwd": (_INT, [_P, _I64, _I32, _INT, _P, _I64, _I32, _P, _I32, _P, _INT, _I64, _INT,

@@ -121,3 +121,115 @@ extern "C" int recemb_sequence_window(const void* data, int kind, int64_t batch,
   RECEMB_LAUNCHED();
   return RECEMB_OK;
 }
+
+// ---- QueryTower's input sum as one kernel (models/lthm/sequence/query_tower.py:89-104) -------------------
+//   x = inp_proj(input) + action_embedding(labels) + hod(ts) + how(ts) + dow(ts);  x = where(mask, pad, x)
+// The reference runs four gathers (each writes [B, L, D]), four adds (two reads + one write each) and a
+// where: ~19 passes over [B, L, D].  Here: one read of the dense term, one write of the result; the tables
+// have 4 / 24 / 168 / 7 rows and live in L1.  fp32 adds in the reference's left-to-right order (bit-exact).
+namespace recemb {
+
+constexpr int kMaxTerms = 8;
+
+struct MultiGatherArgs {
+  const uint4* base;  // [n, dim] or nullptr (zeros)
+  const uint4* table[kMaxTerms];
+  const int64_t* ids[kMaxTerms];
+  HashSpec h[kMaxTerms];
+  int32_t num_terms;
+  int64_t n;
+  int32_t vecs;
+  const uint8_t* mask;      // [n] non-zero = take masked_row
+  const uint4* masked_row;  // [dim]
+  uint4* out;
+};
+
+template <int G, typename T>
+__global__ void __launch_bounds__(kSeqThreads) multi_gather_add_kernel(const MultiGatherArgs a) {
+  constexpr int E = Vec16<T>::kElems;
+  const int lig = threadIdx.x % G;
+  int64_t i = (int64_t)blockIdx.x * (kSeqThreads / G) + threadIdx.x / G;
+  const int64_t stride = (int64_t)gridDim.x * (kSeqThreads / G);
+  for (; i < a.n; i += stride) {
+    if (lig >= a.vecs) continue;
+    if (a.mask && a.mask[i]) {
+      stg_cs_v4(a.out + i * a.vecs + lig, ldg_nc_l1_v4(a.masked_row + lig));
+      continue;
+    }
+    float acc[E];
+    if (a.base) {
+      Vec16<T>::unpack(ldg_nc_v4(a.base + i * a.vecs + lig), acc);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    }
+    for (int k = 0; k < a.num_terms; ++k) {
+      const int64_t row = row_of(a.ids[k][i], a.h[k]);
+      if (row < 0) continue;  // out-of-range identity id: contributes nothing
+      float f[E];
+      Vec16<T>::unpack(ldg_nc_l1_v4(a.table[k] + row * a.vecs + lig), f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] += f[e];
+      if (sizeof(T) == 2) {  // every add of the reference rounds to the tensor dtype
+        uint4 t = Vec16<T>::pack(acc);
+        Vec16<T>::unpack(t, acc);
+      }
+    }
+    stg_cs_v4(a.out + i * a.vecs + lig, Vec16<T>::pack(acc));
+  }
+}
+
+}  // namespace recemb
+
+extern "C" int recemb_multi_gather_add_fwd(const void* base, const recemb_gather_term* terms_host, int32_t num_terms,
+                                           int64_t n, int32_t dim, int dtype, const uint8_t* mask,
+                                           const void* masked_row, void* out, int device, recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(n >= 0 && dim > 0, "bad shape");
+  RECEMB_CHECK_ARG(num_terms >= 0 && num_terms <= kMaxTerms, "num_terms %d outside [0, %d]", num_terms, kMaxTerms);
+  RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "bad dtype");
+  if (n == 0) return RECEMB_OK;
+  RECEMB_CHECK_ARG(out && (num_terms == 0 || terms_host), "null pointer");
+  RECEMB_CHECK_ARG(!mask || masked_row, "a mask needs the row that masked positions receive");
+  const int64_t row_bytes = (int64_t)dim * (dtype == RECEMB_F32 ? 4 : 2);
+  RECEMB_UNSUPPORTED(row_bytes % 16 == 0 && row_bytes <= 512, "row of %lld bytes unsupported (16-byte multiple, <= 512)",
+                     (long long)row_bytes);
+  RECEMB_CHECK_ARG(((uintptr_t)base | (uintptr_t)out | (uintptr_t)masked_row) % 16 == 0, "base / out / masked_row misaligned");
+  MultiGatherArgs a;
+  a.base = (const uint4*)base;
+  a.num_terms = num_terms;
+  a.n = n;
+  a.vecs = (int32_t)(row_bytes / 16);
+  a.mask = mask;
+  a.masked_row = (const uint4*)masked_row;
+  a.out = (uint4*)out;
+  for (int k = 0; k < kMaxTerms; ++k) {
+    a.table[k] = nullptr;
+    a.ids[k] = nullptr;
+  }
+  for (int k = 0; k < num_terms; ++k) {
+    RECEMB_CHECK_ARG(terms_host[k].table && terms_host[k].ids && (uintptr_t)terms_host[k].table % 16 == 0,
+                     "term %d: null / misaligned table or ids", k);
+    a.table[k] = (const uint4*)terms_host[k].table;
+    a.ids[k] = terms_host[k].ids;
+    int rc = make_hash_spec(terms_host[k].hash_mode, terms_host[k].num_rows, terms_host[k].hash_arg, &a.h[k]);
+    if (rc) return rc;
+  }
+  DeviceGuard g(device);
+  RECEMB_CUDA(g.err);
+  int G = 1;
+  while (G < a.vecs) G <<= 1;
+  cudaStream_t s = (cudaStream_t)stream;
+#define MGA(G_)                                                                                   \
+  if (G == G_) {                                                                                  \
+    const int64_t per = kSeqThreads / G_;                                                         \
+    int64_t grid = (n + per - 1) / per;                                                           \
+    const int64_t cap_grid = (int64_t)sm_count(device) * 16;                                      \
+    if (grid > cap_grid) grid = cap_grid;                                                         \
+    if (dtype == RECEMB_F32) multi_gather_add_kernel<G_, float><<<(unsigned)grid, kSeqThreads, 0, s>>>(a);       \
+    else multi_gather_add_kernel<G_, __nv_bfloat16><<<(unsigned)grid, kSeqThreads, 0, s>>>(a);                    \
+  }
+  MGA(1) MGA(2) MGA(4) MGA(8) MGA(16) MGA(32)
+#undef MGA
+  RECEMB_LAUNCHED();
+  return RECEMB_OK;
+}

@@ -85,6 +85,46 @@ def kshift_fwd(table: torch.Tensor, ids: torch.Tensor, num_shifts: int, epilogue
     return out.view(*ids.shape, dim), inv
 
 
+def multi_gather_add_fwd(base: Optional[torch.Tensor], terms, *, mask: Optional[torch.Tensor] = None,
+                         masked_row: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = mask[i] ? masked_row : base[i] + sum_k table_k[transform_k(ids_k[i])] in one pass (added in
+    order k = 0, 1, ...).  terms: sequence of (table [rows, dim], ids [n...] int64, hash_mode, hash_arg)."""
+    if not terms and base is None:
+        raise N.NativeError("nothing to add")
+    first_ids = terms[0][1] if terms else None
+    shape = tuple(base.shape[:-1]) if base is not None else tuple(first_ids.shape)
+    dim = base.shape[-1] if base is not None else terms[0][0].shape[1]
+    dtype = base.dtype if base is not None else terms[0][0].dtype
+    n = 1
+    for d in shape:
+        n *= d
+    keep = []   # keeps the contiguous copies alive until the launch is enqueued
+    if base is not None:
+        base = base.contiguous()
+    arr = (N.GatherTerm * max(len(terms), 1))()
+    for k, (table, ids, hash_mode, hash_arg) in enumerate(terms):
+        flat = _flat_ids(ids)
+        if flat.numel() != n or table.shape[1] != dim or table.dtype != dtype:
+            raise N.NativeError(f"term {k}: ids / table do not match the base shape [{n}, {dim}] {dtype}")
+        keep.append(flat)
+        arr[k].table, arr[k].num_rows, arr[k].ids = table.data_ptr(), table.shape[0], flat.data_ptr()
+        arr[k].hash_mode, arr[k].hash_arg = hash_mode, hash_arg
+    if mask is not None:
+        mask = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+        if mask.numel() != n or mask.dtype != torch.uint8 or masked_row is None:
+            raise N.NativeError("mask must be bool / uint8 of the base's leading shape, with a masked_row")
+        masked_row = masked_row.contiguous().view(-1).to(dtype)
+        if masked_row.numel() != dim:
+            raise N.NativeError("masked_row must hold one row")
+    dev = N.require_cuda(base, mask, masked_row, *[t[0] for t in terms], *keep)
+    ref = base if base is not None else terms[0][0]
+    out = torch.empty(shape + (dim,), dtype=dtype, device=ref.device)
+    N.check(N.load().recemb_multi_gather_add_fwd(N.ptr(base), arr, len(terms), n, dim, N.dtype_code(dtype), N.ptr(mask),
+                                                 N.ptr(masked_row), N.ptr(out), dev, N.stream_ptr(dev)),
+            "recemb_multi_gather_add_fwd")
+    return out
+
+
 def pool_fwd(table: torch.Tensor, ids: torch.Tensor, *, lengths: Optional[torch.Tensor] = None,
              last_n: int = 0, per_slot_weight: Optional[torch.Tensor] = None,
              hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0, pool_mode: int = N.POOL_SUM,

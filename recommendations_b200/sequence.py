@@ -105,3 +105,66 @@ def sequence_trim(mask_inp: torch.Tensor, export_span: int) -> int:
     """QueryTower's `trim` (query_tower.py:73-79) for a left-padded mask [B, L] (True = padded): drop-in for
     the two torch reductions + nonzero of the reference, one kernel + one 8-byte read."""
     return SequenceWindow.from_mask(mask_inp, export_span, drop="head").trim
+
+
+# ------------------------------------------------------------ QueryTower's input sum ----
+class _LookupSumFn(torch.autograd.Function):
+    """out = where(mask, masked_row, base + sum_k table_k[h_k(ids_k)]) as ONE forward kernel
+    (recemb_multi_gather_add_fwd); backward: the masked gradient is the gradient of `base`, every table gets it
+    through the sort-based segmented reduction (tiny tables: a handful of very long runs, closed by the
+    multi-level records), masked_row gets the column sums of the masked positions."""
+
+    @staticmethod
+    def forward(ctx, base, masked_row, mask, specs, record, *anchors):
+        from . import ops
+        terms = [(h.weight.detach(), ids, mode, arg) for (h, ids, mode, arg) in specs]
+        out = ops.multi_gather_add_fwd(base, terms, mask=mask, masked_row=masked_row)
+        ctx.specs, ctx.mask, ctx.has_base = specs, mask, base is not None
+        ctx.row_shape = None if masked_row is None else tuple(masked_row.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import ops
+        g = grad_out.contiguous()
+        dim = g.shape[-1]
+        gm, g_row = g, None
+        if ctx.mask is not None:
+            m = ctx.mask.bool().unsqueeze(-1)
+            if ctx.needs_input_grad[1]:
+                g_row = (g * m).reshape(-1, dim).sum(0).reshape(ctx.row_shape)
+            gm = g.masked_fill(m, 0.0)
+        grads = []
+        for k, (holder, ids, mode, arg) in enumerate(ctx.specs):
+            if not ctx.needs_input_grad[5 + k]:
+                grads.append(None)
+                continue
+            plan = ops.BackwardPlan.build(ids, num_rows=holder.num_embeddings, hash_mode=mode, hash_arg=arg)
+            grads.append(holder.consume(plan, gm.reshape(-1, dim)))
+        return (gm if ctx.has_base and ctx.needs_input_grad[0] else None, g_row, None, None, None) + tuple(grads)
+
+
+def fused_lookup_sum(base: Optional[torch.Tensor], lookups, mask: Optional[torch.Tensor] = None,
+                     masked_row: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """QueryTower's input (models/lthm/sequence/query_tower.py:89-104) in one kernel:
+
+        x = fused_lookup_sum(self.inp_proj(input),
+                             [(self.action_embedding, labels), (self.time_embedding.hod, timestamp),
+                              (self.time_embedding.how, timestamp), (self.time_embedding.dow, timestamp)],
+                             mask=mask.squeeze(-1), masked_row=self.pad)
+
+    == where(mask, pad, inp_proj(input) + action(labels) + hod(ts) + how(ts) + dow(ts)), bit-exact in fp32 (the
+    adds run in the listed order).  `lookups`: (module, ids) pairs, module a recommendations_b200 FlatEmbedding
+    (without output normalisation) or PatternFromTimelocal; ids of base's leading shape."""
+    from . import layers as L
+    specs, anchors = [], []
+    for mod, ids in lookups:
+        if isinstance(mod, L.PatternFromTimelocal):
+            holder, mode, arg = mod.emb, N.HASH_DIV_FLOORMOD, int(mod.div)
+        elif isinstance(mod, L.FlatEmbedding) and not mod._normalize_output and not mod._fused_pad_mask:
+            holder, mode, arg = mod._emb_table, N.HASH_FLOORMOD, 0
+        else:
+            raise N.NativeError("fused_lookup_sum takes FlatEmbedding (plain) and PatternFromTimelocal modules")
+        specs.append((holder, ids.long(), mode, arg))
+        anchors.append(holder.grad_anchor())
+    return _LookupSumFn.apply(base, masked_row, mask, specs, torch.is_grad_enabled(), *anchors)

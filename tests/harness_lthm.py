@@ -279,6 +279,7 @@ class QueryTowerH(nn.Module):
         self.emb_heads = nn.ModuleList([nn.Linear(emb_dim, mc.product_tower.product_emb_dim, bias=False)
                                         for _ in range(self.export_tokens)])
         self.trim_fn = getattr(L, "trim_fn", None)
+        self.lookup_sum = getattr(L, "lookup_sum", None)
 
     @staticmethod
     def reference_trim(mask_inp: torch.Tensor, export_span: int) -> int:
@@ -301,10 +302,18 @@ class QueryTowerH(nn.Module):
         timestamp = timestamp[:, trim:].contiguous().long()
         target = target[:, trim:].contiguous()
         ids = ids[:, trim:].contiguous()
-        x = self.inp_proj(input) + self.action_embedding(labels) + self.time_embedding.hod(timestamp) \
-            + self.time_embedding.how(timestamp) + self.time_embedding.dow(timestamp)
-        seq_len = x.size(1)
-        x = torch.where(mask, self.pad.expand(bsz, seq_len, -1), x)
+        if self.lookup_sum is not None:
+            # query_tower.py:89-104 as one kernel: four tiny-table lookups + the dense term + the pad select
+            x = self.lookup_sum(self.inp_proj(input),
+                                [(self.action_embedding, labels), (self.time_embedding.hod, timestamp),
+                                 (self.time_embedding.how, timestamp), (self.time_embedding.dow, timestamp)],
+                                mask=mask.squeeze(-1), masked_row=self.pad)
+            seq_len = x.size(1)
+        else:
+            x = self.inp_proj(input) + self.action_embedding(labels) + self.time_embedding.hod(timestamp) \
+                + self.time_embedding.how(timestamp) + self.time_embedding.dow(timestamp)
+            seq_len = x.size(1)
+            x = torch.where(mask, self.pad.expand(bsz, seq_len, -1), x)
         pos = seq_len - torch.arange(0, seq_len + 1, device=device).unsqueeze(0)
         x = torch.cat((torch.zeros(1, 1, self.emb_dim, device=device).expand(bsz, -1, -1), x), dim=1)
         x = x + self.wpe(pos)
@@ -361,11 +370,12 @@ def reference_layers():
                            LogQ=LogQFixed, QueryTower=query_tower)
 
 
-def b200_layers(device="cuda:0", trim_fn=None, pretrim=False):
+def b200_layers(device="cuda:0", trim_fn=None, pretrim=False, fused_front_end=False):
     """recommendations_b200 modules swapped in (torch-compatible gradient mode: the reference's AdamW
     drives every parameter, wrapper.py:255-275).  pretrim: the product lookup is windowed BEFORE the rows
     are moved (recommendations_b200.sequence.SequenceWindow on ids == 0; QueryTower's own trim then acts on
-    the window)."""
+    the window).  fused_front_end: QueryTower's input sum (query_tower.py:89-104) through
+    recommendations_b200.fused_lookup_sum and its trim through sequence_trim."""
     import recommendations_b200 as R
     from functools import partial
     L = SimpleNamespace(name="b200",
@@ -374,7 +384,8 @@ def b200_layers(device="cuda:0", trim_fn=None, pretrim=False):
                         KShiftEmbedding=partial(R.KShiftEmbedding, device=device),
                         CosineVectorEmbedding=partial(R.CosineVectorEmbedding, device=device),
                         LogQ=partial(R.CascadedStreamingLogQCorrectionModule, device=device),
-                        trim_fn=trim_fn, pretrim=pretrim)
+                        trim_fn=trim_fn, pretrim=pretrim,
+                        lookup_sum=R.fused_lookup_sum if fused_front_end else None)
     L.QueryTower = lambda mc: QueryTowerH(mc, L)
     return L
 

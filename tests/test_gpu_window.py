@@ -155,3 +155,50 @@ def test_lthm_step_with_the_window_decided_before_the_gather(golden):
     res = H.run_step(model, H.batch_from_golden(g, DEV), steps=2)
     H.compare_with_golden(g, model, res, loss_rtol=1e-5, out_atol=2e-5, out_rtol=1e-4, grad_tol=1e-5, w_tol=1e-5)
     assert model.last_window_keep is not None and model.last_window_keep < model.cfg.hist
+
+
+def test_fused_lookup_sum_equals_the_chain_of_lookups_and_adds():
+    """query_tower.py:89-104 as one kernel: bit-exact forward (fp32 adds in the reference's order), gradients of
+    the dense term, the pad row and the four tiny tables equal to autograd through the separate modules."""
+    import recommendations_b200 as R
+    b, length, dim = 48, 37, 64
+    g = torch.Generator().manual_seed(2)
+    base = torch.randn(b, length, dim, generator=g).to(DEV).requires_grad_(True)
+    base2 = base.detach().clone().requires_grad_(True)
+    labels = torch.randint(0, 4, (b, length), generator=g).to(DEV)
+    ts = torch.randint(1_600_000_000, 1_700_000_000, (b, length), generator=g).to(DEV)
+    mask = (torch.rand(b, length, generator=g) < 0.3).to(DEV)
+    pad = torch.nn.Parameter(torch.randn(1, 1, dim, generator=g).to(DEV))
+    pad2 = torch.nn.Parameter(pad.detach().clone())
+    def mods():
+        torch.manual_seed(5)
+        return (R.FlatEmbedding(4, dim, device=DEV), R.PatternFromTimelocal(3600, 24, dim, device=DEV),
+                R.PatternFromTimelocal(3600, 168, dim, device=DEV), R.PatternFromTimelocal(86400, 7, dim, device=DEV))
+    m1, m2 = mods(), mods()
+    for a, c in zip(m1, m2):
+        c.load_state_dict(a.state_dict())
+    got = R.fused_lookup_sum(base, [(m1[0], labels), (m1[1], ts), (m1[2], ts), (m1[3], ts)], mask=mask, masked_row=pad)
+    x = base2 + m2[0](labels) + m2[1](ts) + m2[2](ts) + m2[3](ts)
+    want = torch.where(mask.unsqueeze(-1), pad2.expand(b, length, -1), x)
+    assert torch.equal(got, want)
+    go = torch.randn(b, length, dim, generator=g).to(DEV)
+    got.backward(go)
+    want.backward(go)
+    assert torch.equal(base.grad, base2.grad)
+    torch.testing.assert_close(pad.grad, pad2.grad, rtol=1e-5, atol=1e-5)
+    for a, c in zip(m1, m2):
+        wa = next(a.parameters()).grad
+        wc = next(c.parameters()).grad
+        torch.testing.assert_close(wa, wc, rtol=1e-5, atol=1e-4)
+
+
+def test_lthm_step_with_fused_front_end(golden):
+    """cfg 1 with every piece of the B200 sequence front end switched on: the window decided before the product
+    lookup, QueryTower's trim through sequence_trim, its input sum through fused_lookup_sum."""
+    import recommendations_b200 as R
+    g = golden("lthm_step")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    L = H.b200_layers(DEV, trim_fn=R.sequence_trim, pretrim=True, fused_front_end=True)
+    model = H.model_from_golden(g, L, device=DEV)
+    res = H.run_step(model, H.batch_from_golden(g, DEV), steps=2)
+    H.compare_with_golden(g, model, res, loss_rtol=1e-5, out_atol=2e-5, out_rtol=1e-4, grad_tol=1e-5, w_tol=1e-5)
