@@ -113,6 +113,9 @@ enum recemb_update {
  *     must hold n rows (K = L); the first (n / L) * K are written.  The plan drops the slots outside the
  *     window and maps the others to the compact gradient rows.  This is QueryTower's batch-wide trim
  *     (models/lthm/sequence/query_tower.py:73-86) applied BEFORE the rows are moved instead of after.
+ *   partition = 1 (peer exchange, table-batched, shard_world > 1): TABLE-wise instead of row-wise -- table t
+ *     lives whole on rank t % shard_world as local table t / shard_world (recemb_peer_bucket_push routes every
+ *     lookup of table t to that rank, local row = (t / W) * num_rows + row).
  *   out_features = F > 0 (table-batched pooled lookups and their plan; b = ids_per_table / bag_size bags per
  *     table): the pooled row of bag g is written at row (g % b) * F + g / b + out_feature_offset of `out`,
  *     i.e. feature-interleaved into a [b, F, dim] tensor -- the input layout of the ranker's dot interaction
@@ -130,6 +133,7 @@ typedef struct recemb_layout {
   const int32_t* window_keep;
   int32_t out_features;
   int32_t out_feature_offset;
+  int32_t partition;
 } recemb_layout;
 
 typedef struct recemb_optim_params {
@@ -448,6 +452,12 @@ RECEMB_API int recemb_peer_pool_fwd(const recemb_peer_group* group, int64_t num_
  * (recemb_sum_partials, fixed owner order). */
 RECEMB_API int recemb_peer_pool_push(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
                           int dtype, int device, recemb_stream_t stream);
+/* Table-wise partitioning (recemb_layout.partition = 1): every bag has exactly one owner, so the partial row
+ * IS the pooled row; zero rows are written only for empty bags of the tables this rank owns (bag g belongs to
+ * table g / bags_per_table), and the requester picks parts[t % world][bags of table t] instead of summing. */
+RECEMB_API int recemb_peer_pool_push_tablewise(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                    int32_t dim, int dtype, int64_t bags_per_table, int device,
+                                    recemb_stream_t stream);
 
 /* Backward, sender side.  recemb_shard_bucket whose entries land in the owners' inboxes: entry
  * k of my bucket for owner o is stored at inbox(o)[rank][k], the bucket size at counts(o)[rank].
@@ -505,6 +515,15 @@ RECEMB_API int recemb_peer_bwd_apply_fused(const recemb_peer_group* group, const
                                 int64_t total_rows, int64_t rows_per_table, void* state1,
                                 const recemb_optim_params* hp, void* workspace, size_t workspace_bytes,
                                 int32_t push_ctas, int device, recemb_stream_t stream);
+/* Same for table-wise partitioning: the gradients of table t are pushed to rank t % world ONLY (every gradient
+ * row crosses NVLink at most once) and gate its local table t / world; `table` holds
+ * ceil((tables - rank) / world) whole tables of rows_per_table rows. */
+RECEMB_API int recemb_peer_bwd_apply_fused_tablewise(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                          const void* plan, size_t plan_bytes, const void* my_grad, int32_t tables,
+                                          int64_t bags_per_table, int32_t dim, int dtype, int update, void* table,
+                                          int64_t total_rows, int64_t rows_per_table, void* state1,
+                                          const recemb_optim_params* hp, void* workspace, size_t workspace_bytes,
+                                          int32_t push_ctas, int device, recemb_stream_t stream);
 
 /* ---- ranker pairwise dot interaction (a11) --------------------------------- */
 /* feats bf16 [batch, num_feats, dim] -> out bf16 [batch, num_feats*(num_feats-1)/2]:

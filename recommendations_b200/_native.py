@@ -55,6 +55,7 @@ class Layout(C.Structure):
         ("window_keep", C.c_void_p),
         ("out_features", C.c_int32),
         ("out_feature_offset", C.c_int32),
+        ("partition", C.c_int32),
     ]
 
 
@@ -168,6 +169,11 @@ SIGNATURES = {
     "recemb_peer_bwd_apply_fused": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _SZ, _P, _I32, _I64,
                                            _I32, _INT, _INT, _P, _I64, _I64, _P, C.POINTER(OptimParams), _P, _SZ,
                                            _I32, _INT, _P]),
+    "recemb_peer_pool_push_tablewise": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _I64, _INT,
+                                               _P]),
+    "recemb_peer_bwd_apply_fused_tablewise": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _SZ, _P, _I32,
+                                                     _I64, _I32, _INT, _INT, _P, _I64, _I64, _P,
+                                                     C.POINTER(OptimParams), _P, _SZ, _I32, _INT, _P]),
     "recemb_peer_pool_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _I32, _INT, _INT, _P]),
     "recemb_peer_bucket_push": (_INT, [C.POINTER(PeerGroupStruct), C.POINTER(PeerArena), _P, _I64,
                                        C.POINTER(Layout), _INT, _I64, _I64, _INT, _I64, _I32, _P, _I32, _P, _SZ,

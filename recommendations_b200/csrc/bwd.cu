@@ -263,6 +263,9 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
   for (int t = 0; t < g.tables; ++t) {
     const uint4* src = g.src + (int64_t)t * g.vecs_per_table;
     const int64_t dst0 = (int64_t)t * g.vecs_per_table;
+    // table-wise partitioning: table t has ONE owner, t % world -- its gradients cross NVLink once
+    const int q_lo = g.partition ? ((t % g.world) - g.rank + g.world - 1) % g.world + 1 : 1;
+    const int q_hi = g.partition ? q_lo : g.world;
     for (int64_t i0 = (int64_t)blockIdx.x * kBwdThreads * 4 + threadIdx.x; i0 < g.vecs_per_table && !(g.debug & 2);
          i0 += stride) {
       uint4 v[4];
@@ -271,7 +274,7 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
         const int64_t i = i0 + u * kBwdThreads;
         if (i < g.vecs_per_table) v[u] = ldg_nc_v4(src + i);
       }
-      for (int q = 1; q <= g.world; ++q) {
+      for (int q = q_lo; q <= q_hi; ++q) {
         int p = g.rank + q;
         if (p >= g.world) p -= g.world;
         uint4* dst = s_dst[p] + dst0;
@@ -298,8 +301,12 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
       // one more sender's table t has landed at rank threadIdx.x: its arrival count of table t goes up by one
       // (remote atomic over NVLink); the count only ever grows, step s is complete at s * world.  Every
       // pusher CTA fenced before its increment of `done`, so all of the table is visible system-wide here.
-      if (last && (int)threadIdx.x < g.world)
+      if (g.partition) {  // only the owner waits for table t, as its local table t / world
+        if (last && (int)threadIdx.x == t % g.world)
+          atomicAdd_system((unsigned long long*)(g.arena[threadIdx.x] + g.off_gate + kGateOffFlags) + t / g.world, 1ull);
+      } else if (last && (int)threadIdx.x < g.world) {
         atomicAdd_system((unsigned long long*)(g.arena[threadIdx.x] + g.off_gate + kGateOffFlags) + t, 1ull);
+      }
     }
   }
 }
@@ -739,8 +746,8 @@ __global__ void __launch_bounds__(kBwdThreads, Cfg::MINB) seg_pre_kernel(const S
       int go = 1;
       if (first < a.n && a.keys[first] < a.sentinel) {
         const uint32_t klast = a.keys[last];
-        const int t_need = klast >= a.sentinel ? a.gate.tables - 1
-                                               : min((int)(klast / a.gate.rows_per_table), a.gate.tables - 1);
+        const int t_need = klast >= a.sentinel ? a.gate.local_tables - 1
+                                               : min((int)(klast / a.gate.rows_per_table), a.gate.local_tables - 1);
         if (!(a.gate.debug & 1)) go = gate_wait(a.gate, t_need);
       }
       s_go = go;
@@ -1353,20 +1360,52 @@ extern "C" int recemb_bwd_apply_guarded(const void* plan, size_t plan_bytes, int
                     workspace_bytes, skip_if_nonzero, device, stream, nullptr);
 }
 
+static int peer_bwd_fused_impl(const recemb_peer_group* group, const recemb_peer_arena* arena, const void* plan,
+                               size_t plan_bytes, const void* my_grad, int32_t tables, int64_t bags_per_table,
+                               int32_t dim, int dtype, int update, void* table, int64_t total_rows,
+                               int64_t rows_per_table, void* state1, const recemb_optim_params* hp, void* workspace,
+                               size_t workspace_bytes, int32_t push_ctas, int partition, int device,
+                               recemb_stream_t stream);
+
 extern "C" int recemb_peer_bwd_apply_fused(const recemb_peer_group* group, const recemb_peer_arena* arena,
                                            const void* plan, size_t plan_bytes, const void* my_grad, int32_t tables,
                                            int64_t bags_per_table, int32_t dim, int dtype, int update, void* table,
                                            int64_t total_rows, int64_t rows_per_table, void* state1,
                                            const recemb_optim_params* hp, void* workspace, size_t workspace_bytes,
                                            int32_t push_ctas, int device, recemb_stream_t stream) {
+  return peer_bwd_fused_impl(group, arena, plan, plan_bytes, my_grad, tables, bags_per_table, dim, dtype, update, table,
+                             total_rows, rows_per_table, state1, hp, workspace, workspace_bytes, push_ctas, 0, device,
+                             stream);
+}
+
+extern "C" int recemb_peer_bwd_apply_fused_tablewise(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                                     const void* plan, size_t plan_bytes, const void* my_grad,
+                                                     int32_t tables, int64_t bags_per_table, int32_t dim, int dtype,
+                                                     int update, void* table, int64_t total_rows,
+                                                     int64_t rows_per_table, void* state1,
+                                                     const recemb_optim_params* hp, void* workspace,
+                                                     size_t workspace_bytes, int32_t push_ctas, int device,
+                                                     recemb_stream_t stream) {
+  return peer_bwd_fused_impl(group, arena, plan, plan_bytes, my_grad, tables, bags_per_table, dim, dtype, update, table,
+                             total_rows, rows_per_table, state1, hp, workspace, workspace_bytes, push_ctas, 1, device,
+                             stream);
+}
+
+static int peer_bwd_fused_impl(const recemb_peer_group* group, const recemb_peer_arena* arena, const void* plan,
+                               size_t plan_bytes, const void* my_grad, int32_t tables, int64_t bags_per_table,
+                               int32_t dim, int dtype, int update, void* table, int64_t total_rows,
+                               int64_t rows_per_table, void* state1, const recemb_optim_params* hp, void* workspace,
+                               size_t workspace_bytes, int32_t push_ctas, int partition, int device,
+                               recemb_stream_t stream) {
   RECEMB_CHECK_ARG(group && arena && my_grad, "null peer group / arena / gradients");
   RECEMB_CHECK_ARG(group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
                        group->rank < group->world, "peer group world / rank out of range");
   RECEMB_CHECK_ARG(tables >= 1 && tables <= kGateTables, "tables %d outside [1, %d]", tables, kGateTables);
   RECEMB_CHECK_ARG(bags_per_table >= 1 && (int64_t)tables * bags_per_table == arena->bags_total,
                    "tables x bags_per_table != arena bags_total");
-  RECEMB_CHECK_ARG(rows_per_table >= 1 && rows_per_table < 0xffffffffll && rows_per_table * tables == total_rows,
-                   "rows_per_table x tables != total_rows");
+  const int local_tables = partition ? (tables - group->rank + group->world - 1) / group->world : tables;
+  RECEMB_CHECK_ARG(rows_per_table >= 1 && rows_per_table < 0xffffffffll && rows_per_table * local_tables == total_rows,
+                   "rows_per_table x (local) tables != total_rows");
   RECEMB_CHECK_ARG(push_ctas >= 1 && push_ctas <= 1024, "push_ctas %d outside [1, 1024]", push_ctas);
   RECEMB_CHECK_ARG(dtype == RECEMB_F32 || dtype == RECEMB_BF16, "bad dtype");
   RECEMB_CHECK_ARG((uintptr_t)my_grad % 16 == 0, "gradients must be 16-byte aligned");
@@ -1399,6 +1438,8 @@ extern "C" int recemb_peer_bwd_apply_fused(const recemb_peer_group* group, const
   }
   char* mine = g.arena[g.rank];
   g.status = (uint32_t*)(mine + arena->off_status);
+  g.partition = partition;
+  g.local_tables = local_tables;
   g.debug = env_flag("RECEMB_GATE_DEBUG", 0);
   DeviceGuard dg(device);
   RECEMB_CUDA(dg.err);

@@ -130,6 +130,7 @@ struct HashSpec {
   uint32_t out_feats;
   uint32_t out_feat_off;
   uint32_t out_bpt;  // bags per table
+  uint32_t partition;  // peer bucket: 1 = table-wise (table t whole on rank t % shard_world)
 };
 
 // output / gradient row of pooled bag g
@@ -274,6 +275,8 @@ struct PeerGate {
   uint32_t rows_per_table;   // local rows of one table in my stacked shard
   long long timeout_cycles;
   uint32_t* status;
+  int32_t partition;     // 1 = table-wise: table t goes to rank t % world only, gating its local table t / world
+  int32_t local_tables;  // tables in MY shard
   int debug;  // RECEMB_GATE_DEBUG (timing experiments only): 1 = reduction does not wait, 2 = pushers do not copy
 };
 

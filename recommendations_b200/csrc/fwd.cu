@@ -773,7 +773,7 @@ extern "C" int recemb_kshift_fwd(const void* table, int64_t num_rows, int32_t di
                                  int32_t flip_len, void* out, float* inv_norm_out, int device,
                                  recemb_stream_t stream) {
   RECEMB_CHECK_ARG(flip_len >= 0, "flip_len < 0");
-  recemb_layout layout = {0, 0, 1, 0, flip_len, 0, 0, nullptr, 0, 0};
+  recemb_layout layout = {0, 0, 1, 0, flip_len, 0, 0, nullptr, 0, 0, 0};
   return recemb_kshift_fwd_layout(table, num_rows, dim, dtype, ids, n, num_shifts, epilogue, &layout, out,
                                   inv_norm_out, device, stream);
 }

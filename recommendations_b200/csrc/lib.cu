@@ -57,9 +57,12 @@ int make_hash_spec(int hash_mode, int64_t num_rows, int64_t hash_arg, HashSpec* 
   h.win_len = 0;
   h.win_side = 0;
   h.win_keep = nullptr;
+  h.partition = 0;
   h.out_feats = h.out_feat_off = h.out_bpt = 0;  // pool_fwd_common / recemb_bwd_plan fill out_bpt from the bag size
   if (layout) {
     RECEMB_CHECK_ARG(layout->out_features >= 0 && layout->out_feature_offset >= 0, "out_features / offset < 0");
+    RECEMB_CHECK_ARG(layout->partition == 0 || layout->partition == 1, "partition must be 0 (row-wise) or 1 (table-wise)");
+    h.partition = (uint32_t)layout->partition;
     if (layout->out_features > 0) {
       RECEMB_CHECK_ARG(layout->ids_per_table > 0, "out_features needs table-batched lookups (ids_per_table)");
       h.out_feats = (uint32_t)layout->out_features;
@@ -170,7 +173,7 @@ extern "C" int recemb_flat_step_host(const int64_t* ids_host, int64_t n, int64_t
   // another stream) is still computing; the kernels below must not.
   if (wait_event_after_copy)
     RECEMB_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)wait_event_after_copy, 0));
-  recemb_layout layout = {ids_per_table, 0, 1, 0, 0, 0, 0, nullptr, 0, 0};  // no sharding, no flip, no window
+  recemb_layout layout = {ids_per_table, 0, 1, 0, 0, 0, 0, nullptr, 0, 0, 0};  // no sharding, no flip, no window
   int rc;
   if (fork) {
     // the plan (hash + radix sort) only needs the ids: it runs on plan_stream while the gather

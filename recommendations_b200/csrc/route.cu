@@ -78,17 +78,24 @@ __global__ void __launch_bounds__(kRtThreads) bucket_count_kernel(const BucketAr
     const int64_t srow = ok ? row_of(id, a.h) : -1;  // -1 also for an out-of-range identity id
     if (srow >= 0) {
       const uint64_t row = (uint64_t)srow;
-      uint64_t q;
-      const uint32_t o = (uint32_t)udivmod(row, a.h.mod_world, &q);
-      // stacked shard of owner o: table t starts at t * local_rows(o)
-      const uint64_t local_rows = ((uint64_t)a.num_rows - o + world - 1) / world;
       uint32_t t = 0;
       if (a.h.ids_per_table) {
         t = (uint32_t)s / a.h.ids_per_table;
         if (a.h.num_tables) t %= a.h.num_tables;
       }
+      uint32_t o;
+      if (a.h.partition) {
+        // table-wise: table t lives whole on rank t % world as its local table t / world
+        o = t % world;
+        lrow = (uint32_t)(row + (uint64_t)(t / world) * (uint64_t)a.num_rows);
+      } else {
+        uint64_t q;
+        o = (uint32_t)udivmod(row, a.h.mod_world, &q);
+        // stacked shard of owner o: table t starts at t * local_rows(o)
+        const uint64_t local_rows = ((uint64_t)a.num_rows - o + world - 1) / world;
+        lrow = (uint32_t)(q + (uint64_t)t * local_rows);
+      }
       owner = (uint8_t)o;
-      lrow = (uint32_t)(q + (uint64_t)t * local_rows);
       atomicAdd(&s_hist[o], 1u);
     }
     a.owner8[s] = owner;
@@ -306,6 +313,7 @@ struct PoolInboxArgs {
   const void* table;
   int32_t vecs;
   uint4* parts[RECEMB_MAX_PEERS];  // requester s: its parts region, slice of THIS owner
+  int64_t bags_per_table;          // > 0: table-wise partitioning, only bags of tables t % world == rank are mine
 };
 
 template <int G, typename T>
@@ -332,8 +340,20 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
   // parts[rank] is written exactly once per step, the requester never zero-fills): the run that follows
   // a gap of bag numbers fills it, the last run of the region fills the tail.
   auto zero_rows = [&](uint32_t k0, uint32_t k1) {  // keys [k0, k1)
-    if (lig < a.vecs)
-      for (uint32_t z = k0; z != k1; ++z) stg_v4(out + (size_t)(z - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
+    if (lig >= a.vecs) return;
+    if (a.bags_per_table > 0) {  // table-wise: skip the bags of tables other ranks own, a whole table at a time
+      uint32_t z = k0;
+      while (z != k1) {
+        const uint32_t t = (uint32_t)((z - key_base) / (uint32_t)a.bags_per_table);
+        const uint32_t t_end = key_base + (t + 1u) * (uint32_t)a.bags_per_table;
+        const uint32_t stop = (t_end - z) < (k1 - z) ? t_end : k1;
+        if ((int)(t % (uint32_t)a.world) == a.rank)
+          for (uint32_t y = z; y != stop; ++y) stg_v4(out + (size_t)(y - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
+        z = stop;
+      }
+      return;
+    }
+    for (uint32_t z = k0; z != k1; ++z) stg_v4(out + (size_t)(z - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
   };
   if (n == 0) {
     if (chunk_local == 0) zero_rows(key_base, key_base + (uint32_t)a.bags_total);
@@ -759,8 +779,24 @@ extern "C" int recemb_peer_plan(const recemb_peer_group* group, const recemb_pee
 }
 
 
+static int peer_pool_push_impl(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
+                               int dtype, int64_t bags_per_table, int device, recemb_stream_t stream);
+
 extern "C" int recemb_peer_pool_push(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
                                      int dtype, int device, recemb_stream_t stream) {
+  return peer_pool_push_impl(group, arena, dim, dtype, 0, device, stream);
+}
+
+extern "C" int recemb_peer_pool_push_tablewise(const recemb_peer_group* group, const recemb_peer_arena* arena,
+                                               int32_t dim, int dtype, int64_t bags_per_table, int device,
+                                               recemb_stream_t stream) {
+  RECEMB_CHECK_ARG(arena && bags_per_table >= 1 && arena->bags_total % bags_per_table == 0,
+                   "bags_total is not a multiple of bags_per_table");
+  return peer_pool_push_impl(group, arena, dim, dtype, bags_per_table, device, stream);
+}
+
+static int peer_pool_push_impl(const recemb_peer_group* group, const recemb_peer_arena* arena, int32_t dim,
+                               int dtype, int64_t bags_per_table, int device, recemb_stream_t stream) {
   RECEMB_CHECK_ARG(group && arena && group->world >= 1 && group->world <= RECEMB_MAX_PEERS && group->rank >= 0 &&
                        group->rank < group->world,
                    "bad peer group");
@@ -784,6 +820,7 @@ extern "C" int recemb_peer_pool_push(const recemb_peer_group* group, const recem
   a.chunks_per_sender = (int32_t)((arena->cap + kPeChunk - 1) / kPeChunk);
   a.table = group->table[group->rank];
   a.vecs = (int32_t)(row_bytes / 16);
+  a.bags_per_table = bags_per_table;
   for (int i = 0; i < RECEMB_MAX_PEERS; ++i) a.parts[i] = nullptr;
   for (int sd = 0; sd < group->world; ++sd) {
     RECEMB_CHECK_ARG(group->arena[sd], "peer arena %d not mapped", sd);

@@ -395,9 +395,10 @@ def peer_pool_fwd(group, ids: torch.Tensor, *, num_rows: int, dim: int, dtype: t
 
 def peer_bucket_push(group, ids: torch.Tensor, *, num_rows: int, lengths: Optional[torch.Tensor] = None,
                      last_n: int = 0, zero_pad: bool = False, pad_id: int = 0, bags_per_table: int = 0,
-                     num_tables: int = 0, hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0) -> None:
+                     num_tables: int = 0, hash_mode: int = N.HASH_FLOORMOD, hash_arg: int = 0,
+                     tablewise: bool = False) -> None:
     """Sender side of the peer backward: my (local row, gradient row) entries land in the owners'
-    inboxes, my bucket sizes in their count slots."""
+    inboxes, my bucket sizes in their count slots.  tablewise: table t lives whole on rank t % world."""
     ids = ids.contiguous()
     if lengths is not None:
         lengths = lengths.to(torch.int32).contiguous()
@@ -405,7 +406,7 @@ def peer_bucket_push(group, ids: torch.Tensor, *, num_rows: int, lengths: Option
     m, p = ids.shape
     lib = N.load()
     layout = N.Layout(ids_per_table=bags_per_table * p, num_tables=num_tables, shard_world=group.world,
-                      shard_rank=group.rank, flip_len=0)
+                      shard_rank=group.rank, flip_len=0, partition=int(tablewise))
     ws = torch.empty((int(lib.recemb_shard_bucket_workspace_bytes(m * p, group.world)),), dtype=torch.uint8,
                      device=ids.device)
     N.check(lib.recemb_peer_bucket_push(C.byref(group.struct), C.byref(group.layout), N.ptr(ids), m * p, layout,
@@ -447,9 +448,15 @@ def peer_rows_scatter_push(group, rows: torch.Tensor, dest: torch.Tensor) -> Non
             "recemb_peer_rows_scatter_push")
 
 
-def peer_pool_push(group, dim: int, dtype: torch.dtype) -> None:
+def peer_pool_push(group, dim: int, dtype: torch.dtype, tablewise_bags_per_table: int = 0) -> None:
     """Owner side of the push forward: pool the (sender, bag) runs of my inbox from my shard and
-    store every partial row into the sender's parts region over NVLink."""
+    store every partial row into the sender's parts region over NVLink.  tablewise_bags_per_table > 0:
+    table-wise partitioning (zero rows only for empty bags of the tables this rank owns)."""
+    if tablewise_bags_per_table:
+        N.check(N.load().recemb_peer_pool_push_tablewise(
+            C.byref(group.struct), C.byref(group.layout), dim, N.dtype_code(dtype), tablewise_bags_per_table,
+            group.device, N.stream_ptr(group.device)), "recemb_peer_pool_push_tablewise")
+        return
     N.check(N.load().recemb_peer_pool_push(C.byref(group.struct), C.byref(group.layout), dim, N.dtype_code(dtype),
                                            group.device, N.stream_ptr(group.device)), "recemb_peer_pool_push")
 
@@ -470,7 +477,8 @@ def peer_barrier(group, channel: int = 0) -> None:
 
 def peer_bwd_apply_fused(plan: "BackwardPlan", my_grad: torch.Tensor, *, group, table: torch.Tensor, update: int,
                          state1: Optional[torch.Tensor], hp, tables: int, bags_per_table: int, rows_per_table: int,
-                         push_ctas: int = 32, workspace: Optional[torch.Tensor] = None) -> None:
+                         push_ctas: int = 32, workspace: Optional[torch.Tensor] = None,
+                         tablewise: bool = False) -> None:
     """Sharded backward, sender and owner side in ONE level-0 launch: the first push_ctas CTAs store my pooled
     gradients into every rank's buffer table by table, the others reduce + update my rows, each chunk gated on
     the flags of the last table it touches (recemb_peer_bwd_apply_fused)."""
@@ -485,7 +493,8 @@ def peer_bwd_apply_fused(plan: "BackwardPlan", my_grad: torch.Tensor, *, group, 
     need = int(lib.recemb_bwd_apply_workspace_bytes(plan.n_slots, dim))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=table.device)
-    N.check(lib.recemb_peer_bwd_apply_fused(
+    fn = lib.recemb_peer_bwd_apply_fused_tablewise if tablewise else lib.recemb_peer_bwd_apply_fused
+    N.check(fn(
         C.byref(group.struct), C.byref(group.layout), N.ptr(plan.buf), plan.buf.numel(), N.ptr(my_grad), tables,
         bags_per_table, dim, N.dtype_code(table.dtype), update, N.ptr(table), table.shape[0], rows_per_table,
         N.ptr(state1), C.byref(hp), N.ptr(workspace), workspace.numel(), push_ctas, dev, N.stream_ptr(dev)),

@@ -918,3 +918,201 @@ class RowWiseShardedEmbedding(RowWiseShardedEmbeddingBag):
         self._ensure_peer_group(flat)
         out = _PeerSeqFn.apply(self.emb.grad_anchor(), flat, self)
         return out.view(shape + (self.emb_dim,))
+
+
+# ------------------------------------------------------------------ table-wise partitioning ----
+class _TableWiseFn(torch.autograd.Function):
+    """exchange over peer memory, tables partitioned whole: table t lives on rank t % W.
+
+      forward   main: bucket: every lookup of table t goes to rank t % W's inbox -> barrier -> the owner pools its
+                      (sender, bag) runs from its tables and STORES the pooled row (exactly one owner per bag: it IS
+                      the result) into the requester's parts[owner][bag] -> [join side] -> barrier -> pick
+                      parts[t % W][bags of table t]
+                side: (after the first barrier) unpack + sort of my inbox = the backward plan
+      backward  main: ONE launch: the first CTAs push the gradients of table t to rank t % W only (each gradient row
+                      crosses NVLink at most once), the others reduce + update my tables, gated per local table
+                      (other update kinds: all-gather push -> barrier -> update)"""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, lengths, module):
+        pg = module.peer_group()
+        pg.raise_on_status()
+        main = torch.cuda.current_stream(ids.device)
+        t, dim, dt = module.num_tables, module.emb_dim, module.emb.weight.dtype
+        b = ids.shape[0] // t
+        ops.peer_bucket_push(pg, ids, num_rows=module.num_embeddings, lengths=lengths, last_n=module.last_n,
+                             zero_pad=module.skip_pad, pad_id=module.pad_id, bags_per_table=b, num_tables=t,
+                             tablewise=True)
+        ops.peer_barrier(pg, channel=0)
+        ctx.plan, ctx.plan_ready, ctx.pg = None, None, pg
+        if ctx.needs_input_grad[0]:
+            side = module._side_stream(ids.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx.plan = ops.peer_plan(pg, module.emb.weight.shape[0], buf=module.__dict__.get("_tw_plan_buf"))
+                module._tw_plan_buf = ctx.plan.buf
+                ctx.plan_ready = torch.cuda.Event()
+                ctx.plan_ready.record(side)
+        ops.peer_pool_push(pg, dim, dt, tablewise_bags_per_table=b)
+        if ctx.plan_ready is not None:
+            main.wait_event(ctx.plan_ready)       # peers may refill my inbox after the next barrier
+        ops.peer_barrier(pg, channel=0)
+        parts = pg.parts_view(dim, dt).view(pg.world, t, b, dim)
+        out = parts[module._owner_of_table.to(ids.device), torch.arange(t, device=ids.device)].reshape(t * b, dim)
+        scale = None
+        if module.mode == "mean":
+            scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad, module.pad_id).clamp_(min=1).float()
+            out = (out.float() * scale.unsqueeze(1)).to(dt)
+        ctx.module, ctx.b = module, b
+        ctx.save_for_backward(scale)
+        module._peer_dirty = False
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (scale,) = ctx.saved_tensors
+        module, pg, b = ctx.module, ctx.pg, ctx.b
+        dt = module.emb.weight.dtype
+        g = grad_out.contiguous()
+        if scale is not None:
+            g = g * scale.unsqueeze(1).to(g.dtype)
+        if g.dtype != dt:
+            g = g.to(dt)
+        main = torch.cuda.current_stream(g.device)
+        if module._peer_dirty:
+            ops.peer_barrier(pg, channel=0)       # two backward passes without a forward in between
+        f = module.emb.fused
+        row_bytes = module.emb_dim * module.emb.weight.element_size()
+        fused_ok = (f is not None and not f.accumulate and f.kind in ("rowwise_adagrad", "sgd")
+                    and row_bytes in (256, 512) and module.fused_push is not False
+                    and (pg.world > 1 or module.fused_push == "force"))
+        if fused_ok:
+            main.wait_event(ctx.plan_ready)
+            module.emb.begin_update()
+            module.emb._apply_fused(ctx.plan, g, 1, None, None, 0.0, peer_push=dict(
+                group=pg, tables=module.num_tables, bags_per_table=b, rows_per_table=module.num_embeddings,
+                push_ctas=module.push_ctas, tablewise=True))
+            module.emb.end_update()
+            res = None
+        else:
+            ops.peer_allgather_push(pg, g, int(pg.layout.off_grads))
+            ops.peer_barrier(pg, channel=0)
+            main.wait_event(ctx.plan_ready)
+            res = module.emb.consume(ctx.plan, pg.grads_view(module.emb_dim, dt), slots_per_grad_row=1,
+                                     guard=pg.status_word())
+        ctx.plan = None
+        pg.snapshot_status()
+        module._peer_dirty = True
+        return res, None, None, None
+
+
+class TableWiseShardedEmbeddingBag(nn.Module):
+    """Pooled multi-hot lookup into T equal-shaped tables partitioned TABLE-wise over the ranks of one NVLink box:
+    table t lives whole on rank t % W (north_star item 4: "row-wise or table-wise sharding").  Peer-memory
+    exchange only (CUDA).  forward(ids [T, b, P] int64 of THIS rank's batch, lengths [T, b]) -> [T, b, D].
+
+    Against row-wise sharding of the same tables: every bag has ONE owner, so one pooled row per bag comes back
+    (instead of W partial rows) and every gradient row is pushed to one rank (instead of all W): (W-1)/W * b T R
+    bytes each way per GPU.  The price is balance: T must be a multiple of W for equal work, and one hot table
+    is one hot GPU.  `emb.weight` holds this rank's ceil((T - rank) / W) tables stacked; gather_full_weight() /
+    load_full_weight() translate to the unsharded [T, N, D] layout."""
+
+    def __init__(self, num_embeddings: int, emb_dim: int, num_tables: int, mode: str = "sum", *, last_n: int = 0,
+                 skip_pad: bool = False, pad_id: int = 0, group=None, comm: Optional[Collectives] = None,
+                 dtype: torch.dtype = torch.float32, device=None,
+                 fused_optimizer: Optional[FusedOptimizerConfig] = None):
+        super().__init__()
+        if mode not in ("sum", "mean"):
+            raise ValueError("mode must be 'sum' or 'mean'")
+        if comm is None:
+            comm = Collectives(group) if dist.is_available() and dist.is_initialized() else SingleProcess()
+        self.comm = comm
+        w, r = comm.world, comm.rank
+        if num_tables < w:
+            raise ValueError(f"table-wise partitioning needs at least one table per rank ({num_tables} tables, {w} ranks)")
+        self.num_embeddings, self.emb_dim, self.num_tables = int(num_embeddings), int(emb_dim), int(num_tables)
+        self.mode, self.last_n, self.skip_pad, self.pad_id = mode, int(last_n), skip_pad, pad_id
+        self.local_tables = (self.num_tables - r + w - 1) // w
+        self.emb = EmbeddingTable(self.local_tables * self.num_embeddings, emb_dim, dtype=dtype, device=device)
+        if fused_optimizer is not None:
+            self.emb.enable_fused_optimizer(fused_optimizer)
+        self._owner_of_table = torch.arange(self.num_tables) % w
+        env = os.environ.get("RECEMB_PEER_FUSED_PUSH", "1")
+        self.fused_push = False if env == "0" else ("force" if env == "force" else True)
+        self.push_ctas = int(os.environ.get("RECEMB_PEER_PUSH_CTAS", "16"))
+        self._peer: Optional[PeerGroup] = None
+        self._peer_key = None
+        self._peer_dirty = True
+
+    def _side_stream(self, device):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
+    def peer_group(self) -> PeerGroup:
+        if self._peer is None:
+            raise N.NativeError("peer exchange: call forward first (the group is built for its batch shape)")
+        return self._peer
+
+    def _ensure_peer_group(self, ids: torch.Tensor) -> None:
+        w = self.emb.weight
+        key = (w.data_ptr(), tuple(ids.shape))
+        if self._peer is not None and self._peer_key == key:
+            return
+        self.close_peer()
+        t, world = self.num_tables, self.comm.world
+        b, p = ids.shape[0] // t, ids.shape[1]
+        cap = -(-t // world) * b * p            # exact: a sender has that many slots for an owner at most
+        cap = max(2, cap + (cap & 1))
+        if world == 1:
+            layout = arena_layout(1, cap, ids.shape[0], self.emb_dim, w.dtype)
+            self._peer = PeerGroup.local(1, 0, [PeerGroup.new_arena(layout, w.device)], [w.detach()], layout)
+        else:
+            self._peer = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group)
+        self._peer_key = key
+        self._peer_dirty = True
+
+    def close_peer(self) -> None:
+        """Collective: unmap the peers' memory (before this rank's tables / arena may be freed)."""
+        if self._peer is None:
+            return
+        torch.cuda.synchronize(self.emb.weight.device)
+        if self.comm.world > 1:
+            dist.barrier(group=self.comm.group)
+        self._peer.close()
+        if self.comm.world > 1:
+            dist.barrier(group=self.comm.group)
+        self._peer, self._peer_key = None, None
+
+    def forward(self, ids: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if ids.dtype != torch.int64 or ids.dim() != 3 or ids.shape[0] != self.num_tables:
+            raise N.NativeError(f"ids must be int64 [num_tables = {self.num_tables}, batch, bag_size]")
+        t, b, p = ids.shape
+        flat = ids.contiguous().view(t * b, p)
+        self._ensure_peer_group(flat)
+        out = _TableWiseFn.apply(self.emb.grad_anchor(), flat,
+                                 None if lengths is None else lengths.contiguous().view(t * b), self)
+        return out.view(t, b, self.emb_dim)
+
+    # ---------------------------------------------------------- checkpoints ----
+    @torch.no_grad()
+    def load_full_weight(self, full: torch.Tensor) -> None:
+        """Take this rank's tables (t % W == rank) out of a global [T, N, D] tensor."""
+        full = full.view(self.num_tables, self.num_embeddings, self.emb_dim)
+        mine = full[self.comm.rank::self.comm.world].reshape(-1, self.emb_dim)
+        self.emb.weight.copy_(mine.to(self.emb.weight.device, self.emb.weight.dtype))
+        self._peer_dirty = True
+
+    @torch.no_grad()
+    def gather_full_weight(self) -> torch.Tensor:
+        """Global [T, N, D] under the unsharded module's layout (collective)."""
+        w, t, n = self.comm.world, self.num_tables, self.num_embeddings
+        lt_max = -(-t // w)
+        pad = torch.zeros((lt_max * n, self.emb_dim), dtype=self.emb.weight.dtype, device=self.emb.weight.device)
+        pad[: self.local_tables * n] = self.emb.weight.detach()
+        shards = self.comm.all_gather(pad).view(w, lt_max, n, self.emb_dim)
+        full = torch.empty((t, n, self.emb_dim), dtype=pad.dtype, device=pad.device)
+        for s in range(w):
+            cnt = (t - s + w - 1) // w
+            full[s::w] = shards[s, :cnt]
+        return full

@@ -515,3 +515,100 @@ def test_fused_push_update_equals_push_barrier_update(kind, forward):
     for m in mods:
         m.peer_group().raise_on_status(synchronize=True)
         m.close_peer()
+
+
+# ------------------------------------------------------------ table-wise partitioning ----
+def make_tablewise_groups(world, full, cap, bags_total, dtype):
+    """full [T, N, D]: rank r holds tables r, r + W, ... stacked."""
+    t, n_rows, dim = full.shape
+    shards = [full[r::world].reshape(-1, dim).contiguous().to(dtype).to(DEV) for r in range(world)]
+    layout = arena_layout(world, cap, bags_total, dim, dtype)
+    arenas = [PeerGroup.new_arena(layout, DEV) for _ in range(world)]
+    return shards, arenas, [PeerGroup.local(world, r, arenas, shards, layout) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,tables", [(1, 3), (2, 5), (4, 8), (8, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tablewise_exchange_emulated_ranks(world, tables, dtype):
+    """Table t lives whole on rank t % W: every sender routes the lookups of table t to that rank, the owner
+    pools them from its local table t / W and stores the pooled row (zero rows for its empty bags only) into
+    the sender's parts[owner]; the sender's result is parts[t % W][bags of t] -- bit-identical to the unsharded
+    bag in fp32.  Backward: each owner's plan over its inbox + all-gathered gradients == the unsharded
+    scatter-add restricted to its tables."""
+    n_rows, dim, b, p = 20011, 64, 41, 20
+    m = tables * b
+    torch.manual_seed(3 * world + tables)
+    full = torch.randn(tables, n_rows, dim).to(dtype)
+    cap = -(-tables // world) * b * p
+    shards, arenas, groups = make_tablewise_groups(world, full.float(), cap, m, dtype)
+    stacked = full.reshape(-1, dim).contiguous().to(DEV)
+    inputs = []
+    for r in range(world):
+        ids = seeded_ids(m * p, 500 + r, (m, p))
+        lengths = torch.randint(0, p + 1, (m,), generator=torch.Generator().manual_seed(60 + r))
+        if r == 0:
+            lengths[: b] = 0                              # a whole table of empty bags
+        groups[r].parts_view(dim, dtype).fill_(float("nan"))
+        ops.peer_bucket_push(groups[r], ids.to(DEV), num_rows=n_rows, lengths=lengths.to(DEV), bags_per_table=b,
+                             num_tables=tables, tablewise=True)
+        inputs.append((ids, lengths))
+    for o in range(world):
+        ops.peer_pool_push(groups[o], dim, dtype, tablewise_bags_per_table=b)
+    owner = torch.arange(tables) % world
+    dense_want = torch.zeros(tables * n_rows, dim)
+    for r, (ids, lengths) in enumerate(inputs):
+        parts = groups[r].parts_view(dim, dtype).view(world, tables, b, dim)
+        got = parts[owner.to(DEV), torch.arange(tables, device=DEV)].reshape(m, dim)
+        want = ops.pool_fwd(stacked, ids.to(DEV), lengths=lengths.to(DEV), num_rows=n_rows, bags_per_table=b,
+                            num_tables=tables)
+        assert torch.equal(got, want)                     # one owner per bag: the unsharded arithmetic
+        grad = torch.randn(m, dim, generator=torch.Generator().manual_seed(r)).to(dtype)
+        ops.peer_allgather_push(groups[r], grad.to(DEV), int(groups[r].layout.off_grads))
+        rows = O.row_index(ids, n_rows, 0) + (torch.arange(m) // b).unsqueeze(1) * n_rows
+        use = torch.arange(p).unsqueeze(0) < lengths.unsqueeze(1)
+        dense_want.index_add_(0, rows[use], grad.float().unsqueeze(1).expand(-1, p, -1)[use])
+    for o in range(world):
+        plan = ops.peer_plan(groups[o], shards[o].shape[0])
+        dense = torch.zeros(shards[o].shape, dtype=torch.float32, device=DEV)
+        ops.bwd_apply(plan, groups[o].grads_view(dim, dtype).float(), table=dense, update=N.UPD_DENSE_GRAD,
+                      slots_per_grad_row=1)
+        want_o = dense_want.view(tables, n_rows, dim)[o::world].reshape(-1, dim)
+        torch.testing.assert_close(dense.cpu(), want_o, rtol=1e-5, atol=1e-4 if dtype == torch.float32 else 5e-2)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+@pytest.mark.parametrize("fused", [None, "sgd", "rowwise_adagrad"])
+def test_tablewise_module_single_rank(mode, fused):
+    """TableWiseShardedEmbeddingBag on one rank (owns every table) == the unsharded pooled collection; the fused
+    push + update launch (forced on) == push -> barrier -> update."""
+    import recommendations_b200 as R
+    from recommendations_b200.sharded import TableWiseShardedEmbeddingBag
+    n_rows, dim, b, p, tables = 9973, 128, 65, 20, 3
+    ids = seeded_ids(tables * b * p, 77, (tables, b, p)).to(DEV)
+    lengths = torch.randint(0, p + 1, (tables, b), generator=torch.Generator().manual_seed(9)).to(DEV)
+    opt = None if fused is None else R.FusedOptimizerConfig(kind=fused, lr=0.05)
+    tw = TableWiseShardedEmbeddingBag(n_rows, dim, tables, mode=mode, dtype=torch.bfloat16, device=DEV, fused_optimizer=opt)
+    ref = R.EmbeddingCollection(tables, n_rows, dim, kind="pooled", mode=mode, dtype=torch.bfloat16, device=DEV,
+                                fused_optimizer=opt)
+    tw.load_full_weight(ref.table.weight.detach().view(tables, n_rows, dim))
+    if fused is not None:
+        tw.fused_push = "force"
+    go = torch.randn(tables, b, dim, device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):
+        out, want = tw(ids, lengths), ref(ids, lengths)
+        torch.testing.assert_close(out.float(), want.float(), rtol=1e-2, atol=1e-2)
+        if mode == "sum":
+            assert torch.equal(out, want)
+        out.backward(go)
+        want.backward(go)
+        if fused is None:
+            gw = torch.cat([m.weight.grad for m in ref.members()])
+            torch.testing.assert_close(tw.emb.weight.grad.float(), gw.float(), rtol=1e-2, atol=1e-2)
+            tw.emb.weight.grad = None
+            for m in ref.members():
+                m.weight.grad = None
+        else:
+            torch.testing.assert_close(tw.emb.weight.float(), ref.table.weight.float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(tw.gather_full_weight().view(-1, dim).float(), tw.emb.weight.float())
+    tw.peer_group().raise_on_status(synchronize=True)
+    tw.close_peer()

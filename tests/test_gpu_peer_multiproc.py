@@ -119,6 +119,38 @@ def _worker(rank, world, port, peer_forward, result):
             sm.peer_group().raise_on_status(synchronize=True)
             sm.close_peer()
             assert not peer._OPENED
+        if peer_forward == "push":
+            # table-wise partitioning (table t whole on rank t % W), fused push + update: SGD with lr 1 leaves
+            # w0 - (gradient of the GLOBAL batch) on the tables this rank owns
+            import recommendations_b200 as R
+            from recommendations_b200.sharded import TableWiseShardedEmbeddingBag
+            full_bf = torch.randn(T, N_ROWS, 128, generator=torch.Generator().manual_seed(11)).bfloat16()
+            tw = TableWiseShardedEmbeddingBag(N_ROWS, 128, T, device=dev, dtype=torch.bfloat16,
+                                              fused_optimizer=R.FusedOptimizerConfig(kind="sgd", lr=1.0))
+            tw.load_full_weight(full_bf)
+            w0 = tw.emb.weight.detach().float().cpu().clone()
+            go_tw = torch.randn(T, B, 128, generator=torch.Generator().manual_seed(40 + rank)).bfloat16()
+            out_t = tw(ids.to(dev), lengths.to(dev))
+            for t in range(T):
+                want = O.pooled_bag(full_bf[t], ids[t], lengths=lengths[t])
+                assert torch.equal(out_t[t].cpu(), want), "table-wise forward must be bit-identical to unsharded"
+            out_t.backward(go_tw.to(dev))
+            torch.cuda.synchronize()
+            gtw = torch.zeros(T, N_ROWS, 128)
+            for r in range(world):
+                ids_r, len_r, _ = _ids(r)
+                go_r = torch.randn(T, B, 128, generator=torch.Generator().manual_seed(40 + r)).bfloat16().float()
+                for t in range(T):
+                    rows = O.row_index(ids_r[t], N_ROWS, 0)
+                    use = torch.arange(P).unsqueeze(0) < len_r[t].unsqueeze(1)
+                    gtw[t].index_add_(0, rows[use], go_r[t].unsqueeze(1).expand(-1, P, -1)[use])
+            torch.testing.assert_close(tw.emb.weight.float().cpu(), w0 - gtw[rank::world].reshape(-1, 128),
+                                       rtol=2e-2, atol=2e-2)
+            full_back = tw.gather_full_weight()
+            assert full_back.shape == (T, N_ROWS, 128)
+            tw.peer_group().raise_on_status(synchronize=True)
+            tw.close_peer()
+            assert not peer._OPENED
         result[rank] = 1
     finally:
         dist.destroy_process_group()
@@ -128,6 +160,9 @@ def _worker(rank, world, port, peer_forward, result):
 @pytest.mark.parametrize("peer_forward", ["pull", "push"])
 def test_two_processes_one_gpu_peer_exchange(peer_forward):
     world = 2
-    result = mp.Manager().dict()
+    # the manager's server process must be SPAWNED: a fork of this process inherits the CUDA tensors / events
+    # of the tests that ran before, and the first garbage collection over there dies in cudaEventDestroy
+    # ("CUDA error: initialization error" in a forked child)
+    result = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), peer_forward, result), nprocs=world, join=True)
     assert dict(result) == {0: 1, 1: 1}
