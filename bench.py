@@ -188,6 +188,9 @@ def bind_to_gpu_numa(local_rank: int):
         return None
 
 
+T_CFG5 = 8   # tables of the sharded config (scripts/bench_sharded.py)
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -369,6 +372,15 @@ def run_b200(args):
                     sharded["w1_anchor_ms_per_step"] = anchor["ms_per_step"]
                     sharded["efficiency_vs_w1"] = anchor["ms_per_step"] / sharded["ms_per_step"]
                 dist.barrier()
+                if T_CFG5 % world == 0:
+                    # the same tables partitioned TABLE-wise (table t whole on rank t % W): one pooled row per bag
+                    # back, every gradient row pushed to one rank -- north_star item 4 names both partitionings
+                    tw = bench_sharded.run_cfg5(world, rank, dev, args.steps, args.warmup, exchange="peer",
+                                                graph=True, partition="table")
+                    if rank == 0:
+                        tw["efficiency_vs_w1"] = sharded["w1_anchor_ms_per_step"] / tw["ms_per_step"]
+                    sharded["tablewise"] = {k: tw[k] for k in ("value", "ms_per_step", "nvlink", "config", "gpu_launches")
+                                            } | ({"efficiency_vs_w1": tw.get("efficiency_vs_w1")} if rank == 0 else {})
         except Exception as exc:  # the headline line must survive a failure of the extra run
             sharded = {"error": f"{type(exc).__name__}: {exc}"}
 

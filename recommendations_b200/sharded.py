@@ -958,7 +958,7 @@ class _TableWiseFn(torch.autograd.Function):
             main.wait_event(ctx.plan_ready)       # peers may refill my inbox after the next barrier
         ops.peer_barrier(pg, channel=0)
         parts = pg.parts_view(dim, dt).view(pg.world, t, b, dim)
-        out = parts[module._owner_of_table.to(ids.device), torch.arange(t, device=ids.device)].reshape(t * b, dim)
+        out = parts[module._owner_idx, module._table_idx].reshape(t * b, dim)   # table t comes from rank t % W
         scale = None
         if module.mode == "mean":
             scale = 1.0 / pooled_counts(ids, lengths, module.last_n, module.skip_pad, module.pad_id).clamp_(min=1).float()
@@ -1071,6 +1071,9 @@ class TableWiseShardedEmbeddingBag(nn.Module):
             self._peer = PeerGroup.connect(w.detach(), cap=cap, bags_total=ids.shape[0], group=self.comm.group)
         self._peer_key = key
         self._peer_dirty = True
+        # device-resident index tensors of the final pick (built here, outside any CUDA-graph capture)
+        self._owner_idx = self._owner_of_table.to(w.device)
+        self._table_idx = torch.arange(t, device=w.device)
 
     def close_peer(self) -> None:
         """Collective: unmap the peers' memory (before this rank's tables / arena may be freed)."""

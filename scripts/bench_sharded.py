@@ -49,7 +49,7 @@ def check(world, rank, dev, exchange=None):
 
 
 def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=None, graph=False,
-             full_check=False, comm=None):
+             full_check=False, comm=None, partition="row"):
     """Times the cfg 5 step on an already initialised process group; returns the result dict
     (every rank computes it, rank 0 prints it)."""
     class A:
@@ -58,9 +58,18 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
     args.steps, args.warmup, args.rows_per_gpu = steps, warmup, rows_per_gpu
     n_rows = args.rows_per_gpu * world
     # comm: sharded.SingleProcess() runs the W = 1 anchor on one rank of a larger job (world = 1 here)
-    mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange=exchange,
-                                     peer_forward=PEER_FORWARD, comm=comm,
-                                     fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
+    if partition == "table":
+        # the same 8 tables of 25 M x W rows, partitioned whole: table t on rank t % W (needs T % W == 0 for balance)
+        from recommendations_b200.sharded import TableWiseShardedEmbeddingBag
+        mod = TableWiseShardedEmbeddingBag(n_rows, DIM, T, dtype=torch.bfloat16, device=dev, comm=comm,
+                                           fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
+        mod.exchange, mod.peer_forward = "peer", "push"
+        mod._pipelined = lambda: False
+        mod._fused_push_ok = lambda g: world > 1
+    else:
+        mod = RowWiseShardedEmbeddingBag(n_rows, DIM, num_tables=T, dtype=torch.bfloat16, device=dev, exchange=exchange,
+                                         peer_forward=PEER_FORWARD, comm=comm,
+                                         fused_optimizer=R.FusedOptimizerConfig(kind="rowwise_adagrad", lr=0.05))
     ids_host = ids_for(rank, T, B_LOCAL, P).pin_memory()
     ids = ids_host.to(dev)
     grad = torch.randn(T, B_LOCAL, DIM, device=dev, dtype=torch.bfloat16)
@@ -75,7 +84,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             dist.barrier()
         torch.cuda.synchronize()
 
-    if full_check and mod.exchange == "peer":
+    if full_check and mod.exchange == "peer" and partition == "row":
         # full size (51.2 GB per GPU), no unsharded copy possible: self-consistency instead.
         # (1) the forward is deterministic; (2) the pull forward (rows loaded from their owners, pooled
         # in slot order: the unsharded arithmetic) and the push forward (owner-side partial pools
@@ -135,6 +144,9 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
         if mod.peer_forward == "push":
             # entries in + one partial row per (bag, remote owner) pair (zero rows included) + gathered gradients
             nv_in = int(remote * T * B_LOCAL * P * 8 + 2 * (world - 1) * T * B_LOCAL * row_bytes)
+        if partition == "table":
+            # entries in + one pooled row per bag of a remote owner back + its gradient row once
+            nv_in = int(remote * T * B_LOCAL * (P * 8 + 2 * row_bytes))
     t_step = ms / args.steps * 1e-3
     mod_exchange = mod.exchange
     mod_peer_forward = mod.peer_forward
@@ -167,7 +179,7 @@ def run_cfg5(world, rank, dev, steps, warmup, rows_per_gpu=25_000_000, exchange=
             "metric": "embedding_lookups_per_sec_fwd_bwd", "value": lookups / t_step, "unit": "lookups/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 row-wise sharded over {world} GPU(s), "
+            "config": {"workload": f"cfg5: {T} tables x {n_rows} x {DIM} bf16 {partition}-wise sharded over {world} GPU(s), "
                                    f"b={B_LOCAL}/GPU, P={P}, pooled sum, fused row-wise Adagrad",
                        "table_bytes_per_gpu": T * args.rows_per_gpu * row_bytes, "exchange": mod_exchange,
                        "peer_forward": mod_peer_forward if mod_exchange == "peer" else None,
@@ -250,6 +262,7 @@ def main():
     ap.add_argument("--phase-bench", action="store_true", help="time the phases of the peer exchange one by one")
     ap.add_argument("--peer-forward", default=None, choices=["pull", "push"])
     ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (peer exchange only)")
+    ap.add_argument("--partition", default="row", choices=["row", "table"])
     args = ap.parse_args()
     global PEER_FORWARD
     PEER_FORWARD = args.peer_forward
@@ -266,7 +279,7 @@ def main():
         res = {"phase_ms": phase_bench(world, rank, dev, args.rows_per_gpu), "n_gpus": world}
     else:
         res = run_cfg5(world, rank, dev, args.steps, args.warmup, args.rows_per_gpu, args.exchange, args.graph,
-                       full_check=args.check)
+                       full_check=args.check, partition=args.partition)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
