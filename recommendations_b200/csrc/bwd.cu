@@ -982,15 +982,16 @@ static void launch_kernel(const SegArgs& a_in, cudaStream_t s) {
     // Wave fit: every group does the same amount of work, so a grid of 2.2 waves takes as long
     // as 3.  Stretch the chunk (never below kChunk0: the workspace is sized for that) until the
     // chunks fill a whole number of waves of resident groups.
-    static int occ = 0;  // per instantiation
+    static int occ_of[64];  // per instantiation (the kernel is a template argument) and per device
     static const int fit = env_flag("RECEMB_SEG_FIT", 1);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_of[(dev >= 0 && dev < 64) ? dev : 0];
     if (occ == 0) {
       int v = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBwdThreads, 0) != cudaSuccess || v < 1) v = 1;
       occ = v;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
     const int64_t resident = (int64_t)occ * sm_count(dev) * groups;
     const int64_t chunks64 = ((int64_t)a.n + CH - 1) / CH;
     if (fit && chunks64 > resident) {

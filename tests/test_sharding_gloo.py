@@ -155,3 +155,40 @@ def test_local_rows_partition_is_exact():
     for n in (1, 7, 8, 9, 1000, 200_000_000):
         for w in (1, 2, 4, 8):
             assert sum(local_rows_of(n, w, r) for r in range(w)) == n
+
+
+def _tablewise_worker(rank, world, port, result):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recommendations_b200.sharded import TableWiseShardedEmbeddingBag
+        t, n, d = 5, 37, 8
+        full = torch.arange(t * n * d, dtype=torch.float32).view(t, n, d)
+        mod = TableWiseShardedEmbeddingBag(n, d, t)
+        assert mod.local_tables == (t - rank + world - 1) // world
+        assert mod.emb.weight.shape == (mod.local_tables * n, d)
+        mod.load_full_weight(full)
+        # rank r holds tables r, r + W, ... whole, stacked in that order
+        assert torch.equal(mod.emb.weight.detach().view(mod.local_tables, n, d), full[rank::world])
+        assert torch.equal(mod.gather_full_weight(), full)
+        assert mod._owner_of_table.tolist() == [i % world for i in range(t)]
+        result[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tablewise_partition_host_logic_gloo_world2():
+    """Table-wise partitioning, host side on CPU / gloo: which tables a rank holds, the checkpoint round trip
+    global [T, N, D] -> owned tables -> global (the exchange itself is peer memory: tests/test_gpu_peer*.py)."""
+    world = 2
+    result = mp.Manager().dict()
+    mp.spawn(_tablewise_worker, args=(world, _free_port(), result), nprocs=world, join=True)
+    assert dict(result) == {0: 1, 1: 1}
+    with pytest.raises(ValueError):
+        from recommendations_b200.sharded import TableWiseShardedEmbeddingBag, SingleProcess
+
+        class _Four(SingleProcess):
+            def __init__(self):
+                super().__init__()
+                self.world = 4
+        TableWiseShardedEmbeddingBag(10, 8, 3, comm=_Four())
