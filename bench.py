@@ -347,7 +347,7 @@ def run_b200(args):
         try:
             sys.path.insert(0, str(ROOT / "scripts"))
             import bench_configs
-            configs = bench_configs.run(["cfg2plan", "kshift", "cfg3", "cfg4"], quiet=True)
+            configs = bench_configs.run(["cfg2plan", "kshift", "cfg3", "cfg4", "frontend"], quiet=True)
         except Exception as exc:
             configs = {"error": f"{type(exc).__name__}: {exc}"}
 

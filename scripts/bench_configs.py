@@ -192,7 +192,46 @@ def cfg2_plan():
     report("cfg2 plan alone (key kernel + library radix sort (cub onesweep); RECEMB_PLAN_SORT=own: hand-written 2 x 12-bit LSD)", ms, t * n * 8 * 2, t * n)
 
 
-RUNNERS = {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4, "cfg2plan": cfg2_plan}
+def front_end():
+    """The sequence front end at the cfg 2 shape (B 8192 x L 200, D 64 fp32): QueryTower's trim decided on the
+    device + windowed lookup, and QueryTower's input sum as one kernel vs the chain of torch ops it replaces."""
+    import recommendations_b200 as R
+    b, l, dim, n_rows = 8192, 200, 64, 1_000_000
+    g = torch.Generator(device=DEV).manual_seed(77)
+    ids = torch.randint(1, 2 ** 62, (b, l), generator=g, device=DEV, dtype=torch.int64)
+    valid = torch.randint(1, 161, (b,), generator=g, device=DEV)          # histories of 1..160 events, right-padded
+    valid[0] = 160
+    ids[torch.arange(l, device=DEV).unsqueeze(0) >= valid.unsqueeze(1)] = 0
+    w = torch.randn(n_rows, dim, device=DEV)
+    r = dim * 4
+    ms_win = timeit(lambda: R.SequenceWindow.from_ids(ids, export_span=8))
+    report("front end: sequence window (trim rule of query_tower.py:73-79 on ids == 0), [8192, 200] ids", ms_win, b * l * 8)
+    win = R.SequenceWindow.from_ids(ids, export_span=8)
+    keep = win.keep
+    out = torch.empty(b * l, dim, device=DEV)
+    ms_full = timeit(lambda: ops.gather_fwd(w, ids, out=out, zero_pad=True, pad_id=0, flip_len=l))
+    ms_w = timeit(lambda: ops.gather_fwd(w, ids, out=out, zero_pad=True, pad_id=0, flip_len=l, window=win))
+    report(f"front end: windowed gather + flip + pad mask, keep {keep} of {l} columns (full lookup: {ms_full:.4f} ms)",
+           ms_w, b * l * 8 + b * keep * 2 * r, b * keep, ms_full_lookup=round(ms_full, 4), keep=keep)
+    mods = (R.FlatEmbedding(4, dim, device=DEV), R.PatternFromTimelocal(3600, 24, dim, device=DEV),
+            R.PatternFromTimelocal(3600, 168, dim, device=DEV), R.PatternFromTimelocal(86400, 7, dim, device=DEV))
+    base = torch.randn(b, l, dim, device=DEV)
+    labels = torch.randint(0, 4, (b, l), generator=g, device=DEV)
+    ts = torch.randint(1_600_000_000, 1_700_000_000, (b, l), generator=g, device=DEV)
+    mask = ids == 0
+    pad = torch.randn(1, 1, dim, device=DEV)
+    with torch.no_grad():
+        fused = lambda: R.fused_lookup_sum(base, [(mods[0], labels), (mods[1], ts), (mods[2], ts), (mods[3], ts)],
+                                           mask=mask, masked_row=pad)
+        chain = lambda: torch.where(mask.unsqueeze(-1), pad.expand(b, l, -1),
+                                    base + mods[0](labels) + mods[1](ts) + mods[2](ts) + mods[3](ts))
+        assert torch.equal(fused(), chain())
+        ms_f, ms_c = timeit(fused), timeit(chain)
+    report("front end: QueryTower input sum (4 tiny-table lookups + dense term + pad select) as one kernel", ms_f,
+           b * l * (2 * r + 16 + 1), b * l * 4, ms_chain_of_lookups_and_adds=round(ms_c, 4))
+
+
+RUNNERS = {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4, "cfg2plan": cfg2_plan, "frontend": front_end}
 
 
 def run(which, quiet=True):
