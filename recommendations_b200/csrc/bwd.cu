@@ -259,14 +259,15 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
     s_dst[threadIdx.x] = (uint4*)(g.arena[threadIdx.x] + g.off_grads) + (int64_t)g.rank * g.sender_vecs;
   __syncthreads();
   uint32_t* done = (uint32_t*)(mine + g.off_gate + kGateOffDone);
-  const int64_t stride = (int64_t)g.push_ctas * kBwdThreads * 4;
-  for (int t = 0; t < g.tables; ++t) {
+  // one table, copied by CTAs `sub` of `cnt`, then signalled
+  auto push_table = [&](int t, int sub, int cnt) {
     const uint4* src = g.src + (int64_t)t * g.vecs_per_table;
     const int64_t dst0 = (int64_t)t * g.vecs_per_table;
     // table-wise partitioning: table t has ONE owner, t % world -- its gradients cross NVLink once
     const int q_lo = g.partition ? ((t % g.world) - g.rank + g.world - 1) % g.world + 1 : 1;
     const int q_hi = g.partition ? q_lo : g.world;
-    for (int64_t i0 = (int64_t)blockIdx.x * kBwdThreads * 4 + threadIdx.x; i0 < g.vecs_per_table && !(g.debug & 2);
+    const int64_t stride = (int64_t)cnt * kBwdThreads * 4;
+    for (int64_t i0 = (int64_t)sub * kBwdThreads * 4 + threadIdx.x; i0 < g.vecs_per_table && !(g.debug & 2);
          i0 += stride) {
       uint4 v[4];
 #pragma unroll
@@ -286,21 +287,19 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
       }
     }
     // ONE system-scope fence per CTA and table, by one thread after the CTA barrier (the barrier orders the
-    // other threads' stores before it): a membar.sys costs microseconds on a busy GPU -- with one per thread
-    // plus one by the last CTA, signalling 8 tables took 0.13 ms and the reduction sat waiting for it.  Only
-    // warp 0 signals; the other warps go straight on to the next table.
+    // other threads' stores before it).  Only warp 0 signals; the other warps go straight on to the next table.
     __syncthreads();
     if (threadIdx.x < 32) {
       int last = 0;
       if (threadIdx.x == 0) {
         asm volatile("fence.acq_rel.sys;" ::: "memory");
-        // wraps back to 0 with the last pusher CTA of the step: nothing to reset
-        last = atomicInc(done + t, (unsigned)g.push_ctas - 1u) == (unsigned)g.push_ctas - 1u;
+        // wraps back to 0 with the last pusher CTA of the table: nothing to reset
+        last = atomicInc(done + t, (unsigned)cnt - 1u) == (unsigned)cnt - 1u;
       }
       last = __shfl_sync(0xffffffffu, last, 0);
-      // one more sender's table t has landed at rank threadIdx.x: its arrival count of table t goes up by one
-      // (remote atomic over NVLink); the count only ever grows, step s is complete at s * world.  Every
-      // pusher CTA fenced before its increment of `done`, so all of the table is visible system-wide here.
+      // one more sender's table t has landed: its arrival count goes up by one on the ranks that wait for it
+      // (remote atomic over NVLink); the count only ever grows, step s is complete at s * world.  Every pusher
+      // CTA fenced before its increment of `done`, so all of the table is visible system-wide here.
       if (g.partition) {  // only the owner waits for table t, as its local table t / world
         if (last && (int)threadIdx.x == t % g.world)
           atomicAdd_system((unsigned long long*)(g.arena[threadIdx.x] + g.off_gate + kGateOffFlags) + t / g.world, 1ull);
@@ -308,6 +307,14 @@ __device__ __forceinline__ void gate_push_role(const PeerGate& g) {
         atomicAdd_system((unsigned long long*)(g.arena[threadIdx.x] + g.off_gate + kGateOffFlags) + t, 1ull);
       }
     }
+  };
+  if (g.partition && g.push_ctas % g.tables == 0) {
+    // table-wise: every owner waits for exactly its own tables from everybody -- push the tables side by side
+    // (CTA c copies table c % T) so that no owner sits behind the other owners' tables
+    push_table((int)blockIdx.x % g.tables, (int)blockIdx.x / g.tables, g.push_ctas / g.tables);
+  } else {
+    // row-wise: the reduction consumes the tables in order -- push them one after the other, all CTAs on each
+    for (int t = 0; t < g.tables; ++t) push_table(t, (int)blockIdx.x, g.push_ctas);
   }
 }
 
@@ -1415,6 +1422,7 @@ static int peer_bwd_fused_impl(const recemb_peer_group* group, const recemb_peer
                          (update == RECEMB_UPD_ROWWISE_ADAGRAD || update == RECEMB_UPD_SGD) &&
                          env_flag("RECEMB_SEG_PRE", 1) != 0,
                      "fused push: rows of 256 / 512 bytes with row-wise Adagrad or SGD only");
+  if (partition && push_ctas % tables != 0) push_ctas = (push_ctas / tables + 1) * tables;  // tables side by side
   PeerGate g;
   g.push_ctas = push_ctas;
   g.world = group->world;

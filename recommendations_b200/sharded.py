@@ -690,7 +690,9 @@ class RowWiseShardedEmbeddingBag(nn.Module):
     # ----------------------------------------------------------- peer group ----
     def peer_capacity(self, n_slots: int) -> int:
         w = self.comm.world
-        f = self.capacity_factor if self.capacity_factor is not None else (1.0 if w == 1 else 1.5)
+        f = self.capacity_factor
+        if f is None:   # RECEMB_PEER_CAPACITY: process-wide default (tuning runs); hashed ids spread binomially
+            f = 1.0 if w == 1 else float(os.environ.get("RECEMB_PEER_CAPACITY", "1.5"))
         cap = min(n_slots, int(n_slots / w * f) + 64)
         return max(2, cap + (cap & 1))
 
