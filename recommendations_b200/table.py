@@ -100,6 +100,11 @@ class EmbeddingTable(nn.Module):
         for name in ("opt_state1", "opt_state2"):
             if name in self._buffers:
                 del self._buffers[name]
+        if w.is_cuda:
+            # create the optimizer state now, on the stream the module is built on, not lazily inside the first
+            # backward (autograd thread): no fill kernel right in front of the first update, fixed addresses
+            # before any CUDA graph is captured
+            self._ensure_state()
         return self
 
     def _ensure_state(self) -> None:
