@@ -162,10 +162,12 @@ def run_reference(args):
 
 # --------------------------------------------------------------------- B200 arm ----
 def bind_to_gpu_numa(local_rank: int):
-    """Multi-GPU runs: pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned id buffers
-    are allocated (first touch puts them on that NUMA node), so that 8 ranks x 131 MB of ids per step do not
-    all cross one socket's memory controller / inter-socket link on their way to PCIe.  Best effort: returns
-    the CPU list it bound to, or None (NVML unavailable, mask too narrow, affinity not settable)."""
+    """Multi-GPU runs: pin this rank to the CPUs of the NUMA node its GPU hangs off BEFORE the pinned id buffers
+    are allocated (first touch puts them on that node), so that 8 ranks x 131 MB of ids per step do not all
+    cross one socket's memory controller / the inter-socket link on their way to PCIe.  The node comes from
+    sysfs (/sys/bus/pci/devices/<bdf>/numa_node), the CPU set from NVML's affinity mask as a fallback.  Best
+    effort: returns a short description of what it bound to, or None (no NUMA information, mask as wide as the
+    machine, affinity not settable)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -177,13 +179,31 @@ def bind_to_gpu_numa(local_rank: int):
                 return None
             idx = int(ent)
         handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
-        cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
-        if len(cpus) < 2:
+        allowed = os.sched_getaffinity(0)
+        cpus, how = set(), None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:         # NVML prints an 8-digit domain, sysfs a 4-digit one
+                bus = bus[4:]
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            if node >= 0:
+                for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                how = f"numa node {node}"
+        except Exception:
+            cpus = set()
+        if not cpus:
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+            cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1}
+            how = "nvml affinity"
+        cpus &= allowed
+        if len(cpus) < 2 or cpus == allowed:
             return None
         os.sched_setaffinity(0, cpus)
-        return sorted(cpus)
+        return f"{how}: {len(cpus)} of {len(allowed)} cpus"
     except Exception:
         return None
 
@@ -398,7 +418,7 @@ def run_b200(args):
             "module_path": module_path, "configs": configs, "sharded_cfg5": sharded,
             "clocks": clocks,
             "host": {"cpu_count": os.cpu_count(),
-                     "rank0_bound_to_gpu_local_cpus": None if numa_cpus is None else len(numa_cpus)},
+                     "rank0_bound_to": numa_cpus},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
