@@ -129,3 +129,43 @@ def test_sharded_module_peer_capacity_and_modes():
         RowWiseShardedEmbeddingBag(1000, 16, exchange="peer", comm=FakeComm(2, 0), peer_forward="sideways")
     with pytest.raises(N.NativeError):
         one.peer_group()                                              # built on the first forward only
+
+
+def test_round2_entry_points_validate_before_touching_the_gpu():
+    """Argument errors of the sequence window, the fused lookup sum, the sequence-mode / table-wise / fused-push
+    peer entry points are error codes + a message, not crashes (no GPU involved)."""
+    lib = N.load()
+    dummy = (C.c_int64 * 64)()
+    out2 = (C.c_int32 * 2)()
+    ws = (C.c_uint8 * 4096)()
+    assert lib.recemb_sequence_window_workspace_bytes(50) >= 51 * 4
+    assert lib.recemb_sequence_window(None, 0, 4, 16, 0, 2, 0, ws, 4096, out2, 0, None) == -1          # null data
+    assert lib.recemb_sequence_window(dummy, 2, 4, 16, 0, 2, 0, ws, 4096, out2, 0, None) == -1         # bad kind
+    assert lib.recemb_sequence_window(dummy, 0, 4, 16, 0, 2, 3, ws, 4096, out2, 0, None) == -1         # bad side
+    assert lib.recemb_sequence_window(dummy, 0, 4, 100_000, 0, 2, 0, ws, 4096, out2, 0, None) == -3    # too long
+    assert lib.recemb_sequence_window(dummy, 0, 4, 16, 0, 2, 0, ws, 8, out2, 0, None) == -1            # workspace
+    terms = (N.GatherTerm * 9)()
+    assert lib.recemb_multi_gather_add_fwd(None, terms, 9, 4, 64, N.F32, None, None, dummy, 0, None) == -1   # > 8 terms
+    assert lib.recemb_multi_gather_add_fwd(None, terms, 1, 4, 64, N.F32, None, None, dummy, 0, None) == -1   # null table
+    assert lib.recemb_multi_gather_add_fwd(None, terms, 0, 4, 3, N.F32, None, None, dummy, 0, None) == -3    # 12-byte row
+    assert lib.recemb_multi_gather_add_fwd(None, terms, 0, 4, 64, N.F32, dummy, None, dummy, 0, None) == -1  # mask, no row
+    g = N.PeerGroupStruct()
+    a = N.PeerArena()
+    lib.recemb_peer_arena_layout(2, 64, 16, 64, N.F32, C.byref(a))
+    assert a.off_gate > a.off_counts and a.off_inbox - a.off_gate >= 64 + 64 * 4 + 64 * 8
+    g.world, g.rank = 2, 0
+    hp = N.OptimParams()
+    # sequence mode needs an arena laid out with bags_total == cap
+    assert lib.recemb_peer_bucket_push_rows(C.byref(g), C.byref(a), dummy, 8, None, N.HASH_FLOORMOD, 100, 0, 0, 0,
+                                            dummy, ws, 4096, 0, None) == -1
+    assert b"bags_total == cap" in lib.recemb_last_error()
+    assert lib.recemb_peer_rows_scatter_push(C.byref(g), C.byref(a), dummy, 8, 64, N.F32, dummy, 0, None) == -1
+    assert lib.recemb_peer_pool_push_tablewise(C.byref(g), C.byref(a), 64, N.F32, 5, 0, None) == -1    # 16 % 5 != 0
+    for fn in (lib.recemb_peer_bwd_apply_fused, lib.recemb_peer_bwd_apply_fused_tablewise):
+        # tables x bags_per_table != bags_total
+        assert fn(C.byref(g), C.byref(a), dummy, 512, dummy, 3, 4, 64, N.F32, N.UPD_SGD, dummy, 300, 100, None,
+                  C.byref(hp), ws, 4096, 16, 0, None) == -1
+    # row-wise Adagrad / SGD on 256- or 512-byte rows only (elementwise Adagrad keeps push -> barrier -> update)
+    assert lib.recemb_peer_bwd_apply_fused(C.byref(g), C.byref(a), dummy, 512, dummy, 4, 4, 64, N.F32, N.UPD_ADAGRAD,
+                                           dummy, 400, 100, None, C.byref(hp), ws, 4096, 16, 0, None) in (-1, -3)
+    assert lib.recemb_peer_signal(C.byref(g), C.byref(a), 9, 0, None) == -1                           # channel
