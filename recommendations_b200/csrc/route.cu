@@ -180,12 +180,27 @@ __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const Bucket
   __shared__ uint32_t s_run[kMaxWorld];                       // running offset per owner
   __shared__ uint32_t s_wc[kRtThreads / 32][kMaxWorld];       // per-warp counts of this round
   __shared__ int64_t* s_dst[PEER ? RECEMB_MAX_PEERS : 1];     // PEER: my region of every owner's inbox
+  // PEER: the CTA's entries are first grouped by owner in shared memory and then copied out by consecutive
+  // threads -- contiguous runs of ~kRtBlock / world entries per owner leave as full-width NVLink writes instead
+  // of the 8-byte stores of the lanes that happen to share an owner (a handful of bytes per packet)
+  __shared__ int64_t s_stage[PEER ? kRtBlock : 1];
+  __shared__ uint32_t s_base0[PEER ? kMaxWorld : 1];          // the CTA's first position in owner o's bucket
+  __shared__ uint32_t s_lbase[PEER ? kMaxWorld + 1 : 1];      // first staging slot of owner o
   const uint32_t world = a.h.shard_world;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < world) s_run[threadIdx.x] = a.block_base[(int64_t)blockIdx.x * world + threadIdx.x];
   if constexpr (PEER) {
     if (threadIdx.x < RECEMB_MAX_PEERS) s_dst[threadIdx.x] = a.peer_inbox[threadIdx.x];
-  }  // both published by the first __syncthreads() of the loop
+    if (threadIdx.x < world) s_base0[threadIdx.x] = a.block_base[(int64_t)blockIdx.x * world + threadIdx.x];
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (uint32_t o = 0; o < world; ++o) {
+        s_lbase[o] = run;
+        run += a.block_hist[(int64_t)blockIdx.x * world + o];
+      }
+      s_lbase[world] = run;
+    }
+  }  // published by the first __syncthreads() of the loop
   const int64_t base = (int64_t)blockIdx.x * kRtBlock;
   for (int r = 0; r < kRtItems; ++r) {
     for (int i = threadIdx.x; i < (kRtThreads / 32) * kMaxWorld; i += kRtThreads) (&s_wc[0][0])[i] = 0;
@@ -206,10 +221,8 @@ __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const Bucket
       const uint32_t grow = a.dest ? a.seq_base + pos : a.bag_base + bag;  // gradient row at the owner
       const int64_t entry = (int64_t)(((uint64_t)a.rowbuf[s] << 32) | (uint64_t)grow);
       if constexpr (PEER) {
-        if (pos < a.cap) {
-          s_dst[owner][pos] = entry;  // store into the owner's HBM over NVLink
-          dest = (int64_t)(((uint64_t)owner << 32) | pos);
-        }
+        s_stage[s_lbase[owner] + (pos - s_base0[owner])] = entry;
+        if (pos < a.cap) dest = (int64_t)(((uint64_t)owner << 32) | pos);
       } else {
         a.entries[pos] = entry;
       }
@@ -222,6 +235,15 @@ __global__ void __launch_bounds__(kRtThreads) bucket_scatter_kernel(const Bucket
       s_run[threadIdx.x] += add;
     }
     __syncthreads();
+  }
+  if constexpr (PEER) {
+    const uint32_t total = s_lbase[world];
+    for (uint32_t i = threadIdx.x; i < total; i += kRtThreads) {
+      uint32_t o = 0;
+      while (i >= s_lbase[o + 1]) ++o;
+      const uint32_t pos = s_base0[o] + (i - s_lbase[o]);
+      if (pos < a.cap) s_dst[o][pos] = s_stage[i];  // into the owner's HBM over NVLink, consecutive threads ->
+    }                                                // consecutive inbox positions
   }
 }
 
@@ -316,6 +338,26 @@ struct PoolInboxArgs {
   int64_t bags_per_table;          // > 0: table-wise partitioning, only bags of tables t % world == rank are mine
 };
 
+// zero rows for the bags [k0, k1) of a sender's region that have no entry on this owner (table-wise
+// partitioning: only the bags of the tables this rank owns, skipping foreign tables a whole table at a time)
+__device__ __noinline__ void zero_gap_rows(uint4* out, uint32_t key_base, uint32_t k0, uint32_t k1, int vecs, int lig,
+                                           int64_t bags_per_table, int world, int rank) {
+  if (lig >= vecs) return;
+  if (bags_per_table > 0) {
+    uint32_t z = k0;
+    while (z != k1) {
+      const uint32_t t = (uint32_t)((z - key_base) / (uint32_t)bags_per_table);
+      const uint32_t t_end = key_base + (t + 1u) * (uint32_t)bags_per_table;
+      const uint32_t stop = (t_end - z) < (k1 - z) ? t_end : k1;
+      if ((int)(t % (uint32_t)world) == rank)
+        for (uint32_t y = z; y != stop; ++y) stg_v4(out + (size_t)(y - key_base) * vecs + lig, make_uint4(0, 0, 0, 0));
+      z = stop;
+    }
+    return;
+  }
+  for (uint32_t z = k0; z != k1; ++z) stg_v4(out + (size_t)(z - key_base) * vecs + lig, make_uint4(0, 0, 0, 0));
+}
+
 template <int G, typename T>
 __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const PoolInboxArgs a) {
   constexpr int E = Vec16<T>::kElems;
@@ -339,21 +381,10 @@ __global__ void __launch_bounds__(kRtThreads, 4) pool_inbox_push_kernel(const Po
   // Bags of this sender without an entry on this owner get a zero row from here as well (every row of
   // parts[rank] is written exactly once per step, the requester never zero-fills): the run that follows
   // a gap of bag numbers fills it, the last run of the region fills the tail.
+  // gaps are rare (a bag without an entry on this owner): the filler stays out of line so that the walk below
+  // keeps its registers and its instruction footprint
   auto zero_rows = [&](uint32_t k0, uint32_t k1) {  // keys [k0, k1)
-    if (lig >= a.vecs) return;
-    if (a.bags_per_table > 0) {  // table-wise: skip the bags of tables other ranks own, a whole table at a time
-      uint32_t z = k0;
-      while (z != k1) {
-        const uint32_t t = (uint32_t)((z - key_base) / (uint32_t)a.bags_per_table);
-        const uint32_t t_end = key_base + (t + 1u) * (uint32_t)a.bags_per_table;
-        const uint32_t stop = (t_end - z) < (k1 - z) ? t_end : k1;
-        if ((int)(t % (uint32_t)a.world) == a.rank)
-          for (uint32_t y = z; y != stop; ++y) stg_v4(out + (size_t)(y - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
-        z = stop;
-      }
-      return;
-    }
-    for (uint32_t z = k0; z != k1; ++z) stg_v4(out + (size_t)(z - key_base) * a.vecs + lig, make_uint4(0, 0, 0, 0));
+    if (k0 != k1) zero_gap_rows(out, key_base, k0, k1, a.vecs, lig, a.bags_per_table, a.world, a.rank);
   };
   if (n == 0) {
     if (chunk_local == 0) zero_rows(key_base, key_base + (uint32_t)a.bags_total);
