@@ -89,7 +89,9 @@ struct GatherArgs {
   int l1_rows;         // rows may stay in L1 (skewed ids: hot rows are re-read by every SM)
 };
 
-template <int G, int V, typename T, int EPI, bool TWO>
+// MAP: the output position is remapped (flipped sequences and / or a sequence window); the plain lookup
+// (MAP = false, the cfg 2 headline) carries none of that code or its registers
+template <int G, int V, typename T, int EPI, bool TWO, bool MAP = true>
 __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
   constexpr int RPW = 32 / G;                  // rows per warp pass
   constexpr int UNROLL = (V >= 4) ? 2 : (V == 2 ? 2 : 4);
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 
   IdStager st;
   st.init(s_ids[0], s_ids[1], s_bar, a.bulk_ok != 0);
-  const uint32_t keep = window_keep(a.h1);
+  const uint32_t keep = MAP ? window_keep(a.h1) : 0u;
 
   int64_t tile = blockIdx.x;
   int b = 0;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
       if (TWO) s_rows2[i] = pad ? -1 : row_of(id, a.h2);
       const int64_t r1 = pad ? -1 : row_of(id, a.h1);  // -1: pad position or out-of-range identity id
       int64_t r = r1 < 0 ? -1 : r1 + table_offset(tile * kTileIds + i, a.h1);
-      if (a.h1.win_len && out_row(tile * kTileIds + i, a.h1, keep) < 0) {
+      if (MAP && a.h1.win_len && out_row(tile * kTileIds + i, a.h1, keep) < 0) {
         r = -2;
         if (TWO) s_rows2[i] = -1;
       }
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
 #pragma unroll
               for (int e = 0; e < E; ++e) f[j][e] = f[j][e] / denom;
             if (a.inv_norm && l[u] < cnt && lig == 0) {
-              const int64_t o = out_row(tile * kTileIds + l[u], a.h1, keep);
+              const int64_t o = MAP ? out_row(tile * kTileIds + l[u], a.h1, keep) : tile * kTileIds + l[u];
               if (o >= 0) a.inv_norm[o] = 1.f / denom;
             }
           }
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const GatherArgs a) {
         }
         if (l[u] < cnt) {
           uint4* dst = out_tile + (int64_t)l[u] * a.row_vecs;
-          if (a.h1.flip_len | a.h1.win_len) {
+          if constexpr (MAP) {
             const int64_t o = out_row(tile * kTileIds + l[u], a.h1, keep);
             dst = o < 0 ? nullptr : a.out + o * a.row_vecs;
           }
@@ -607,7 +609,10 @@ template <typename T>
 static int launch_gather(const GatherArgs& a, RowShape shape, int epilogue, bool two, int64_t tiles,
                          int device, cudaStream_t s) {
   bool launched = false;
-  if (!two && epilogue == RECEMB_EPI_NONE) {
+  const bool map = (a.h1.flip_len | a.h1.win_len) != 0;
+  if (!two && epilogue == RECEMB_EPI_NONE && !map) {
+    DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_NONE, false, false>>(a, tiles, device, s)))
+  } else if (!two && epilogue == RECEMB_EPI_NONE) {
     DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_NONE, false>>(a, tiles, device, s)))
   } else if (!two) {
     DISPATCH_SHAPES((launch_persistent<gather_kernel<G, V, T, RECEMB_EPI_L2NORM, false>>(a, tiles, device, s)))
