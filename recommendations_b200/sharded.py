@@ -1109,15 +1109,49 @@ class TableWiseShardedEmbeddingBag(nn.Module):
         self._peer_dirty = True
 
     @torch.no_grad()
-    def gather_full_weight(self) -> torch.Tensor:
-        """Global [T, N, D] under the unsharded module's layout (collective)."""
+    def _gather_tables(self, local: torch.Tensor) -> torch.Tensor:
+        """[local_tables * N, ...] of every rank -> global [T, N, ...] (local table j of rank s = table j * W + s)."""
         w, t, n = self.comm.world, self.num_tables, self.num_embeddings
         lt_max = -(-t // w)
-        pad = torch.zeros((lt_max * n, self.emb_dim), dtype=self.emb.weight.dtype, device=self.emb.weight.device)
-        pad[: self.local_tables * n] = self.emb.weight.detach()
-        shards = self.comm.all_gather(pad).view(w, lt_max, n, self.emb_dim)
-        full = torch.empty((t, n, self.emb_dim), dtype=pad.dtype, device=pad.device)
+        tail = tuple(local.shape[1:])
+        pad = torch.zeros((lt_max * n,) + tail, dtype=local.dtype, device=local.device)
+        pad[: self.local_tables * n] = local
+        shards = self.comm.all_gather(pad).view((w, lt_max, n) + tail)
+        full = torch.empty((t, n) + tail, dtype=pad.dtype, device=pad.device)
         for s in range(w):
             cnt = (t - s + w - 1) // w
             full[s::w] = shards[s, :cnt]
         return full
+
+    @torch.no_grad()
+    def gather_full_weight(self) -> torch.Tensor:
+        """Global [T, N, D] under the unsharded module's layout (collective)."""
+        return self._gather_tables(self.emb.weight.detach())
+
+    @torch.no_grad()
+    def gather_full_optimizer_state(self) -> dict:
+        """Fused-optimizer state of the GLOBAL tables ([T, N] for row-wise Adagrad, [T, N, D] otherwise) + the step
+        count, as RowWiseShardedEmbeddingBag.gather_full_optimizer_state (collective)."""
+        if self.emb.fused is None:
+            raise N.NativeError("gather_full_optimizer_state needs the fused optimizer mode")
+        self.emb._ensure_state()
+        out = {"kind": self.emb.fused.kind, "step": self.emb.fused_step}
+        for name, key in (("opt_state1", "state1"), ("opt_state2", "state2")):
+            buf = self.emb._buffers.get(name)
+            out[key] = None if buf is None else self._gather_tables(buf)
+        return out
+
+    @torch.no_grad()
+    def load_full_optimizer_state(self, state: dict) -> None:
+        """Inverse of gather_full_optimizer_state: every rank keeps the tables it owns (resume on any world size)."""
+        if self.emb.fused is None or state["kind"] != self.emb.fused.kind:
+            raise N.NativeError("optimizer kind of the checkpoint does not match this module")
+        self.emb._ensure_state()
+        self.emb.fused_step = int(state["step"])
+        for name, key in (("opt_state1", "state1"), ("opt_state2", "state2")):
+            buf = self.emb._buffers.get(name)
+            if buf is None:
+                continue
+            full = state[key]
+            full = full.reshape((self.num_tables, self.num_embeddings) + tuple(full.shape[2:]))
+            buf.copy_(full[self.comm.rank::self.comm.world].reshape(buf.shape).to(buf.device, buf.dtype))

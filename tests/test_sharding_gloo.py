@@ -172,6 +172,20 @@ def _tablewise_worker(rank, world, port, result):
         assert torch.equal(mod.emb.weight.detach().view(mod.local_tables, n, d), full[rank::world])
         assert torch.equal(mod.gather_full_weight(), full)
         assert mod._owner_of_table.tolist() == [i % world for i in range(t)]
+        # fused-optimizer state: global layout out, owned tables back in
+        from recommendations_b200.table import FusedOptimizerConfig
+        for kind, shape in (("rowwise_adagrad", (t, n)), ("adam", (t, n, d))):
+            fm = TableWiseShardedEmbeddingBag(n, d, t, fused_optimizer=FusedOptimizerConfig(kind=kind))
+            glob = torch.arange(t * n, dtype=torch.float32).view(t, n)
+            glob = glob if len(shape) == 2 else glob.unsqueeze(2).expand(*shape).contiguous()
+            fm.load_full_optimizer_state({"kind": kind, "step": 7, "state1": glob,
+                                          "state2": glob * 2 if kind == "adam" else None})
+            assert fm.emb.fused_step == 7
+            assert torch.equal(fm.emb._buffers["opt_state1"].reshape((fm.local_tables,) + shape[1:]), glob[rank::world])
+            back = fm.gather_full_optimizer_state()
+            assert back["step"] == 7 and torch.equal(back["state1"], glob)
+            if kind == "adam":
+                assert torch.equal(back["state2"], glob * 2)
         result[rank] = 1
     finally:
         dist.destroy_process_group()
