@@ -166,8 +166,16 @@ def adagrad_step(w: torch.Tensor, g: torch.Tensor, state_sum: torch.Tensor, lr: 
 
 def rowwise_adagrad_step(w: torch.Tensor, g: torch.Tensor, touched: torch.Tensor,
                          state_row: torch.Tensor, lr: float, eps: float = 1e-10) -> None:
-    """Row-wise Adagrad (FBGEMM / SURVEY.md section 8d cfg 4 definition; no reference code):
-    s_r += mean_d(g_r^2); w_r -= lr * g_r / (sqrt(s_r) + eps), touched rows only."""
+    """Row-wise Adagrad (SURVEY.md section 8d cfg 4; the reference has no code for it, and fbgemm_gpu -- whose
+    EXACT_ROWWISE_ADAGRAD this is -- is neither a dependency of the reference nor installed here: PARITY UNPINNED,
+    the published algorithm is restated).  fbgemm_gpu's optimizer code generator (rowwise_adagrad in
+    codegen/genscript/optimizers.py) emits, per touched row of dimension D:
+        g_avg_square        = sum_d(g_d^2) / D
+        new_sum_square_grads = momentum1[row] + g_avg_square ;  momentum1[row] = new_sum_square_grads
+        multiplier           = learning_rate / (sqrtf(new_sum_square_grads) + eps)
+        weight_d            -= multiplier * g_d
+    i.e. s_r += mean_d(g_r^2); w_r -= lr * g_r / (sqrt(s_r) + eps), touched rows only (no weight decay / max-norm
+    variant here)."""
     gr = g[touched]
     s_new = state_row[touched] + (gr * gr).mean(dim=1)
     state_row[touched] = s_new
