@@ -86,47 +86,70 @@ struct PlanKeyArgs {
   uint32_t* vals;
 };
 
+// Slot indices fit 32 bits (the plan stores them as uint32), so the per-slot divisions (slot -> id, id -> bag)
+// are 32-bit; every thread handles kPlanUnroll slots per round with their id loads issued together (one
+// dependent 8-byte load per round was all the memory parallelism this kernel had: 2.4 TB/s).
+constexpr int kPlanUnroll = 4;
+
 __global__ void __launch_bounds__(kBwdThreads) plan_keys_kernel(const PlanKeyArgs a) {
   const uint32_t keep = window_keep(a.h);
-  int64_t s = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * kBwdThreads;
-  for (; s < a.n_slots; s += stride) {
-    int64_t id_idx = s;
-    int c = 0;
-    if (a.slots_per_id > 1) {
-      id_idx = s / a.slots_per_id;
-      c = (int)(s - id_idx * a.slots_per_id);
-    }
-    const int64_t id = a.ids[id_idx];
-    bool ok = !(a.zero_pad && id == a.pad_id);
-    if (ok && a.bag_size > 0) {
-      const int64_t bag = id_idx / a.bag_size;
-      const int p = (int)(id_idx - bag * a.bag_size);
-      int hi = a.bag_size;
-      if (a.lengths) hi = min(max(a.lengths[bag], 0), a.bag_size);
-      const int lo = a.last_n > 0 ? max(0, hi - a.last_n) : 0;
-      ok = p >= lo && p < hi;
-    }
-    // the slot's gradient row: mirrored inside its sequence when the forward wrote flipped outputs, compacted
-    // to the sequence window (slots outside it carry nothing)
-    const int64_t orow = (a.h.flip_len | a.h.win_len) ? out_row(id_idx, a.h, keep) : id_idx;
-    ok = ok && orow >= 0;
-    uint32_t key = a.sentinel;
-    if (ok) {
-      int64_t row = a.slots_per_id > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
-      if (row != a.pad_row) {
-        row = shard_local_row(row, a.h);  // -1: another rank owns this row
-        if (row >= 0) key = (uint32_t)(row + table_offset(id_idx, a.h));
+  const uint32_t n = (uint32_t)a.n_slots;
+  const uint32_t spi = (uint32_t)a.slots_per_id, bsz = (uint32_t)a.bag_size;
+  const bool remap = (a.h.flip_len | a.h.win_len) != 0;
+  const uint64_t round = (uint64_t)gridDim.x * kBwdThreads * kPlanUnroll;
+  for (uint64_t s0 = (uint64_t)blockIdx.x * kBwdThreads * kPlanUnroll + threadIdx.x; s0 < n; s0 += round) {
+    uint32_t idx[kPlanUnroll];
+    int64_t idv[kPlanUnroll];
+#pragma unroll
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const uint64_t s = s0 + (uint64_t)u * kBwdThreads;
+      idx[u] = 0;
+      idv[u] = 0;
+      if (s < n) {
+        idx[u] = spi > 1 ? (uint32_t)s / spi : (uint32_t)s;
+        idv[u] = a.ids[idx[u]];
       }
     }
-    a.keys[s] = key;
-    if (a.h.out_feats && a.bag_size > 0) {
-      // pooled bags whose gradient arrives feature-interleaved ([bags_per_table, F, dim], the interaction's
-      // backward): slot -> (gradient row of its bag) * bag_size + position
-      const int64_t bag = id_idx / a.bag_size;
-      a.vals[s] = (uint32_t)(bag_out_row(bag, a.h) * a.bag_size + (id_idx - bag * a.bag_size));
-    } else {
-      a.vals[s] = (a.h.flip_len | a.h.win_len) ? (uint32_t)(max(orow, (int64_t)0) * a.slots_per_id + c) : (uint32_t)s;
+#pragma unroll
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const uint64_t s64 = s0 + (uint64_t)u * kBwdThreads;
+      if (s64 >= n) continue;
+      const uint32_t s = (uint32_t)s64;
+      const uint32_t id_idx = idx[u];
+      const int c = spi > 1 ? (int)(s - id_idx * spi) : 0;
+      const int64_t id = idv[u];
+      bool ok = !(a.zero_pad && id == a.pad_id);
+      uint32_t bag = 0, p = 0;
+      if (bsz > 0) {
+        bag = id_idx / bsz;
+        p = id_idx - bag * bsz;
+        if (ok) {
+          int hi = (int)bsz;
+          if (a.lengths) hi = min(max(a.lengths[bag], 0), (int)bsz);
+          const int lo = a.last_n > 0 ? max(0, hi - a.last_n) : 0;
+          ok = (int)p >= lo && (int)p < hi;
+        }
+      }
+      // the slot's gradient row: mirrored inside its sequence when the forward wrote flipped outputs, compacted
+      // to the sequence window (slots outside it carry nothing)
+      const int64_t orow = remap ? out_row((int64_t)id_idx, a.h, keep) : (int64_t)id_idx;
+      ok = ok && orow >= 0;
+      uint32_t key = a.sentinel;
+      if (ok) {
+        int64_t row = spi > 1 ? kshift_row(id, c, a.h.mod_rows) : row_of(id, a.h);
+        if (row != a.pad_row) {
+          row = shard_local_row(row, a.h);  // -1: another rank owns this row
+          if (row >= 0) key = (uint32_t)(row + table_offset((int64_t)id_idx, a.h));
+        }
+      }
+      a.keys[s] = key;
+      if (a.h.out_feats && bsz > 0) {
+        // pooled bags whose gradient arrives feature-interleaved ([bags_per_table, F, dim], the interaction's
+        // backward): slot -> (gradient row of its bag) * bag_size + position
+        a.vals[s] = (uint32_t)(bag_out_row((int64_t)bag, a.h) * bsz + p);
+      } else {
+        a.vals[s] = remap ? (uint32_t)(max(orow, (int64_t)0) * spi + c) : s;
+      }
     }
   }
 }
@@ -1273,7 +1296,7 @@ extern "C" int recemb_bwd_plan(const int64_t* ids, int64_t n_ids, const recemb_l
   a.keys = (uint32_t*)(base + (start_in_out ? L.off_keys_out : L.off_keys_in));
   a.vals = (uint32_t*)(base + (start_in_out ? L.off_vals_out : L.off_vals_in));
   const int sms = sm_count(device);
-  int64_t grid = (n + kBwdThreads - 1) / kBwdThreads;
+  int64_t grid = (n + (int64_t)kBwdThreads * kPlanUnroll - 1) / ((int64_t)kBwdThreads * kPlanUnroll);
   if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
   plan_keys_kernel<<<(unsigned)grid, kBwdThreads, 0, s>>>(a);
   RECEMB_LAUNCHED();
