@@ -267,6 +267,7 @@ struct SegArgs {
   int32_t chunk;          // consecutive entries per group (level 0: wave-fitted, >= kChunk0)
   int32_t pf_bulk;        // level 0 fast path: rows prefetched with one bulk L2 prefetch per row
   PeerGate gate;          // seg_pre_kernel, sharded backward: fused gradient push + per-table gating
+  int32_t* chunk_used;    // HOST pointer (never read on the device): the level-0 chunk length the launch chose
 };
 
 // ---- fused gradient push (sharded backward) ---------------------------------------------------
@@ -995,8 +996,6 @@ static bool pick_quads(int quads, QuadShape* s) {
 constexpr int kChunk0 = RECEMB_CHUNK0;  // sorted entries per group at level 0
 constexpr int kChunkN = 32;             // records per group at levels >= 1
 
-// chunk size the last level-0 launch of this thread used (the host sizes level 1 from it)
-static thread_local int t_chunk_used = 0;
 static int env_flag(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -1032,7 +1031,7 @@ static void launch_kernel(const SegArgs& a_in, cudaStream_t s) {
       const int64_t c = slots > 0 ? ((int64_t)a.n + slots - 1) / slots : 0;
       if (c > CH && c <= 2 * CH) a.chunk = (int32_t)c;
     }
-    t_chunk_used = a.chunk;
+    if (a.chunk_used) *a.chunk_used = a.chunk;  // the host sizes level 1 from it
   }
   const int chunks = (a.n + a.chunk - 1) / a.chunk;
   kernel<<<(unsigned)((chunks + groups - 1) / groups + a.gate.push_ctas), kBwdThreads, 0, s>>>(a);
@@ -1552,6 +1551,8 @@ static int apply_impl(const void* plan, size_t plan_bytes, int64_t n_slots, cons
   a.chunk = kChunk0;
   a.guard = skip_if_nonzero;
   a.gate.push_ctas = 0;
+  int32_t chunk_used = kChunk0;  // per call, no state carried between calls or threads
+  a.chunk_used = &chunk_used;
   {
     static const int pf = env_flag("RECEMB_SEG_PF_BULK", 0);
     a.pf_bulk = pf;
@@ -1594,10 +1595,10 @@ static int apply_impl(const void* plan, size_t plan_bytes, int64_t n_slots, cons
     if (l == 0 && t_ev_stop) cudaEventRecord(t_ev_stop, s);
     if (l == 0) t_ev_start = t_ev_stop = nullptr;
     if (rc) return rc;
-    if (l == 0 && t_chunk_used > kChunk0) {
+    if (l == 0 && chunk_used > kChunk0) {
       // level 0 used longer chunks: fewer records than the (upper-bound) layout reserves;
       // the levels above shrink accordingly (offsets stay inside the reserved areas)
-      sizes[1] = 2 * ((n + t_chunk_used - 1) / t_chunk_used);
+      sizes[1] = 2 * ((n + chunk_used - 1) / chunk_used);
       int64_t m = sizes[1];
       int LL = 2;
       while (m > kChunkN && LL < kMaxLevels) {
