@@ -144,38 +144,59 @@ struct MultiGatherArgs {
   uint4* out;
 };
 
+// Two phases per round of 256 positions: (1) thread t hashes ALL terms of position t once (a 64-bit
+// divide-by-constant each; done by every lane of a row group it cost 16x the instructions and the kernel sat at
+// 64 % issue-active with DRAM at 31 %) and leaves the rows in shared memory; (2) groups of G lanes move the rows.
 template <int G, typename T>
 __global__ void __launch_bounds__(kSeqThreads) multi_gather_add_kernel(const MultiGatherArgs a) {
   constexpr int E = Vec16<T>::kElems;
-  const int lig = threadIdx.x % G;
-  int64_t i = (int64_t)blockIdx.x * (kSeqThreads / G) + threadIdx.x / G;
-  const int64_t stride = (int64_t)gridDim.x * (kSeqThreads / G);
-  for (; i < a.n; i += stride) {
-    if (lig >= a.vecs) continue;
-    if (a.mask && a.mask[i]) {
-      stg_cs_v4(a.out + i * a.vecs + lig, ldg_nc_l1_v4(a.masked_row + lig));
-      continue;
-    }
-    float acc[E];
-    if (a.base) {
-      Vec16<T>::unpack(ldg_nc_v4(a.base + i * a.vecs + lig), acc);
-    } else {
+  constexpr int GROUPS = kSeqThreads / G;
+  __shared__ int32_t s_row[kMaxTerms][kSeqThreads];
+  __shared__ uint8_t s_masked[kSeqThreads];
+  const int lig = threadIdx.x % G, grp = threadIdx.x / G;
+  for (int64_t base = (int64_t)blockIdx.x * kSeqThreads; base < a.n; base += (int64_t)gridDim.x * kSeqThreads) {
+    const int64_t i = base + threadIdx.x;
+    if (i < a.n) {
+      const bool m = a.mask && a.mask[i];
+      s_masked[threadIdx.x] = m;
 #pragma unroll
-      for (int e = 0; e < E; ++e) acc[e] = 0.f;
+      for (int k = 0; k < kMaxTerms; ++k)
+        if (k < a.num_terms) s_row[k][threadIdx.x] = m ? -1 : (int32_t)row_of(a.ids[k][i], a.h[k]);
     }
-    for (int k = 0; k < a.num_terms; ++k) {
-      const int64_t row = row_of(a.ids[k][i], a.h[k]);
-      if (row < 0) continue;  // out-of-range identity id: contributes nothing
-      float f[E];
-      Vec16<T>::unpack(ldg_nc_l1_v4(a.table[k] + row * a.vecs + lig), f);
+    __syncthreads();
+    const int cnt = (int)min((int64_t)kSeqThreads, a.n - base);
+    if (lig < a.vecs) {
+      for (int p = grp; p < cnt; p += GROUPS) {
+        uint4* dst = a.out + (base + p) * a.vecs + lig;
+        if (s_masked[p]) {
+          stg_cs_v4(dst, ldg_nc_l1_v4(a.masked_row + lig));
+          continue;
+        }
+        float acc[E];
+        if (a.base) {
+          Vec16<T>::unpack(ldg_nc_v4(a.base + (base + p) * a.vecs + lig), acc);
+        } else {
 #pragma unroll
-      for (int e = 0; e < E; ++e) acc[e] += f[e];
-      if (sizeof(T) == 2) {  // every add of the reference rounds to the tensor dtype
-        uint4 t = Vec16<T>::pack(acc);
-        Vec16<T>::unpack(t, acc);
+          for (int e = 0; e < E; ++e) acc[e] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxTerms; ++k) {
+          if (k >= a.num_terms) break;
+          const int32_t row = s_row[k][p];
+          if (row < 0) continue;  // out-of-range identity id: contributes nothing
+          float f[E];
+          Vec16<T>::unpack(ldg_nc_l1_v4(a.table[k] + (int64_t)row * a.vecs + lig), f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] += f[e];
+          if (sizeof(T) == 2) {  // every add of the reference rounds to the tensor dtype
+            uint4 t = Vec16<T>::pack(acc);
+            Vec16<T>::unpack(t, acc);
+          }
+        }
+        stg_cs_v4(dst, Vec16<T>::pack(acc));
       }
     }
-    stg_cs_v4(a.out + i * a.vecs + lig, Vec16<T>::pack(acc));
+    __syncthreads();  // the rows of this round are consumed before the next round overwrites them
   }
 }
 
@@ -209,6 +230,8 @@ extern "C" int recemb_multi_gather_add_fwd(const void* base, const recemb_gather
   for (int k = 0; k < num_terms; ++k) {
     RECEMB_CHECK_ARG(terms_host[k].table && terms_host[k].ids && (uintptr_t)terms_host[k].table % 16 == 0,
                      "term %d: null / misaligned table or ids", k);
+    RECEMB_UNSUPPORTED(terms_host[k].num_rows >= 1 && terms_host[k].num_rows < 0x7fffffffll,
+                       "term %d: num_rows outside [1, 2^31)", k);
     a.table[k] = (const uint4*)terms_host[k].table;
     a.ids[k] = terms_host[k].ids;
     int rc = make_hash_spec(terms_host[k].hash_mode, terms_host[k].num_rows, terms_host[k].hash_arg, &a.h[k]);
@@ -221,8 +244,7 @@ extern "C" int recemb_multi_gather_add_fwd(const void* base, const recemb_gather
   cudaStream_t s = (cudaStream_t)stream;
 #define MGA(G_)                                                                                   \
   if (G == G_) {                                                                                  \
-    const int64_t per = kSeqThreads / G_;                                                         \
-    int64_t grid = (n + per - 1) / per;                                                           \
+    int64_t grid = (n + kSeqThreads - 1) / kSeqThreads;                                           \
     const int64_t cap_grid = (int64_t)sm_count(device) * 16;                                      \
     if (grid > cap_grid) grid = cap_grid;                                                         \
     if (dtype == RECEMB_F32) multi_gather_add_kernel<G_, float><<<(unsigned)grid, kSeqThreads, 0, s>>>(a);       \

@@ -227,8 +227,11 @@ def front_end():
                                     base + mods[0](labels) + mods[1](ts) + mods[2](ts) + mods[3](ts))
         assert torch.equal(fused(), chain())
         ms_f, ms_c = timeit(fused), timeit(chain)
+    unmasked = int((~mask).sum())
+    # one write per position, one read of the dense term per UNMASKED position, labels + timestamps + mask
     report("front end: QueryTower input sum (4 tiny-table lookups + dense term + pad select) as one kernel", ms_f,
-           b * l * (2 * r + 16 + 1), b * l * 4, ms_chain_of_lookups_and_adds=round(ms_c, 4))
+           b * l * (r + 16 + 1) + unmasked * r, unmasked * 4, ms_chain_of_lookups_and_adds=round(ms_c, 4),
+           unmasked_share=round(unmasked / (b * l), 3))
 
 
 RUNNERS = {"kshift": kshift_series, "cfg3": cfg3, "cfg4": cfg4, "cfg2plan": cfg2_plan, "frontend": front_end}
