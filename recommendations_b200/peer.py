@@ -178,7 +178,7 @@ class PeerGroup:
                 "peer exchange: an owner's inbox overflowed (entries were dropped, the last update is incomplete); "
                 "raise capacity_factor -- the ids are more skewed across ranks than the inbox allows")
         if st & STATUS_BARRIER_TIMEOUT:
-            raise N.NativeError("peer exchange: device barrier timed out (a rank did not reach it within ~2 s)")
+            raise N.NativeError("peer exchange: a device barrier or gradient gate timed out (a rank did not reach it within RECEMB_PEER_BARRIER_TIMEOUT_S, default 600 s); the update of that step was skipped")
 
     def table_ptrs(self) -> List[int]:
         return [int(self.struct.table[i] or 0) for i in range(self.world)]
