@@ -169,3 +169,36 @@ def test_round2_entry_points_validate_before_touching_the_gpu():
     assert lib.recemb_peer_bwd_apply_fused(C.byref(g), C.byref(a), dummy, 512, dummy, 4, 4, 64, N.F32, N.UPD_ADAGRAD,
                                            dummy, 400, 100, None, C.byref(hp), ws, 4096, 16, 0, None) in (-1, -3)
     assert lib.recemb_peer_signal(C.byref(g), C.byref(a), 9, 0, None) == -1                           # channel
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the header's structs (recemb_layout, recemb_optim_params, recemb_peer_group,
+    recemb_peer_arena, recemb_gather_term) have the size and field offsets a C compiler gives the header."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {
+        "recemb_layout": N.Layout, "recemb_optim_params": N.OptimParams, "recemb_peer_group": N.PeerGroupStruct,
+        "recemb_peer_arena": N.PeerArena, "recemb_gather_term": N.GatherTerm,
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "recemb_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, val = line.split()
+        cls = structs[cname]
+        want = C.sizeof(cls) if what == "size" else getattr(cls, what).offset
+        assert int(val) == want, line
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
