@@ -202,3 +202,20 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(val) == want, line
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_prototype_arity_matches_the_ctypes_signatures():
+    """Every RECEMB_API prototype has as many parameters as its ctypes argtypes list, and pointer / scalar
+    parameters line up (a pointer in the header is a c_void_p / POINTER / array there)."""
+    header = re.sub(r"/\*.*?\*/", " ", HEADER, flags=re.S)          # comments may contain commas
+    protos = re.findall(r"RECEMB_API\s+[\w\s\*]+?\b(recemb_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(N.SIGNATURES)
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        _, argtypes = N.SIGNATURES[name]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        for p, t in zip(plist, argtypes):
+            is_ptr_c = "*" in p or "[" in p or "recemb_stream_t" in p
+            is_ptr_py = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or hasattr(t, "_length_")
+            assert is_ptr_c == is_ptr_py, (name, p, t)
